@@ -1,0 +1,227 @@
+/*
+ * jobshoplab_b200 -- C ABI of the B200-native batched JobShopLab env-step path.
+ *
+ * Every entry point replaces a seam of the (pure Python) reference; the reference
+ * file:line each one stands in for is cited next to it.  Plain pointers and sizes only,
+ * no torch types.  Conventions: return 0 on success / negative JSL_E_* code, never throw
+ * across the ABI; the caller owns every buffer; device work is asynchronous on the
+ * stream passed in (a cudaStream_t cast to void*; NULL = legacy default stream); no host
+ * sync inside jsl_step / jsl_rollout.  One stream at a time per jsl_batch_t.
+ *
+ * The same POD descriptor structs are consumed by the CPU oracle (oracle/jsl_oracle.c),
+ * which is TEST INFRASTRUCTURE and is never linked into or called by this library.
+ */
+#ifndef JOBSHOPLAB_B200_H
+#define JOBSHOPLAB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JSL_ABI_VERSION 1
+
+/* buffer types -- jobshoplab/types/instance_config_types.py:30-36 (BufferTypeConfig) */
+#define JSL_BUF_FIFO 0
+#define JSL_BUF_LIFO 1
+#define JSL_BUF_DUMMY 2
+#define JSL_BUF_FLEX 3
+/* buffer roles -- instance_config_types.py:147-158 (BufferRoleConfig) */
+#define JSL_ROLE_INPUT 0
+#define JSL_ROLE_OUTPUT 1
+#define JSL_ROLE_COMPONENT 2
+#define JSL_ROLE_COMPENSATION 3
+/* time behaviours -- jobshoplab/types/stochasticy_models.py:44-121, mapper.py:661-695 */
+#define JSL_TIME_STATIC 0
+#define JSL_TIME_POISSON 1
+#define JSL_TIME_UNIFORM 2
+#define JSL_TIME_GAUSSIAN 3
+#define JSL_TIME_GAMMA 4
+/* "no capacity limit" (reference: sys.maxsize) and "no entry in the mapping" */
+#define JSL_CAP_INF 0x7fffffff
+#define JSL_NO_TIME (-1)
+
+/* machine states -- types/state_types.py:167-175 ; transport states :178-188 */
+#define JSL_M_IDLE 0
+#define JSL_M_SETUP 1
+#define JSL_M_WORKING 2
+#define JSL_M_OUTAGE 3
+#define JSL_T_IDLE 0
+#define JSL_T_WORKING 1
+#define JSL_T_PICKUP 2
+#define JSL_T_TRANSIT 3
+#define JSL_T_OUTAGE 4
+#define JSL_T_WAITINGPICKUP 5
+
+/* Per-env status: the reference's exceptions / outcomes as data. */
+#define JSL_ST_OK 0
+#define JSL_ST_DONE 1                /* terminated: all jobs in an output buffer (core_utils.py:44) */
+#define JSL_ST_TRUNCATED 2           /* truncation joker < 0 (middleware.py:433) */
+#define JSL_ST_STEP_FAILED 3         /* StateMachineResult.success == False (state.py:202-210) -> truncated */
+#define JSL_ST_BUFFER_FULL 4         /* BufferFullError (buffer_type_utils.py:90) */
+#define JSL_ST_UNSUCCESSFUL 5        /* UnsuccessfulStateMachineResult (middleware.py:330,344) */
+#define JSL_ST_NO_POSSIBLE 6         /* InvalidValue "No possible transitions" (actions.py:141) */
+#define JSL_ST_ENV_DONE 7            /* EnvDone: step() after done (env.py:441) */
+#define JSL_ST_ACTION_OUT_OF_SPACE 8 /* ActionOutOfActionSpace (actions.py:148) */
+#define JSL_ST_OTHER_INVALID 9       /* any other raise (missing travel/setup time, not-implemented branch) */
+
+/* error codes */
+#define JSL_OK 0
+#define JSL_E_INVALID (-1)
+#define JSL_E_UNSUPPORTED (-2)
+#define JSL_E_CUDA (-3)
+#define JSL_E_NOMEM (-4)
+
+/* policies for jsl_rollout -- jobshoplab/utils/dipatching_benchmark.py:17-67 */
+#define JSL_POLICY_FIFO 0   /* always accept */
+#define JSL_POLICY_SPT 1    /* dispatch_rules_uitls.py:57-79 */
+#define JSL_POLICY_MWKR 2   /* dispatch_rules_uitls.py:82-111 ("srpt": least TOTAL job work) */
+#define JSL_POLICY_RANDOM 3 /* Philox4x32-10(key=seed, ctr=(step,0,env_lo,env_hi)).x & 1 */
+#define JSL_POLICY_TAPE 4   /* actions read from a u8 tape [B][tape_stride] */
+
+/* observation kinds -- jobshoplab/env/factories/observations.py */
+#define JSL_OBS_NONE 0
+#define JSL_OBS_BINARY_ACTION 1 /* BinaryActionObservationFactory :488-551 (default) */
+#define JSL_OBS_OPERATION_ARRAY 2 /* BinaryOperationArrayObservation :631-693 */
+
+/*
+ * Lowered instance: what jobshoplab.compiler (compiler.py:84, mapper.py:1201,1387) produces,
+ * as structure-of-arrays int32.  Index spaces:
+ *   buffer idx : pre(m)=3m, post(m)=3m+1, machine buffer(m)=3m+2, agv(t)=3M+t, standalone s=3M+T+s
+ *   place      : machine m -> m, standalone buffer s -> M+s          (travel matrix axis)
+ *   time object: every DeterministicTimeConfig|StochasticTimeConfig of the instance; *_kind/_param
+ *                arrays are NULL for a fully deterministic instance.
+ */
+/* Time behaviour of a family of time objects.  All three NULL = static (deterministic).
+ * kind: JSL_TIME_*; base: base_time; param: offset (uniform) / std (gaussian) / scale (gamma). */
+typedef struct jsl_time_spec {
+    const int32_t* kind;
+    const int32_t* base;
+    const float* param;
+} jsl_time_spec;
+
+typedef struct jsl_instance_desc {
+    int32_t abi_version;
+    int32_t n_jobs, n_machines, n_transports, n_sbuf, n_tools, n_ops;
+    const int32_t* job_op_start; /* [J+1] ragged op offsets */
+    const int32_t* op_machine;   /* [N] */
+    const int32_t* op_tool;      /* [N] */
+    const int32_t* op_duration;  /* [N] duration.time at compile time */
+    const int32_t* pre_type;     /* [M] JSL_BUF_* */
+    const int32_t* pre_cap;      /* [M] */
+    const int32_t* post_type;    /* [M] */
+    const int32_t* post_cap;     /* [M] */
+    const int32_t* setup_time;   /* [M*nt*nt] (old tool, new tool) .time; JSL_NO_TIME = missing */
+    int32_t default_tool;        /* index of "tl-0" (mapper.py:396) */
+    const int32_t* sbuf_type;    /* [S] */
+    const int32_t* sbuf_cap;     /* [S] */
+    const int32_t* sbuf_role;    /* [S] JSL_ROLE_* */
+    const int32_t* buf_ref_id;   /* [3M+T+S] numeric part of the reference's "b-<k>" id per buffer idx */
+    const int32_t* travel_time;  /* [(M+S)^2] row=from place, col=to place, .time; JSL_NO_TIME = missing */
+    const int32_t* agv_init_place; /* [T] */
+    const int32_t* job_init_buf; /* [J] buffer idx */
+    int32_t start_time;
+    /* outages (mapper.py:989-1008): machine outages per machine, transport outages shared by all AGVs */
+    const int32_t* m_outage_start; /* [M+1] offsets into the m_outage_* arrays */
+    const int32_t* m_outage_freq;  /* [n] frequency.time */
+    const int32_t* m_outage_dur;   /* [n] duration.time */
+    int32_t n_t_outages;
+    const int32_t* t_outage_freq;  /* [n_t_outages] */
+    const int32_t* t_outage_dur;   /* [n_t_outages] */
+    /* stochastic behaviour of each family (index-aligned with the arrays above) */
+    jsl_time_spec op_spec, setup_spec, travel_spec, m_ofreq_spec, m_odur_spec, t_ofreq_spec, t_odur_spec;
+    /* constants computed once on the host (utils.py:310-352) */
+    int32_t lower_bound;
+    int32_t max_allowed_time;
+} jsl_instance_desc;
+
+/* Behavioural configuration: state_machine / middleware / reward_factory groups of
+ * jobshoplab/types/config_types.py:135-145 that reach the step path. */
+typedef struct jsl_env_cfg {
+    int32_t allow_early_transport; /* state.py:325, default 1 */
+    int32_t truncation_joker;      /* middleware.py:260, default 5 */
+    int32_t truncation_active;     /* middleware.py:262, default 0 */
+    int32_t obs_kind;              /* JSL_OBS_* */
+    double sparse_bias;            /* rewards.py:90-153, defaults 1.0 / 0.001 / -1.0 */
+    double dense_bias;
+    double truncation_bias;
+    int32_t record_ops;            /* keep per-op (start,end) log for render()/history (8(f)1) */
+    int32_t reserved;
+} jsl_env_cfg;
+
+typedef struct jsl_instance jsl_instance_t;
+typedef struct jsl_batch jsl_batch_t;
+
+/* Sizes (bytes / elements) a caller needs to allocate step outputs. */
+typedef struct jsl_shape {
+    int32_t n_jobs, n_machines, n_transports, n_sbuf, n_ops, n_tools;
+    int32_t obs_bytes;     /* packed observation record per env */
+    int32_t state_bytes;   /* HBM bytes of one env's mutable state */
+    int32_t digest_cap;    /* upper bound on jsl_get_state digest length (int32 elements) */
+} jsl_shape;
+
+/* Device output pointers of one jsl_step; any pointer may be NULL (= not wanted). */
+typedef struct jsl_step_out {
+    uint8_t* obs;        /* [B][obs_bytes]   ObservationFactory.make (observations.py:515) */
+    double* reward;      /* [B]              RewardFactory.make (rewards.py:145) */
+    uint8_t* terminated; /* [B]              env.py:446 */
+    uint8_t* truncated;  /* [B]              env.py:447-450 */
+    uint8_t* status;     /* [B]              JSL_ST_* */
+    int32_t* time;       /* [B]              state.time.time */
+    int32_t* makespan;   /* [B]              info["makespan"] (time if terminated else -1), env.py:404 */
+    int16_t* cand;       /* [B][4]           next possible_transitions[0]: kind(0 m/1 t), comp, job, n_remaining */
+} jsl_step_out;
+
+/* Device output pointers of one jsl_rollout; any may be NULL. */
+typedef struct jsl_rollout_out {
+    int32_t* makespan;   /* [B] final state.time.time */
+    int32_t* n_steps;    /* [B] env.step calls made */
+    double* ret;         /* [B] sum of rewards */
+    uint8_t* status;     /* [B] JSL_ST_* at the end */
+    int32_t* no_op_count;/* [B] info["no_op_count"] */
+} jsl_rollout_out;
+
+const char* jsl_last_error(void);
+int jsl_abi_version(void);
+
+/* Compiler.compile() result -> device-ready instance (compiler.py:84-106).  Host arrays are
+ * copied; returns NULL (+ jsl_last_error) on failure. */
+jsl_instance_t* jsl_instance_create(const jsl_instance_desc* d);
+void jsl_instance_destroy(jsl_instance_t*);
+
+/* B envs over n_inst same-shaped instances (env b uses instance b % n_inst), on CUDA device
+ * `device`.  Replaces JobShopLabEnv.__init__ wiring (env.py:388-402) for a whole batch. */
+jsl_batch_t* jsl_batch_create(jsl_instance_t* const* insts, int n_inst, int64_t B, int device,
+                              uint64_t seed, const jsl_env_cfg* cfg);
+void jsl_batch_destroy(jsl_batch_t*);
+int jsl_batch_shape(const jsl_batch_t*, jsl_shape* out);
+
+/* env.reset (env.py:456-545) + middleware.reset (middleware.py:264-290) for every env whose
+ * reset_mask byte is non-zero (NULL = all).  Writes the first observation / candidate to `out`. */
+int jsl_reset(jsl_batch_t*, const uint8_t* reset_mask /*dev [B], nullable*/, jsl_step_out out, void* stream);
+
+/* env.step (env.py:427-454) for all B envs: actions dev u8[B] in {0,1}. */
+int jsl_step(jsl_batch_t*, const uint8_t* actions, jsl_step_out out, void* stream);
+
+/* `while not env.done: env.step(policy(env))` fused on device (dipatching_benchmark.py:131-137).
+ * Runs at most max_steps further env.steps per env from the CURRENT state (call jsl_reset first).
+ * action_tape: dev u8 [B][tape_stride] for JSL_POLICY_TAPE, else NULL. */
+int jsl_rollout(jsl_batch_t*, int policy, const uint8_t* action_tape, int64_t tape_stride,
+                int max_steps, jsl_rollout_out out, void* stream);
+
+/* Canonical int32 digest of env `idx` (state + possible transitions; layout in DESIGN.md),
+ * copied to host: parity tests, render(), history reconstruction.  Synchronises.
+ * Returns the number of int32 written (<= cap) or a negative error. */
+int jsl_get_state(jsl_batch_t*, int64_t idx, int32_t* host_out, int cap);
+
+/* Per-op (start,end) log of env idx, host int32 [n_ops][2]; needs cfg.record_ops. */
+int jsl_get_op_log(jsl_batch_t*, int64_t idx, int32_t* host_out);
+
+/* How many kernels this batch has launched so far (bench.py "gpu_launches"). */
+int64_t jsl_launch_count(const jsl_batch_t*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JOBSHOPLAB_B200_H */
