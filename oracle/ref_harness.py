@@ -162,14 +162,11 @@ def make_env(kind: str, src, seed=None, **cfg_over) -> JobShopLabEnv:
 
 
 def tool_list(instance) -> list[str]:
+    """Tools the state machine can ever mount: "tl-0" plus every operation's tool, sorted."""
     tools = {"tl-0"}
     for job in instance.instance.specification:
         for op in job.operations:
             tools.add(op.tool)
-    for m in instance.machines:
-        for a, b in m.setup_times.keys():
-            tools.add(a)
-            tools.add(b)
     return sorted(tools)
 
 
