@@ -194,8 +194,18 @@ void jsl_instance_destroy(jsl_instance_t*);
  * `device`.  Replaces JobShopLabEnv.__init__ wiring (env.py:388-402) for a whole batch. */
 jsl_batch_t* jsl_batch_create(jsl_instance_t* const* insts, int n_inst, int64_t B, int device,
                               uint64_t seed, const jsl_env_cfg* cfg);
+/* Synthetic same-shape batches: n_inst variants of `tmpl` that differ only in
+ * the operation tables.  op_machine / op_duration: host int32 [n_inst][n_ops]; lower_bound /
+ * max_allowed_time: host int32 [n_inst] (utils.py:310-352, computed by the caller). */
+jsl_batch_t* jsl_batch_create_variants(const jsl_instance_t* tmpl, int64_t n_inst, const int32_t* op_machine,
+                                       const int32_t* op_duration, const int32_t* lower_bound,
+                                       const int32_t* max_allowed_time, int64_t B, int device, uint64_t seed,
+                                       const jsl_env_cfg* cfg);
 void jsl_batch_destroy(jsl_batch_t*);
 int jsl_batch_shape(const jsl_batch_t*, jsl_shape* out);
+/* Global index of env 0 of this batch: the RANDOM policy draws from Philox stream (env_base + b), so a
+ * job sharded over several GPUs reproduces the single-GPU action streams. */
+int jsl_batch_set_env_base(jsl_batch_t*, int64_t env_base);
 
 /* env.reset (env.py:456-545) + middleware.reset (middleware.py:264-290) for every env whose
  * reset_mask byte is non-zero (NULL = all).  Writes the first observation / candidate to `out`. */
@@ -207,8 +217,10 @@ int jsl_step(jsl_batch_t*, const uint8_t* actions, jsl_step_out out, void* strea
 /* `while not env.done: env.step(policy(env))` fused on device (dipatching_benchmark.py:131-137).
  * Runs at most max_steps further env.steps per env from the CURRENT state (call jsl_reset first).
  * action_tape: dev u8 [B][tape_stride] for JSL_POLICY_TAPE, else NULL. */
+#define JSL_RO_RESET_FIRST 1   /* fuse env.reset into the launch (state is not read from HBM) */
+#define JSL_RO_NO_WRITEBACK 2  /* do not store the final state image (results only) */
 int jsl_rollout(jsl_batch_t*, int policy, const uint8_t* action_tape, int64_t tape_stride,
-                int max_steps, jsl_rollout_out out, void* stream);
+                int max_steps, int flags, jsl_rollout_out out, void* stream);
 
 /* Canonical int32 digest of env `idx` (state + possible transitions; layout in DESIGN.md),
  * copied to host: parity tests, render(), history reconstruction.  Synchronises.

@@ -1,0 +1,54 @@
+"""Build libjsl_b200.so in-tree with nvcc for sm_100a (no JIT, no torch extension machinery).
+
+    python -m jobshoplab_b200.build [--force]
+
+Each translation unit is compiled by its own nvcc process (they run in parallel) and linked into
+jobshoplab_b200/csrc/libjsl_b200.so, which travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+INCLUDE = Path(__file__).resolve().parent.parent / "include"
+LIB = CSRC / "libjsl_b200.so"
+UNITS = ["jsl_abi.cu", "jsl_kernels_jw1.cu", "jsl_kernels_jw2.cu", "jsl_kernels_jw4.cu"]
+HEADERS = [CSRC / "jsl_engine.cuh", CSRC / "jsl_kernels.cuh", INCLUDE / "jobshoplab_b200.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(exe).exists():
+        raise RuntimeError("nvcc not found: the CUDA engine cannot be built")
+    return exe
+
+
+def _compile(unit: str, force: bool) -> Path:
+    src, obj = CSRC / unit, CSRC / (unit[:-3] + ".o")
+    newest = max(p.stat().st_mtime for p in [src, *HEADERS])
+    if not force and obj.exists() and obj.stat().st_mtime >= newest:
+        return obj
+    log = subprocess.run([nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
+    (CSRC / (unit[:-3] + ".ptxas.log")).write_text(log.stderr)
+    if log.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {unit}:\n{log.stderr[-4000:]}")
+    return obj
+
+
+def build(force: bool = False) -> Path:
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        objs = list(ex.map(lambda u: _compile(u, force), UNITS))
+    if force or not LIB.exists() or LIB.stat().st_mtime < max(o.stat().st_mtime for o in objs):
+        subprocess.check_call([nvcc(), "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build("--force" in sys.argv))

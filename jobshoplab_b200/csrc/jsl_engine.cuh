@@ -1,0 +1,1280 @@
+// jsl_engine.cuh -- warp-per-env discrete-event engine of the JobShopLab env-step path (sm_100a).
+//
+// One warp owns one env.  The env's mutable state (EnvS) is staged in shared memory; control flow
+// is warp-uniform (all 32 lanes execute the same scalar code on the same shared data) and every
+// scan over jobs / machines / transports is lane-parallel through three primitives:
+//     wp_ballot  -- predicate over i in [0,n)  -> bit mask          (__ballot_sync)
+//     wp_min     -- min over i in [0,n)                             (__reduce_min_sync)
+//     wp_for     -- independent per-element work + __syncwarp()
+// Ordered buffers (FIFO/LIFO stores of the reference) are not stored as lists: every job carries the
+// buffer it is in and a monotone sequence stamp; queue head/tail, fill level and position tests are
+// ballots / min-reductions over (loc, seq).
+//
+// The header also compiles as plain C++ (JSL_HOST_SIM) with the primitives written as loops.  That
+// build exists only for CPU-side debugging of this very source (tests/hostsim) -- the product never
+// loads it and has no CPU execution path.
+//
+// Reference semantics implemented here (file:line relative to /root/reference/jobshoplab/):
+//   state_machine/core/state_machine/state.py:154-467, handler.py:55-1161, manipulate.py:45-444,
+//   validate.py:30-161, core/transitions.py:82-186, state_machine/time_machines.py:61-221,
+//   utils/state_machine_utils/{possible_transition_utils,buffer_type_utils,outage_utils}.py,
+//   state_machine/middleware/middleware.py:264-443, env/factories/{actions,observations,rewards}.py,
+//   env/env.py:427-454, utils/dipatching_benchmark.py:17-67.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/jobshoplab_b200.h"
+
+#if defined(__CUDACC__) && !defined(JSL_HOST_SIM)
+#define JSL_D __device__ __forceinline__
+#define JSL_M __device__ __forceinline__
+#define JSL_DN __device__ __noinline__
+#define JSL_LANE ((int)(threadIdx.x & 31))
+#define JSL_SYNCWARP() __syncwarp()
+#define JSL_POPC(x) __popc(x)
+#define JSL_FFS(x) __ffs(x)
+#define JSL_FNS(x, n) __fns((x), 0, (n))
+#else
+#define JSL_D static inline
+#define JSL_M inline
+#define JSL_DN static inline
+#define JSL_SYNCWARP() ((void)0)
+#define JSL_POPC(x) __builtin_popcount(x)
+#define JSL_FFS(x) __builtin_ffs((int)(x))
+static inline unsigned jsl_fns_host(unsigned x, int n) {
+    for (unsigned b = 0; b < 32; b++)
+        if ((x >> b) & 1u)
+            if (--n == 0) return b;
+    return 0xffffffffu;
+}
+#define JSL_FNS(x, n) jsl_fns_host((x), (n))
+#endif
+
+namespace jsl {
+
+constexpr int NONE8 = 0xff;
+constexpr int OCC_NOTIME = 0, OCC_TIME = 1, OCC_TD = 2;
+constexpr int INT_BIG = 0x7fffffff;
+constexpr int MAX_OUT = 2;  // outage slots per component
+
+// ------------------------------------------------------------------------------------ instance
+// Device-resident lowered instance set (one shape, n_inst variants of the op tables).
+struct InstDev {
+    int J, M, T, S, NT, N, NB, NP;
+    int n_inst;
+    const int32_t* job_op_start;  // [J+1]
+    const int32_t* op_mt;         // [n_inst][N]  machine | tool << 16
+    const int32_t* op_dur;        // [n_inst][N]
+    const int32_t* job_work;      // [n_inst][J]  sum of the job's durations ("mwkr" key)
+    const int32_t* lb_mat;        // [n_inst][2]  lower_bound, max_allowed_time
+    const uint8_t* pre_type;      // [M]
+    const int32_t* pre_cap;       // [M]
+    const uint8_t* post_type;     // [M]
+    const int32_t* post_cap;      // [M]
+    const int32_t* setup;         // [M*NT*NT] or nullptr (= all zero)
+    const uint8_t* sbuf_type;     // [S]
+    const int32_t* sbuf_cap;      // [S]
+    const uint8_t* sbuf_role;     // [S]
+    const int32_t* buf_ref_id;    // [NB]
+    const int32_t* travel;        // [NP*NP] or nullptr (= all zero)
+    const uint8_t* agv_init_place;  // [T]
+    const uint16_t* job_init_buf;   // [J]
+    const int32_t* m_out_start;     // [M+1]
+    const int32_t* m_out_freq;      // [n]
+    const int32_t* m_out_dur;       // [n]
+    const int32_t* t_out_freq;      // [n_t_out]
+    const int32_t* t_out_dur;       // [n_t_out]
+    const uint8_t* job_lex;         // [J] r-th job in string-id order
+    const uint8_t* mach_lex;        // [M]
+    int n_t_out;
+    int out_buf;      // first OUTPUT-role buffer idx or -1
+    int default_tool;
+    int start_time;
+    int flex_pre;     // every prebuffer is FLEX  -> no automatic machine starts
+    int flex_post;    // every postbuffer and standalone buffer is FLEX -> "ready" needs no position test
+    int caps_inf;     // no finite capacity anywhere
+    int has_m_out, has_t_out;
+};
+
+struct CfgDev {
+    int allow_early_transport, truncation_joker, truncation_active, obs_kind, record_ops;
+    double sparse_bias, dense_bias, truncation_bias;
+};
+
+// ------------------------------------------------------------------------------------ state
+// Mutable state of one env.  JW = ceil(max(J,T)/32) lane words; machines <= 32.
+// The same struct is the HBM image (step mode) and the shared-memory working copy.
+template <int JW>
+struct alignas(16) EnvS {
+    static constexpr int MJ = 32 * JW, MT = 32 * JW, MM = 32;
+    // scalars (uniform)
+    int32_t time;
+    int32_t seq_ctr;
+    int32_t n_possible;       // len(possible_transitions) after the last state-machine call
+    int32_t skip;             // candidates dropped by "no-op with >1 candidates" since then
+    int32_t joker;            // middleware.py:260
+    int32_t step_noop, step_action;  // SubTimeStepper, middleware.py:45-124
+    int32_t reward_noop;      // rewards.py:106 no_op_counter
+    int32_t n_steps, noop_count;
+    int32_t max_done_end;     // max end_time over DONE ops (state.py:270-275)
+    int32_t status;           // JSL_ST_*
+    uint8_t terminated, truncated, last_action_empty, obs_done;
+    int32_t pad0[2];
+    double ret;               // sum of rewards
+    // jobs
+    int32_t j_start[MJ], j_end[MJ];  // of the PROCESSING op
+    uint32_t j_seq[MJ];              // order stamp inside the current buffer
+    uint16_t j_loc[MJ];              // buffer idx
+    uint8_t j_k[MJ];                 // number of DONE ops == index of the next not-done op
+    uint8_t j_proc[MJ];              // op j_k is PROCESSING
+    uint8_t j_agv[MJ];               // transport whose transport_job is this job, or NONE8
+    uint8_t j_mach[MJ];              // machine of op j_k (NONE8 when all ops are done)
+    // machines
+    int32_t m_occ[MM];
+    uint16_t m_done[MM];             // DONE ops on this machine (observation)
+    uint8_t m_state[MM], m_tool[MM], m_job[MM];
+    uint8_t x_mkind[MM], x_mjob[MM];  // scratch: timed machine transitions of this iteration
+    // transports
+    int32_t t_occ[MT];               // time | blocking job (TimeDependency)
+    uint16_t t_loc1[MT], t_tdbuf[MT];
+    uint8_t t_state[MT], t_job[MT], t_carry[MT], t_occkind[MT], t_lockind[MT], t_loc0[MT], t_loc2[MT];
+    uint8_t t_tdcomp[MT], t_tdjob[MT];
+    uint8_t x_tkind[MT], x_tcomp[MT], x_tjob[MT];  // scratch: timed transport transitions
+};
+
+// Outage bookkeeping (types/state_types.py:178-197), only allocated for instances with outages.
+template <int JW>
+struct alignas(16) OutS {
+    static constexpr int MT = 32 * JW, MM = 32;
+    int32_t mo_a[MM * MAX_OUT], mo_b[MM * MAX_OUT];
+    int32_t to_a[MT * MAX_OUT], to_b[MT * MAX_OUT];
+    uint8_t mo_active[MM * MAX_OUT], to_active[MT * MAX_OUT];
+};
+
+// per-call context: uniform values kept in registers
+struct Ctx {
+    const InstDev* I;
+    const CfgDev* C;
+    const int32_t* op_mt;   // this env's variant
+    const int32_t* op_dur;
+    int32_t* op_log;        // [N][2] or nullptr
+    void* outs;             // OutS<JW>* or nullptr
+    int raise;              // JSL_ST_* of an escaping exception, 0 = none
+    int now;
+    int lower_bound, max_allowed_time;
+};
+
+#define JSL_RAISE(c, code)          \
+    do {                            \
+        if (!(c).raise) (c).raise = (code); \
+        return;                     \
+    } while (0)
+#define JSL_RAISE_V(c, code, v)     \
+    do {                            \
+        if (!(c).raise) (c).raise = (code); \
+        return (v);                 \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ primitives
+template <int W>
+struct Mask {
+    uint32_t w[W];
+    JSL_M bool any() const {
+        uint32_t a = 0;
+#pragma unroll
+        for (int i = 0; i < W; i++) a |= w[i];
+        return a != 0;
+    }
+    JSL_M int count() const {
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < W; i++) c += JSL_POPC(w[i]);
+        return c;
+    }
+    JSL_M bool test(int i) const { return (w[i >> 5] >> (i & 31)) & 1u; }
+    JSL_M int first() const {  // -1 if empty
+#pragma unroll
+        for (int i = 0; i < W; i++)
+            if (w[i]) return i * 32 + JSL_FFS(w[i]) - 1;
+        return -1;
+    }
+    JSL_M int pop_first() {
+#pragma unroll
+        for (int i = 0; i < W; i++)
+            if (w[i]) {
+                int b = JSL_FFS(w[i]) - 1;
+                w[i] &= w[i] - 1;
+                return i * 32 + b;
+            }
+        return -1;
+    }
+    JSL_M int nth(int k) const {  // k-th set bit (0-based), -1 if fewer
+#pragma unroll
+        for (int i = 0; i < W; i++) {
+            int c = JSL_POPC(w[i]);
+            if (k < c) return i * 32 + (int)JSL_FNS(w[i], k + 1);
+            k -= c;
+        }
+        return -1;
+    }
+};
+
+#if defined(__CUDACC__) && !defined(JSL_HOST_SIM)
+template <int W, class F>
+JSL_D Mask<W> wp_ballot(int n, F f) {
+    Mask<W> m;
+    const int lane = JSL_LANE;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        int i = w * 32 + lane;
+        bool p = (i < n) && f(i);
+        m.w[w] = __ballot_sync(0xffffffffu, p);
+    }
+    return m;
+}
+template <int W, class F>
+JSL_D int wp_min(int n, F f) {  // f(i) -> int key (INT_BIG = not participating)
+    int v = INT_BIG;
+    const int lane = JSL_LANE;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        int i = w * 32 + lane;
+        if (i < n) {
+            int k = f(i);
+            v = k < v ? k : v;
+        }
+    }
+    return __reduce_min_sync(0xffffffffu, v);
+}
+template <int W, class F>
+JSL_D void wp_for(int n, F f) {
+    const int lane = JSL_LANE;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        int i = w * 32 + lane;
+        if (i < n) f(i);
+    }
+    __syncwarp();
+}
+template <class F>
+JSL_D void wp_for_dyn(int n, F f) {
+    for (int i = JSL_LANE; i < n; i += 32) f(i);
+    __syncwarp();
+}
+#else
+template <int W, class F>
+JSL_D Mask<W> wp_ballot(int n, F f) {
+    Mask<W> m;
+    for (int w = 0; w < W; w++) m.w[w] = 0;
+    for (int i = 0; i < n && i < 32 * W; i++)
+        if (f(i)) m.w[i >> 5] |= 1u << (i & 31);
+    return m;
+}
+template <int W, class F>
+JSL_D int wp_min(int n, F f) {
+    int v = INT_BIG;
+    for (int i = 0; i < n && i < 32 * W; i++) {
+        int k = f(i);
+        v = k < v ? k : v;
+    }
+    return v;
+}
+template <int W, class F>
+JSL_D void wp_for(int n, F f) {
+    for (int i = 0; i < n && i < 32 * W; i++) f(i);
+}
+template <class F>
+JSL_D void wp_for_dyn(int n, F f) {
+    for (int i = 0; i < n; i++) f(i);
+}
+#endif
+
+// ------------------------------------------------------------------------------------ lookups
+JSL_D int buf_type(const InstDev& I, int b) {
+    if (b < 3 * I.M) {
+        int m = b / 3, r = b - 3 * m;
+        return r == 0 ? I.pre_type[m] : r == 1 ? I.post_type[m] : JSL_BUF_FLEX;
+    }
+    if (b < 3 * I.M + I.T) return JSL_BUF_FLEX;
+    return I.sbuf_type[b - 3 * I.M - I.T];
+}
+JSL_D int buf_cap(const InstDev& I, int b) {
+    if (b < 3 * I.M) {
+        int m = b / 3, r = b - 3 * m;
+        return r == 0 ? I.pre_cap[m] : r == 1 ? I.post_cap[m] : 1;
+    }
+    if (b < 3 * I.M + I.T) return 1;
+    return I.sbuf_cap[b - 3 * I.M - I.T];
+}
+JSL_D bool is_standalone(const InstDev& I, int b) { return b >= 3 * I.M + I.T; }
+JSL_D bool is_agv_buf(const InstDev& I, int b) { return b >= 3 * I.M && b < 3 * I.M + I.T; }
+JSL_D bool is_output(const InstDev& I, int b) {
+    return b >= 3 * I.M + I.T && I.sbuf_role[b - 3 * I.M - I.T] == JSL_ROLE_OUTPUT;
+}
+// place of a buffer: machine for machine buffers, M+s for standalone, -1 for an AGV buffer
+JSL_D int place_of_buf(const InstDev& I, int b) {
+    if (b < 3 * I.M) return b / 3;
+    if (b >= 3 * I.M + I.T) return I.M + (b - 3 * I.M - I.T);
+    return -1;
+}
+JSL_D int job_nops(const InstDev& I, int j) { return I.job_op_start[j + 1] - I.job_op_start[j]; }
+JSL_D int travel_time(const InstDev& I, int a, int b) { return I.travel ? I.travel[a * I.NP + b] : 0; }
+
+// ------------------------------------------------------------------------------------ buffers as (loc, seq)
+template <int JW>
+JSL_D int buf_count(const EnvS<JW>& s, const InstDev& I, int b) {
+    return wp_ballot<JW>(I.J, [&](int j) { return s.j_loc[j] == b; }).count();
+}
+
+// buffer_type_utils.py:236-262 get_next_job_from_buffer; -1 = None
+template <int JW>
+JSL_D int next_job_from_buffer(const EnvS<JW>& s, const InstDev& I, int b) {
+    int ty = buf_type(I, b);
+    if (ty == JSL_BUF_FLEX) return -1;
+    // seq stamps are unique per env, so the stamp identifies the job
+    if (ty == JSL_BUF_LIFO) {
+        int k = wp_min<JW>(I.J, [&](int j) { return s.j_loc[j] == b ? (int)(0x7ffffffe - s.j_seq[j]) : INT_BIG; });
+        if (k == INT_BIG) return -1;
+        uint32_t sq = (uint32_t)(0x7ffffffe - k);
+        return wp_ballot<JW>(I.J, [&](int j) { return s.j_loc[j] == b && s.j_seq[j] == sq; }).first();
+    }
+    int k = wp_min<JW>(I.J, [&](int j) { return s.j_loc[j] == b ? (int)s.j_seq[j] : INT_BIG; });
+    if (k == INT_BIG) return -1;
+    return wp_ballot<JW>(I.J, [&](int j) { return s.j_loc[j] == b && (int)s.j_seq[j] == k; }).first();
+}
+
+// buffer_type_utils.py:328-353 is_job_ready_for_pickup_from_postbuffer (uniform j)
+template <int JW>
+JSL_D bool ready_for_pickup(const EnvS<JW>& s, const InstDev& I, int j) {
+    int b = s.j_loc[j];
+    bool right = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
+    if (!right) return false;
+    int ty = buf_type(I, b);
+    if (ty == JSL_BUF_FLEX) return true;
+    uint32_t sq = s.j_seq[j];
+    if (ty == JSL_BUF_LIFO)
+        return !wp_ballot<JW>(I.J, [&](int q) { return s.j_loc[q] == b && s.j_seq[q] > sq; }).any();
+    return !wp_ballot<JW>(I.J, [&](int q) { return s.j_loc[q] == b && s.j_seq[q] < sq; }).any();
+}
+// same test evaluated by one lane for its own job (serial scan; only used when early transport is off)
+template <int JW>
+JSL_D bool ready_for_pickup_lane(const EnvS<JW>& s, const InstDev& I, int j) {
+    int b = s.j_loc[j];
+    bool right = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
+    if (!right) return false;
+    int ty = buf_type(I, b);
+    if (ty == JSL_BUF_FLEX) return true;
+    uint32_t sq = s.j_seq[j];
+    bool ok = true;
+    for (int q = 0; q < I.J; q++)
+        if (s.j_loc[q] == b && (ty == JSL_BUF_LIFO ? s.j_seq[q] > sq : s.j_seq[q] < sq)) ok = false;
+    return ok;
+}
+
+// buffer_type_utils.py:77-105 put_in_buffer (multi-slot buffers)
+template <int JW>
+JSL_D void put_in_buffer(EnvS<JW>& s, Ctx& c, int b, int j) {
+    const InstDev& I = *c.I;
+    if (!I.caps_inf) {
+        int cap = buf_cap(I, b);
+        if (cap != JSL_CAP_INF && buf_count(s, I, b) >= cap) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
+    }
+    s.j_loc[j] = (uint16_t)b;
+    s.j_seq[j] = (uint32_t)s.seq_ctr;
+    s.seq_ctr = s.seq_ctr + 1;
+}
+
+// ------------------------------------------------------------------------------------ possible transitions
+template <int JW>
+struct Poss {
+    Mask<JW> p1;    // jobs with a possible machine start        (state.py:317-338)
+    Mask<JW> idle;  // idle AGVs                                 (possible_transition_utils.py:121-139)
+    Mask<JW> lr;    // lonely running jobs                       (:258-273)
+    Mask<JW> li;    // lonely idle transportable jobs            (:264-273)
+    JSL_M int n_lonely() const { return lr.count() + li.count(); }
+    JSL_M int total() const { return p1.count() + idle.count() * n_lonely(); }
+};
+
+// machine of the next IDLE op of job j and whether it has one (lane-local)
+template <int JW>
+JSL_D int next_idle_place(const EnvS<JW>& s, const Ctx& c, int j) {  // -1 = none -> output buffer
+    const InstDev& I = *c.I;
+    int k = s.j_k[j] + (s.j_proc[j] ? 1 : 0);
+    if (k >= job_nops(I, j)) return -1;
+    return c.op_mt[I.job_op_start[j] + k] & 0xffff;
+}
+
+template <int JW>
+JSL_D Poss<JW> compute_poss(const EnvS<JW>& s, const Ctx& c) {
+    const InstDev& I = *c.I;
+    Poss<JW> p;
+    // possible_transition_utils.py:68-118 is_action_possible
+    p.p1 = wp_ballot<JW>(I.J, [&](int j) {
+        int m = s.j_mach[j];
+        return !s.j_proc[j] && m != NONE8 && s.j_loc[j] == 3 * m && s.m_state[m] == JSL_M_IDLE;
+    });
+    p.idle = wp_ballot<JW>(I.T, [&](int t) { return s.t_state[t] == JSL_T_IDLE; });
+    const bool early = c.C->allow_early_transport != 0;
+    p.lr = wp_ballot<JW>(I.J, [&](int j) {
+        if (!s.j_proc[j] || s.j_agv[j] != NONE8) return false;
+        return early || ready_for_pickup_lane(s, I, j);
+    });
+    // possible_transition_utils.py:167-213 is_transportable
+    p.li = wp_ballot<JW>(I.J, [&](int j) {
+        if (s.j_proc[j] || s.j_agv[j] != NONE8) return false;
+        int m = s.j_mach[j];
+        bool tr = (m == NONE8) ? !is_output(I, s.j_loc[j]) : (s.j_loc[j] != 3 * m);
+        if (!tr) return false;
+        return early || ready_for_pickup_lane(s, I, j);
+    });
+    return p;
+}
+
+struct Trans {
+    int kind, comp, new_state, job;
+};
+
+// idx-th element of get_possible_transitions(state) (state.py:298-341 ordering)
+template <int JW>
+JSL_D Trans nth_possible(const EnvS<JW>& s, const Ctx& c, const Poss<JW>& p, int idx) {
+    Trans t;
+    int n1 = p.p1.count();
+    if (idx < n1) {
+        int j = p.p1.nth(idx);
+        t.kind = 0; t.comp = s.j_mach[j]; t.new_state = JSL_M_SETUP; t.job = j;
+        return t;
+    }
+    int r = idx - n1, nl = p.n_lonely(), nr = p.lr.count();
+    int a = r / nl, q = r - a * nl;
+    t.kind = 1; t.comp = p.idle.nth(a); t.new_state = JSL_T_WORKING;
+    t.job = q < nr ? p.lr.nth(q) : p.li.nth(q - nr);
+    return t;
+}
+
+// ------------------------------------------------------------------------------------ outages
+// outage_utils.py:20-131: sample, occupied time; static frequencies/durations (stochastic: TODO tape)
+JSL_D int sample_outages(Ctx& c, int now, int n, const int32_t* freq, const int32_t* dur, uint8_t* active,
+                         int32_t* a, int32_t* b) {
+    int occupied = 0;
+    for (int i = 0; i < n; i++) {
+        if (active[i]) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, 0);
+        int last = a[i] < 0 ? 0 : a[i];
+        int elapsed = now - last;
+        if (freq[i] >= elapsed) {  // sic, outage_utils.py:48
+            active[i] = 1; a[i] = now; b[i] = now + dur[i];
+        }
+    }
+    bool any = false;
+    for (int i = 0; i < n; i++)
+        if (active[i]) {
+            int len = b[i] - a[i];
+            if (!any || len > occupied) occupied = len;
+            any = true;
+        }
+    return any ? occupied : 0;
+}
+JSL_D void release_outages(int n, uint8_t* active, int32_t* a, int32_t* b) {
+    for (int i = 0; i < n; i++)
+        if (active[i]) { active[i] = 0; a[i] = b[i]; b[i] = -1; }
+}
+
+// ------------------------------------------------------------------------------------ machine handlers
+// validate.py:30-82.  returns false on a validation error (StateMachineResult.success = False)
+template <int JW>
+JSL_D bool machine_valid(const EnvS<JW>& s, Ctx& c, int m, int to, int job) {
+    int from = s.m_state[m];
+    if (from == to) return false;
+    bool ok = from == JSL_M_IDLE ? to == JSL_M_SETUP
+              : from == JSL_M_SETUP ? to == JSL_M_WORKING
+              : from == JSL_M_WORKING ? (to == JSL_M_OUTAGE)
+                                      : to == JSL_M_IDLE;
+    if (!ok) return false;
+    if (from == JSL_M_OUTAGE || from == JSL_M_WORKING) return true;
+    if (job != NONE8) {
+        if (s.j_mach[job] == NONE8) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, false);
+        if (s.j_mach[job] != m) return false;
+    }
+    return true;
+}
+
+// handler.py:414-457 + manipulate.py:378-444
+template <int JW>
+JSL_D void machine_idle_to_setup(EnvS<JW>& s, Ctx& c, int m, int j) {
+    const InstDev& I = *c.I;
+    if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    if (s.j_loc[j] != 3 * m) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    int o = I.job_op_start[j] + s.j_k[j];
+    int tool = (c.op_mt[o] >> 16) & 0xffff;
+    int setup = 0;
+    if (I.setup) {
+        setup = I.setup[(m * I.NT + s.m_tool[m]) * I.NT + tool];
+        if (setup == JSL_NO_TIME) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    }
+    if (s.m_job[m] != NONE8) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
+    s.j_proc[j] = 1; s.j_start[j] = c.now; s.j_end[j] = c.now + setup;
+    s.j_loc[j] = (uint16_t)(3 * m + 2);
+    s.m_job[m] = (uint8_t)j;
+    s.m_state[m] = JSL_M_SETUP; s.m_occ[m] = c.now + setup; s.m_tool[m] = (uint8_t)tool;
+}
+// handler.py:460-503 + manipulate.py:225-276
+template <int JW>
+JSL_D void machine_setup_to_working(EnvS<JW>& s, Ctx& c, int m, int j) {
+    const InstDev& I = *c.I;
+    if (j == NONE8 || s.j_loc[j] != 3 * m + 2) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    int dur = c.op_dur[I.job_op_start[j] + s.j_k[j]];
+    s.j_proc[j] = 1; s.j_start[j] = c.now; s.j_end[j] = c.now + dur;
+    s.m_state[m] = JSL_M_WORKING; s.m_occ[m] = c.now + dur;
+}
+// handler.py:506-543 + manipulate.py:328-375
+template <int JW>
+JSL_D void machine_working_to_outage(EnvS<JW>& s, Ctx& c, int m, int j) {
+    const InstDev& I = *c.I;
+    int occupied_for = 0;
+    if (I.has_m_out) {
+        int b = I.m_out_start[m], n = I.m_out_start[m + 1] - b;
+        OutS<JW>& o = *(OutS<JW>*)c.outs;
+        occupied_for = sample_outages(c, c.now, n, I.m_out_freq + b, I.m_out_dur + b, o.mo_active + m * MAX_OUT,
+                                      o.mo_a + m * MAX_OUT, o.mo_b + m * MAX_OUT);
+        if (c.raise) return;
+    }
+    s.m_state[m] = JSL_M_OUTAGE; s.m_occ[m] = c.now + occupied_for;
+    if (j == NONE8 || !s.j_proc[j]) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    s.j_end[j] = c.now + occupied_for;
+}
+// handler.py:546-574 + manipulate.py:117-193
+template <int JW>
+JSL_D void machine_outage_to_idle(EnvS<JW>& s, Ctx& c, int m) {
+    const InstDev& I = *c.I;
+    int j = s.m_job[m];
+    if (j == NONE8 || !s.j_proc[j]) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    int k = s.j_k[j];
+    if (c.op_log) {
+        int o = I.job_op_start[j] + k;
+        c.op_log[2 * o] = s.j_start[j];
+        c.op_log[2 * o + 1] = c.now;
+    }
+    s.j_k[j] = (uint8_t)(k + 1);
+    s.j_proc[j] = 0;
+    s.j_mach[j] = (k + 1 < job_nops(I, j)) ? (uint8_t)(c.op_mt[I.job_op_start[j] + k + 1] & 0xffff) : (uint8_t)NONE8;
+    if (c.now > s.max_done_end) s.max_done_end = c.now;
+    s.m_done[m] = (uint16_t)(s.m_done[m] + 1);
+    s.m_job[m] = NONE8;
+    put_in_buffer(s, c, 3 * m + 1, j);
+    if (c.raise) return;
+    if (I.has_m_out) {
+        OutS<JW>& o = *(OutS<JW>*)c.outs;
+        release_outages(I.m_out_start[m + 1] - I.m_out_start[m], o.mo_active + m * MAX_OUT, o.mo_a + m * MAX_OUT,
+                        o.mo_b + m * MAX_OUT);
+    }
+    s.m_state[m] = JSL_M_IDLE;
+}
+
+// process one machine transition (validate + handle); false = validation error
+template <int JW>
+JSL_D bool apply_machine(EnvS<JW>& s, Ctx& c, int m, int to, int job) {
+    if (!machine_valid(s, c, m, to, job)) return false;
+    if (c.raise) return true;
+    int from = s.m_state[m];
+    if (from == JSL_M_IDLE) machine_idle_to_setup(s, c, m, job);
+    else if (from == JSL_M_SETUP) machine_setup_to_working(s, c, m, job);
+    else if (from == JSL_M_WORKING) machine_working_to_outage(s, c, m, job);
+    else machine_outage_to_idle(s, c, m);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------ transport handlers
+JSL_D int t_general(int st) { return st == JSL_T_IDLE ? 0 : st == JSL_T_OUTAGE ? 2 : 1; }
+// validate.py:85-118 + transitions.py:82-107,161-186
+template <int JW>
+JSL_D bool transport_valid(const EnvS<JW>& s, int t, int to) {
+    int from = s.t_state[t];
+    if (from == to && from != JSL_T_WAITINGPICKUP) return false;
+    int gf = t_general(from), gt = t_general(to);
+    if (gf == 0) return gt == 1;
+    if (gf == 1) return gt == 2 || gt == 1;
+    return gt == 0;
+}
+
+JSL_D int output_place(Ctx& c) {
+    if (c.I->out_buf < 0) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, 0);
+    return c.I->M + (c.I->out_buf - 3 * c.I->M - c.I->T);
+}
+
+// handler.py:808-902 idle -> working (PICKUP)
+template <int JW>
+JSL_D void agv_idle_to_working(EnvS<JW>& s, Ctx& c, int t, int j) {
+    const InstDev& I = *c.I;
+    if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    if (s.t_lockind[t] != 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    int target = next_idle_place(s, c, j);
+    if (target < 0) target = output_place(c);
+    if (c.raise) return;
+    int loc = s.j_loc[j];
+    int src = place_of_buf(I, loc);
+    if (src < 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TransportConfigError
+    int ttp = travel_time(I, s.t_loc0[t], src);        // no resample (handler.py:876-885)
+    if (ttp == JSL_NO_TIME) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    s.t_occkind[t] = OCC_TIME; s.t_occ[t] = c.now + ttp;
+    s.t_lockind[t] = 1; s.t_loc1[t] = (uint16_t)loc; s.t_loc2[t] = (uint8_t)target;
+    s.t_state[t] = JSL_T_PICKUP;
+    s.t_job[t] = (uint8_t)j;
+    s.j_agv[j] = (uint8_t)t;
+}
+
+// handler.py:577-639 _get_waiting_time, :642-702, :989-1030
+template <int JW>
+JSL_D void agv_to_waitingpickup(EnvS<JW>& s, Ctx& c, int t, int j) {
+    const InstDev& I = *c.I;
+    if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    int loc = s.j_loc[j];
+    int kind = OCC_TIME, val = c.now;
+    if (is_standalone(I, loc)) {
+        // now
+    } else if (is_agv_buf(I, loc)) {
+        JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    } else if (loc % 3 == 1) {  // in the machine's postbuffer
+        if (!ready_for_pickup(s, I, j)) {
+            int nxt = next_job_from_buffer(s, I, loc);
+            if (nxt < 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+            int other = s.j_agv[nxt];
+            if (other == NONE8) {
+                kind = OCC_TD; val = nxt;
+                s.t_tdbuf[t] = (uint16_t)loc; s.t_tdcomp[t] = (uint8_t)t; s.t_tdjob[t] = (uint8_t)j;
+            } else {  // the other transport's occupied_till, whatever it is
+                kind = s.t_occkind[other]; val = s.t_occ[other];
+                if (kind == OCC_TD) {
+                    s.t_tdbuf[t] = s.t_tdbuf[other]; s.t_tdcomp[t] = s.t_tdcomp[other]; s.t_tdjob[t] = s.t_tdjob[other];
+                }
+            }
+        }
+    } else {  // prebuffer or machine buffer: wait for the processing op
+        if (!s.j_proc[j]) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // MissingProcessingOperationError
+        val = s.j_end[j];
+    }
+    s.t_occkind[t] = (uint8_t)kind; s.t_occ[t] = val;
+    s.t_state[t] = JSL_T_WAITINGPICKUP;
+}
+
+// handler.py:705-805 (waiting)pickup -> transit
+template <int JW>
+JSL_D void agv_to_transit(EnvS<JW>& s, Ctx& c, int t, int j) {
+    const InstDev& I = *c.I;
+    if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    int loc = s.j_loc[j];
+    int src = place_of_buf(I, loc);
+    if (src < 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    int dst;
+    int nip = next_idle_place(s, c, j);
+    if (nip < 0) dst = output_place(c);
+    else dst = s.j_mach[j];  // get_next_not_done_operation(job).machine_id
+    if (c.raise) return;
+    if (!(src < I.M || dst < I.M)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    int travel = travel_time(I, src, dst);
+    if (travel == JSL_NO_TIME) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TravelTimeError
+    if (s.t_carry[t] != NONE8) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
+    if (loc % 3 == 2 && loc < 3 * I.M) s.m_job[loc / 3] = NONE8;  // lifted out of a machine buffer
+    s.j_loc[j] = (uint16_t)(3 * I.M + t);
+    s.t_carry[t] = (uint8_t)j;
+    s.t_state[t] = JSL_T_TRANSIT;
+    s.t_occkind[t] = OCC_TIME; s.t_occ[t] = c.now + travel;
+}
+
+// handler.py:905-958 + manipulate.py:45-114 transit -> outage (drop-off)
+template <int JW>
+JSL_D void agv_transit_to_outage(EnvS<JW>& s, Ctx& c, int t, int j) {
+    const InstDev& I = *c.I;
+    if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    if (s.t_lockind[t] != 1) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    if (s.t_carry[t] != j) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // JobNotInBufferError
+    int dest = s.t_loc2[t];
+    int to_buf = dest < I.M ? 3 * dest : 3 * I.M + I.T + (dest - I.M);
+    s.t_carry[t] = NONE8;
+    put_in_buffer(s, c, to_buf, j);
+    if (c.raise) return;
+    int occupied_for = 0;
+    if (I.has_t_out) {
+        OutS<JW>& o = *(OutS<JW>*)c.outs;
+        occupied_for = sample_outages(c, c.now, I.n_t_out, I.t_out_freq, I.t_out_dur, o.to_active + t * MAX_OUT,
+                                      o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
+        if (c.raise) return;
+    }
+    s.t_state[t] = JSL_T_OUTAGE;
+    s.t_occkind[t] = OCC_TIME; s.t_occ[t] = c.now + occupied_for;
+    s.t_lockind[t] = 0; s.t_loc0[t] = (uint8_t)dest;
+    s.j_agv[j] = NONE8;
+    s.t_job[t] = NONE8;
+}
+
+// process one transport transition; false = validation error
+template <int JW>
+JSL_D bool apply_transport(EnvS<JW>& s, Ctx& c, int t, int to, int job) {
+    if (!transport_valid(s, t, to)) return false;
+    int from = s.t_state[t];
+    if (from == JSL_T_IDLE && to == JSL_T_WORKING) agv_idle_to_working(s, c, t, job);
+    else if (from == JSL_T_PICKUP && to == JSL_T_WAITINGPICKUP) agv_to_waitingpickup(s, c, t, job);
+    else if ((from == JSL_T_WAITINGPICKUP || from == JSL_T_PICKUP) && to == JSL_T_TRANSIT) agv_to_transit(s, c, t, job);
+    else if ((from == JSL_T_WORKING || from == JSL_T_TRANSIT) && to == JSL_T_OUTAGE) agv_transit_to_outage(s, c, t, job);
+    else if (from == JSL_T_OUTAGE && to == JSL_T_IDLE) {  // handler.py:961-986
+        if (c.I->has_t_out) {
+            OutS<JW>& o = *(OutS<JW>*)c.outs;
+            release_outages(c.I->n_t_out, o.to_active + t * MAX_OUT, o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
+        }
+        s.t_state[t] = JSL_T_IDLE;
+    } else if (from == JSL_T_WAITINGPICKUP && to == JSL_T_WAITINGPICKUP) agv_to_waitingpickup(s, c, t, job);
+    else { if (!c.raise) c.raise = JSL_ST_OTHER_INVALID; }  // NotImplementedError, handler.py:1125
+    return true;
+}
+
+// ------------------------------------------------------------------------------------ time machines
+// time_machines.py:133-221
+template <int JW>
+JSL_D int force_jump_to_event(const EnvS<JW>& s, Ctx& c) {
+    const InstDev& I = *c.I;
+    int bj = wp_min<JW>(I.J, [&](int j) { return s.j_proc[j] ? s.j_end[j] : INT_BIG; });
+    bool bad = false;
+    int bt = INT_BIG;
+    if (I.T > 0) {
+        Mask<JW> nt = wp_ballot<JW>(I.T, [&](int t) {
+            return s.t_state[t] != JSL_T_IDLE && s.t_occkind[t] == OCC_NOTIME;
+        });
+        bad = nt.any();
+        bt = wp_min<JW>(I.T, [&](int t) {
+            return (s.t_state[t] != JSL_T_IDLE && s.t_occkind[t] == OCC_TIME) ? s.t_occ[t] : INT_BIG;
+        });
+    }
+    if (bad) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, c.now);
+    // INT_BIG doubles as "nobody": a real end time never reaches it
+    if (bj == INT_BIG && bt == INT_BIG) return c.now + 1;  // jump_by_one
+    return bj < bt ? bj : bt;
+}
+
+// ------------------------------------------------------------------------------------ timed transitions
+// handler.py:55-153, :329-379: evaluate on the current snapshot into the x_* scratch arrays.
+// returns true when at least one transition was created.
+template <int JW>
+JSL_D bool create_timed(EnvS<JW>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm) {
+    const InstDev& I = *c.I;
+    const int now = c.now;
+    // machines: occupied_till reached -> next state
+    mm = wp_ballot<1>(I.M, [&](int m) {
+        int st = s.m_state[m];
+        bool due = s.m_occ[m] != JSL_NO_TIME && s.m_occ[m] <= now && st != JSL_M_IDLE;
+        if (due) { s.x_mkind[m] = (uint8_t)((st + 1) & 3); s.x_mjob[m] = s.m_job[m]; }
+        return due;
+    });
+    JSL_SYNCWARP();
+    if (!I.flex_pre) {  // handler.py:117-153: automatic start from FIFO/LIFO/DUMMY prebuffers
+        Mask<1> cand = wp_ballot<1>(I.M, [&](int m) {
+            return !mm.test(m) && s.m_state[m] == JSL_M_IDLE && I.pre_type[m] != JSL_BUF_FLEX;
+        });
+        while (cand.any()) {
+            int m = cand.pop_first();
+            int j = next_job_from_buffer(s, I, 3 * m);
+            if (j >= 0) {
+                s.x_mkind[m] = JSL_M_SETUP; s.x_mjob[m] = (uint8_t)j;
+                mm.w[0] |= 1u << m;
+            }
+        }
+    }
+    {   // a due machine with an empty buffer: machine.buffer.store[0] raises IndexError
+        Mask<1> bad = wp_ballot<1>(I.M, [&](int m) { return mm.test(m) && s.x_mjob[m] == NONE8; });
+        if (bad.any()) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, false);
+    }
+    // transports
+    Mask<JW> need_ready, td, bad_t;
+    tm = wp_ballot<JW>(I.T, [&](int t) {
+        s.x_tkind[t] = NONE8;
+        if (s.t_occkind[t] != OCC_TIME || s.t_occ[t] > now) return false;
+        int st = s.t_state[t];
+        if (st == JSL_T_PICKUP) { s.x_tkind[t] = JSL_T_WAITINGPICKUP; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = s.t_job[t]; return true; }
+        if (st == JSL_T_WAITINGPICKUP) { s.x_tkind[t] = JSL_T_WAITINGPICKUP; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = s.t_job[t]; return true; }
+        if (st == JSL_T_TRANSIT) { s.x_tkind[t] = JSL_T_OUTAGE; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = s.t_carry[t]; return true; }
+        if (st == JSL_T_OUTAGE) { s.x_tkind[t] = JSL_T_IDLE; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = NONE8; return true; }
+        return false;
+    });
+    JSL_SYNCWARP();
+    need_ready = wp_ballot<JW>(I.T, [&](int t) { return tm.test(t) && s.t_state[t] == JSL_T_WAITINGPICKUP; });
+    bad_t = wp_ballot<JW>(I.T, [&](int t) {
+        if (s.t_occkind[t] == OCC_TIME && s.t_occ[t] <= now && s.t_state[t] == JSL_T_WORKING) return true;
+        if (!tm.test(t)) return false;
+        int st = s.t_state[t];
+        if ((st == JSL_T_PICKUP || st == JSL_T_WAITINGPICKUP) && s.t_job[t] == NONE8) return true;  // TransportJobError
+        if (st == JSL_T_TRANSIT && s.t_carry[t] == NONE8) return true;
+        return false;
+    });
+    if (bad_t.any()) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, false);
+    while (need_ready.any()) {  // handler.py:191-252: WAITINGPICKUP & ready -> TRANSIT
+        int t = need_ready.pop_first();
+        int j = s.t_job[t];
+        bool ready;
+        if (I.flex_post) {
+            int b = s.j_loc[j];
+            ready = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
+        } else ready = ready_for_pickup(s, I, j);
+        if (ready) s.x_tkind[t] = JSL_T_TRANSIT;
+    }
+    if (!I.flex_post) {  // handler.py:278-326,356-359 resolved TimeDependency -> stored transition
+        td = wp_ballot<JW>(I.T, [&](int t) { return s.t_occkind[t] == OCC_TD; });
+        while (td.any()) {
+            int t = td.pop_first();
+            int b = s.t_tdbuf[t];
+            int nxt = next_job_from_buffer(s, I, b);
+            int mine = s.t_job[t] == NONE8 ? -1 : (int)s.t_job[t];
+            bool resolved = mine == nxt;
+            int blocking = s.t_occ[t];
+            if (!resolved) resolved = s.j_agv[blocking] != NONE8;
+            if (resolved) {
+                s.x_tkind[t] = JSL_T_WAITINGPICKUP; s.x_tcomp[t] = s.t_tdcomp[t]; s.x_tjob[t] = s.t_tdjob[t];
+                tm.w[t >> 5] |= 1u << (t & 31);
+            }
+        }
+    }
+    JSL_SYNCWARP();
+    return mm.any() || tm.any();
+}
+
+// ------------------------------------------------------------------------------------ state.step
+constexpr int TM_JUMP = 0, TM_FORCE = 1;
+
+template <int JW>
+JSL_D bool any_possible(const EnvS<JW>& s, const Ctx& c) {
+    Poss<JW> p = compute_poss(s, c);
+    return p.p1.any() || (p.idle.any() && (p.lr.any() || p.li.any()));
+}
+
+// state.py:154-295.  Returns success (false = validation error -> success=False); escaping
+// exceptions are left in c.raise.  On return s.n_possible / s.skip describe the new candidate list.
+template <int JW>
+JSL_D bool sm_step(EnvS<JW>& s, Ctx& c, bool has_action, Trans act, int time_machine) {
+    const InstDev& I = *c.I;
+    c.now = s.time;
+    if (has_action) {
+        bool ok = act.kind == 0 ? apply_machine(s, c, act.comp, act.new_state, act.job)
+                                : apply_transport(s, c, act.comp, act.new_state, act.job);
+        if (c.raise) return true;
+        if (!ok) return false;
+    }
+    if (time_machine == TM_FORCE) c.now = force_jump_to_event(s, c);
+    else if (!any_possible(s, c)) c.now = force_jump_to_event(s, c);
+    if (c.raise) return true;
+    Mask<1> mm;
+    Mask<JW> tm;
+    bool have = create_timed(s, c, mm, tm);
+    if (c.raise) return true;
+    // teleports (state.py:229-232, :414-467): i-th idle AGV <- i-th lonely job with zero travel time
+    Mask<JW> tele_idle, zr, zi;
+    {
+        Poss<JW> p = compute_poss(s, c);
+        tele_idle = p.idle;
+        bool active = p.idle.any();
+        Mask<JW> badm;
+        auto zero_travel = [&](int j, bool& bad) {
+            int cur = place_of_buf(I, s.j_loc[j]);
+            int nxt = next_idle_place(s, c, j);
+            if (nxt < 0) nxt = I.out_buf < 0 ? -2 : I.M + (I.out_buf - 3 * I.M - I.T);
+            if (nxt == -2) { bad = true; return false; }
+            if (cur == nxt) return true;
+            if (cur < 0) { bad = true; return false; }
+            int tt = travel_time(I, cur, nxt);
+            if (tt == JSL_NO_TIME) { bad = true; return false; }
+            return tt == 0;
+        };
+        zr = wp_ballot<JW>(I.J, [&](int j) { bool b = false; return active && p.lr.test(j) && zero_travel(j, b); });
+        zi = wp_ballot<JW>(I.J, [&](int j) { bool b = false; return active && p.li.test(j) && zero_travel(j, b); });
+        badm = wp_ballot<JW>(I.J, [&](int j) {
+            bool b = false;
+            if (active && (p.lr.test(j) || p.li.test(j))) zero_travel(j, b);
+            return b;
+        });
+        if (badm.any()) { c.raise = JSL_ST_OTHER_INVALID; return true; }
+    }
+    bool first = true;
+    int guard = 0;
+    while (have || (first && tele_idle.any() && (zr.any() || zi.any()))) {
+        while (mm.any()) {
+            int m = mm.pop_first();
+            bool ok = apply_machine(s, c, m, s.x_mkind[m], s.x_mjob[m]);
+            if (c.raise) return true;
+            if (!ok) return false;
+        }
+        while (tm.any()) {
+            int t = tm.pop_first();
+            bool ok = apply_transport(s, c, s.x_tcomp[t], s.x_tkind[t], s.x_tjob[t]);
+            if (c.raise) return true;
+            if (!ok) return false;
+        }
+        if (first) {
+            while (tele_idle.any() && (zr.any() || zi.any())) {
+                int t = tele_idle.pop_first();
+                int j = zr.any() ? zr.pop_first() : zi.pop_first();
+                bool ok = apply_transport(s, c, t, JSL_T_WORKING, j);
+                if (c.raise) return true;
+                if (!ok) return false;
+            }
+            first = false;
+        }
+        JSL_SYNCWARP();
+        if (!any_possible(s, c)) c.now = force_jump_to_event(s, c);
+        if (c.raise) return true;
+        have = create_timed(s, c, mm, tm);
+        if (c.raise) return true;
+        if (++guard > 100000) { c.raise = JSL_ST_OTHER_INVALID; return true; }  // the reference would spin
+    }
+    s.time = c.now;
+    s.skip = 0;
+    // core_utils.py:44-68 is_done, state.py:270-283
+    bool done = !wp_ballot<JW>(I.J, [&](int j) { return !is_output(I, s.j_loc[j]); }).any();
+    if (done) {
+        if (s.max_done_end >= 0) s.time = s.max_done_end;
+        s.n_possible = 0;
+    } else {
+        s.n_possible = compute_poss(s, c).total();
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------ reset
+template <int JW>
+JSL_D void env_init(EnvS<JW>& s, Ctx& c) {
+    const InstDev& I = *c.I;
+    s.time = I.start_time; s.seq_ctr = 0; s.n_possible = 0; s.skip = 0;
+    s.joker = c.C->truncation_joker; s.step_noop = 0; s.step_action = 0; s.reward_noop = 0;
+    s.n_steps = 0; s.noop_count = 0; s.max_done_end = -1; s.status = JSL_ST_OK;
+    s.terminated = 0; s.truncated = 0; s.last_action_empty = 1; s.obs_done = 0;
+    s.ret = 0.0;
+    JSL_SYNCWARP();
+    wp_for<JW>(EnvS<JW>::MJ, [&](int j) {
+        bool live = j < I.J;
+        s.j_start[j] = -1; s.j_end[j] = -1;
+        s.j_seq[j] = (uint32_t)j;  // initial stores list jobs in job order (mapper.py:1296-1321)
+        s.j_loc[j] = live ? I.job_init_buf[j] : (uint16_t)0xffff;
+        s.j_k[j] = 0; s.j_proc[j] = 0; s.j_agv[j] = NONE8;
+        s.j_mach[j] = (live && job_nops(I, j) > 0) ? (uint8_t)(c.op_mt[I.job_op_start[j]] & 0xffff) : (uint8_t)NONE8;
+    });
+    wp_for<1>(32, [&](int m) {
+        s.m_occ[m] = JSL_NO_TIME; s.m_done[m] = 0; s.m_state[m] = JSL_M_IDLE;
+        s.m_tool[m] = (uint8_t)I.default_tool; s.m_job[m] = NONE8; s.x_mkind[m] = 0; s.x_mjob[m] = NONE8;
+    });
+    wp_for<JW>(EnvS<JW>::MT, [&](int t) {
+        s.t_occ[t] = -1; s.t_loc1[t] = 0; s.t_tdbuf[t] = 0;
+        s.t_state[t] = JSL_T_IDLE; s.t_job[t] = NONE8; s.t_carry[t] = NONE8; s.t_occkind[t] = OCC_NOTIME;
+        s.t_lockind[t] = 0; s.t_loc0[t] = t < I.T ? I.agv_init_place[t] : 0; s.t_loc2[t] = 0;
+        s.t_tdcomp[t] = NONE8; s.t_tdjob[t] = NONE8; s.x_tkind[t] = NONE8; s.x_tcomp[t] = 0; s.x_tjob[t] = NONE8;
+    });
+    if (c.outs) {
+        OutS<JW>& o = *(OutS<JW>*)c.outs;
+        wp_for<1>(32, [&](int m) {
+            for (int k = 0; k < MAX_OUT; k++) { o.mo_active[m * MAX_OUT + k] = 0; o.mo_a[m * MAX_OUT + k] = -1; o.mo_b[m * MAX_OUT + k] = -1; }
+        });
+        wp_for<JW>(EnvS<JW>::MT, [&](int t) {
+            for (int k = 0; k < MAX_OUT; k++) { o.to_active[t * MAX_OUT + k] = 0; o.to_a[t * MAX_OUT + k] = -1; o.to_b[t * MAX_OUT + k] = -1; }
+        });
+    }
+    s.seq_ctr = EnvS<JW>::MJ;
+    JSL_SYNCWARP();
+}
+
+// env.py:456-545 + middleware.py:264-290: init + one dummy step (jump_to_event, no transitions)
+template <int JW>
+JSL_D void env_reset(EnvS<JW>& s, Ctx& c) {
+    env_init(s, c);
+    if (c.op_log) wp_for_dyn(2 * c.I->N, [&](int i) { c.op_log[i] = -1; });
+    Trans none = {0, 0, 0, 0};
+    bool ok = sm_step(s, c, false, none, TM_JUMP);
+    if (c.raise) { s.status = c.raise; return; }
+    if (!ok) s.n_possible = 0;
+}
+
+// ------------------------------------------------------------------------------------ reward / step
+// rewards.py:118-148 BinaryActionJsspReward.make, IEEE double without contraction
+template <int JW>
+JSL_D double make_reward(EnvS<JW>& s, const Ctx& c) {
+    double sr;
+    if (s.truncated) sr = (c.C->truncation_bias * 1.0) / c.C->sparse_bias;
+    else if (!s.terminated) sr = 0.0;
+    else sr = (double)(c.max_allowed_time - s.time) / (double)(c.max_allowed_time - c.lower_bound);
+    if (s.last_action_empty) s.reward_noop = s.reward_noop + 1;
+    else s.reward_noop = 0;
+    double dr = (double)(-(s.reward_noop >= c.I->J ? 1 : 0)) / (double)c.I->N;
+#if defined(__CUDACC__) && !defined(JSL_HOST_SIM)
+    return __dadd_rn(__dmul_rn(sr, c.C->sparse_bias), __dmul_rn(dr, c.C->dense_bias));
+#else
+    volatile double a = sr * c.C->sparse_bias;
+    volatile double b = dr * c.C->dense_bias;
+    return a + b;
+#endif
+}
+
+// env.py:427-454 step + middleware.py:384-431 step + :304-368 _get_no_op_result.
+// `snap` receives the pre-step state image when the caller wants reference-exact rollback on a
+// failed step (step mode keeps the HBM copy instead and passes nullptr).
+template <int JW>
+JSL_D double env_step(EnvS<JW>& s, Ctx& c, int action) {
+    if (s.status > JSL_ST_TRUNCATED) return 0.0;             // a raise already escaped env.step
+    if (s.terminated || s.truncated) { s.status = JSL_ST_ENV_DONE; return 0.0; }  // env.py:441
+    const int remaining = s.n_possible - s.skip;
+    if (remaining <= 0) { s.status = JSL_ST_NO_POSSIBLE; return 0.0; }             // actions.py:141
+    if (action != 0 && action != 1) { s.status = JSL_ST_ACTION_OUT_OF_SPACE; return 0.0; }
+    bool success = true, failed_keep = false;
+    const bool action_empty = action == 0;
+    if (action == 0) {
+        s.step_noop = s.step_noop + 1;
+        if (remaining == 1) {
+            Trans none = {0, 0, 0, 0};
+            success = sm_step(s, c, false, none, TM_FORCE);
+            if (c.raise) { s.status = c.raise; return 0.0; }
+            if (!success) { s.status = JSL_ST_UNSUCCESSFUL; return 0.0; }  // old state is never done here
+            if (s.n_possible == 0) {
+                bool fin = !wp_ballot<JW>(c.I->J, [&](int j) { return !is_output(*c.I, s.j_loc[j]); }).any();
+                if (!fin) { s.status = JSL_ST_UNSUCCESSFUL; return 0.0; }    // middleware.py:344
+            } else {
+                if (c.C->truncation_active && s.step_action == 0) s.joker = s.joker - 1;  // :347
+                s.step_noop = 1; s.step_action = 0;                                       // :351
+            }
+        } else {
+            s.skip = s.skip + 1;  // :355-368 drop the first candidate; state machine not called
+        }
+    } else {
+        s.step_action = s.step_action + 1;
+        Poss<JW> p = compute_poss(s, c);
+        Trans cand = nth_possible(s, c, p, s.skip);
+        success = sm_step(s, c, true, cand, TM_JUMP);
+        if (c.raise) { s.status = c.raise; return 0.0; }
+        failed_keep = !success;
+    }
+    if (success) {
+        s.last_action_empty = action_empty;
+        s.obs_done = (s.n_possible - s.skip) == 0;
+        s.noop_count = s.noop_count + (action_empty ? 1 : 0);
+        s.terminated = !wp_ballot<JW>(c.I->J, [&](int j) { return !is_output(*c.I, s.j_loc[j]); }).any();
+        s.truncated = s.joker < 0;
+    } else {
+        s.obs_done = 1;
+        s.truncated = 1; s.terminated = 0;
+    }
+    (void)failed_keep;
+    double r = make_reward(s, c);
+    s.ret = s.ret + r;
+    s.n_steps = s.n_steps + 1;
+    s.status = !success ? JSL_ST_STEP_FAILED : s.terminated ? JSL_ST_DONE : s.truncated ? JSL_ST_TRUNCATED : JSL_ST_OK;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------ policies
+JSL_D uint32_t philox_bit(uint64_t seed, uint64_t env_idx, uint32_t step) {
+    uint32_t c0 = step, c1 = 0u, c2 = (uint32_t)env_idx, c3 = (uint32_t)(env_idx >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0 & 1u;
+}
+
+// dipatching_benchmark.py:17-67 + dispatch_rules_uitls.py:57-111
+template <int JW>
+JSL_D int policy_action(const EnvS<JW>& s, const Ctx& c, int policy, uint64_t seed, uint64_t env_idx,
+                        const int32_t* job_work) {
+    const InstDev& I = *c.I;
+    if (policy == JSL_POLICY_RANDOM) return (int)philox_bit(seed, env_idx, (uint32_t)s.n_steps);
+    if (policy == JSL_POLICY_FIFO || s.n_possible - s.skip <= 0) return 1;
+    Poss<JW> p = compute_poss(s, c);
+    Trans cand = nth_possible(s, c, p, s.skip);
+    if (cand.kind == 1) return 1;
+    const int pre = 3 * cand.comp, cj = cand.job;
+    auto key = [&](int j) {
+        return policy == JSL_POLICY_SPT ? c.op_dur[I.job_op_start[j] + s.j_k[j]] : job_work[j];
+    };
+    const int ck = key(cj);
+    const uint32_t cs = s.j_seq[cj];
+    // accept iff the candidate is Python's min(): first job in buffer order with the smallest key
+    bool better = wp_ballot<JW>(I.J, [&](int j) {
+        if (s.j_loc[j] != pre || j == cj) return false;
+        int k = key(j);
+        return k < ck || (k == ck && s.j_seq[j] < cs);
+    }).any();
+    return better ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------ observations
+// Packed record of BinaryActionObservationFactory.make (observations.py:515-551 over :419-479):
+//   f32 current_time | f32 current_transition[3] | i32 job_progression[J] | i32 machine_progression[M]
+//   | i8 job_running[J] | i8 available_jobs[J] | i8 machine_running[M] | i8 job_executed_on_machine[J*M]
+//   zero-padded to a multiple of 16 bytes.  Rows follow the reference's string-id ordering quirk.
+#if defined(__CUDACC__) && !defined(JSL_HOST_SIM)
+#define JSL_HD __host__ __device__ inline
+#else
+#define JSL_HD static inline
+#endif
+JSL_HD int obs_bytes_binary(int J, int M) { return (16 + 4 * J + 4 * M + 2 * J + M + J * M + 15) & ~15; }
+JSL_HD int obs_bytes_oparray(int J, int N) { return (16 + 4 * N + 4 * J + 15) & ~15; }
+
+template <int JW>
+JSL_D void cand_floats(const EnvS<JW>& s, const Ctx& c, float* tr) {
+    const InstDev& I = *c.I;
+    if (!s.obs_done && s.n_possible - s.skip > 0) {
+        Poss<JW> p = compute_poss(s, c);
+        Trans cand = nth_possible(s, c, p, s.skip);
+        int comp_idx = cand.kind == 0 ? cand.comp : I.M + cand.comp;
+        tr[0] = (float)((double)comp_idx / (double)(I.M + I.T));
+        tr[1] = (float)((double)cand.job / (double)I.J);
+        tr[2] = cand.kind == 0 ? 0.0f : (float)0.33;
+    } else {
+        tr[0] = tr[1] = tr[2] = 1.0f;
+    }
+}
+
+template <int JW>
+JSL_D void write_obs_binary(const EnvS<JW>& s, const Ctx& c, uint8_t* out) {
+    const InstDev& I = *c.I;
+    const int J = I.J, M = I.M;
+    float tr[3];
+    cand_floats(s, c, tr);
+    float* f = (float*)out;
+    int32_t* jprog = (int32_t*)(out + 16);
+    int32_t* mprog = jprog + J;
+    int8_t* jrun = (int8_t*)(mprog + M);
+    int8_t* avail = jrun + J;
+    int8_t* mrun = avail + J;
+    int8_t* exec = mrun + M;
+    const int total = obs_bytes_binary(J, M);
+    wp_for_dyn(1, [&](int) {
+        f[0] = (float)((double)s.time / (double)c.max_allowed_time);
+        f[1] = tr[0]; f[2] = tr[1]; f[3] = tr[2];
+        for (int i = 16 + 4 * J + 4 * M + 2 * J + M + J * M; i < total; i++) out[i] = 0;
+    });
+    wp_for<JW>(J, [&](int r) {
+        int j = I.job_lex[r];
+        jrun[r] = (int8_t)s.j_proc[j];
+        bool any_idle = (s.j_k[j] + (s.j_proc[j] ? 1 : 0)) < job_nops(I, j);
+        // numeric index into the lexicographically ordered tuple (observations.py:437-441)
+        avail[r] = (int8_t)(any_idle && !s.j_proc[I.job_lex[j]]);
+        jprog[r] = s.j_k[r];
+        int8_t* row = exec + r * M;
+        for (int m = 0; m < M; m++) row[m] = 0;
+        int o0 = I.job_op_start[j];
+        for (int k = 0; k < s.j_k[j]; k++) row[c.op_mt[o0 + k] & 0xffff] = 1;
+    });
+    wp_for<1>(M, [&](int r) {
+        int m = I.mach_lex[r];
+        mrun[r] = (int8_t)(s.m_state[m] == JSL_M_WORKING);
+        mprog[r] = s.m_done[m];
+    });
+}
+
+// BinaryOperationArrayObservation.make (observations.py:631-693 over :588-618):
+//   f32 current_transition[3] | f32 0 | f32 operation_state[N] | f32 job_locations[J]
+template <int JW>
+JSL_D void write_obs_oparray(const EnvS<JW>& s, Ctx& c, uint8_t* out) {
+    const InstDev& I = *c.I;
+    float tr[3];
+    cand_floats(s, c, tr);
+    float* f = (float*)out;
+    float* ops = f + 4;
+    float* loc = ops + I.N;
+    const int total = obs_bytes_oparray(I.J, I.N);
+    wp_for_dyn(1, [&](int) {
+        f[0] = tr[0]; f[1] = tr[1]; f[2] = tr[2]; f[3] = 0.f;
+        for (int i = 16 + 4 * I.N + 4 * I.J; i < total; i++) out[i] = 0;
+    });
+    const int max_buffer_id = I.S + 3 * I.M + I.T - 1;
+    Mask<JW> bad = wp_ballot<JW>(I.J, [&](int j) {
+        int o0 = I.job_op_start[j], n = job_nops(I, j), k = s.j_k[j];
+        bool zero_div = false;
+        for (int i = 0; i < n; i++) {
+            float v = i < k ? 1.f : 0.f;
+            if (i == k && s.j_proc[j]) {
+                int dur = s.j_end[j] - s.j_start[j];
+                if (dur == 0) zero_div = true;
+                else v = (float)((double)(s.time - s.j_start[j]) / (double)dur);
+            }
+            ops[o0 + i] = v;
+        }
+        loc[j] = (float)((double)I.buf_ref_id[s.j_loc[j]] / (double)max_buffer_id);
+        return zero_div;
+    });
+    JSL_SYNCWARP();
+    if (bad.any() && !c.raise) c.raise = JSL_ST_OTHER_INVALID;  // ZeroDivisionError
+}
+
+// ------------------------------------------------------------------------------------ canonical digest
+// Layout documented in DESIGN.md / oracle/ref_harness.py.  Executed by one env's warp (diagnostics,
+// parity tests, render()).  Returns the number of int32 produced (writes at most cap).
+template <int JW>
+JSL_D int write_digest(const EnvS<JW>& s, const Ctx& c, int32_t* out, int cap) {
+    const InstDev& I = *c.I;
+    int n = 0;
+    // executed redundantly by every lane with identical values (uniform stores)
+#define JSL_PUT(v) do { if (n < cap) out[n] = (int32_t)(v); n++; } while (0)
+    JSL_PUT(s.time); JSL_PUT(I.J); JSL_PUT(I.M); JSL_PUT(I.T); JSL_PUT(I.S);
+    for (int j = 0; j < I.J; j++) {
+        int k = s.j_k[j], nops = job_nops(I, j), o0 = I.job_op_start[j];
+        JSL_PUT(k); JSL_PUT(s.j_proc[j]); JSL_PUT(s.j_loc[j]);
+        for (int i = 0; i < nops; i++) {
+            if (i < k) { JSL_PUT(2); JSL_PUT(c.op_log ? c.op_log[2 * (o0 + i)] : -1); JSL_PUT(c.op_log ? c.op_log[2 * (o0 + i) + 1] : -1); }
+            else if (i == k && s.j_proc[j]) { JSL_PUT(1); JSL_PUT(s.j_start[j]); JSL_PUT(s.j_end[j]); }
+            else { JSL_PUT(0); JSL_PUT(-1); JSL_PUT(-1); }
+        }
+    }
+    auto put_store = [&](int b) {  // jobs of buffer b in stamp order
+        int cnt = 0;
+        for (int j = 0; j < I.J; j++) cnt += s.j_loc[j] == b;
+        JSL_PUT(cnt);
+        uint32_t last = 0; bool have = false;
+        for (int i = 0; i < cnt; i++) {
+            int best = -1;
+            for (int j = 0; j < I.J; j++)
+                if (s.j_loc[j] == b && (!have || s.j_seq[j] > last) && (best < 0 || s.j_seq[j] < s.j_seq[best])) best = j;
+            JSL_PUT(best); last = s.j_seq[best]; have = true;
+        }
+    };
+    for (int m = 0; m < I.M; m++) {
+        JSL_PUT(s.m_state[m]); JSL_PUT(s.m_occ[m]); JSL_PUT(s.m_tool[m]);
+        put_store(3 * m); put_store(3 * m + 2); put_store(3 * m + 1);
+    }
+    for (int t = 0; t < I.T; t++) {
+        JSL_PUT(s.t_state[t]); JSL_PUT(s.t_occkind[t]);
+        if (s.t_occkind[t] == OCC_TD) { JSL_PUT(s.t_occ[t]); JSL_PUT(s.t_tdbuf[t]); JSL_PUT(s.t_tdcomp[t]); JSL_PUT(s.t_tdjob[t]); }
+        else if (s.t_occkind[t] == OCC_TIME) { JSL_PUT(s.t_occ[t]); JSL_PUT(-1); JSL_PUT(-1); JSL_PUT(-1); }
+        else { JSL_PUT(-1); JSL_PUT(-1); JSL_PUT(-1); JSL_PUT(-1); }
+        JSL_PUT(s.t_carry[t] == NONE8 ? -1 : s.t_carry[t]);
+        JSL_PUT(s.t_job[t] == NONE8 ? -1 : s.t_job[t]);
+        JSL_PUT(s.t_lockind[t]); JSL_PUT(s.t_loc0[t]);
+        JSL_PUT(s.t_lockind[t] ? (int)s.t_loc1[t] : -1); JSL_PUT(s.t_lockind[t] ? (int)s.t_loc2[t] : -1);
+    }
+    for (int b = 3 * I.M + I.T; b < I.NB; b++) put_store(b);
+    if (c.outs) {
+        const OutS<JW>& ou = *(const OutS<JW>*)c.outs;
+        for (int m = 0; m < I.M; m++) {
+            int nm = I.has_m_out ? I.m_out_start[m + 1] - I.m_out_start[m] : 0;
+            for (int k = 0; k < nm; k++) {
+                int i = m * MAX_OUT + k;
+                JSL_PUT(ou.mo_active[i]); JSL_PUT(ou.mo_a[i]); JSL_PUT(ou.mo_active[i] ? ou.mo_b[i] : -1);
+            }
+        }
+        for (int t = 0; t < I.T; t++)
+            for (int k = 0; k < (I.has_t_out ? I.n_t_out : 0); k++) {
+                int i = t * MAX_OUT + k;
+                JSL_PUT(ou.to_active[i]); JSL_PUT(ou.to_a[i]); JSL_PUT(ou.to_active[i] ? ou.to_b[i] : -1);
+            }
+    }
+    int remaining = s.n_possible - s.skip;
+    if (remaining < 0) remaining = 0;
+    JSL_PUT(remaining);
+    if (remaining > 0) {
+        Poss<JW> p = compute_poss(s, c);
+        for (int i = 0; i < remaining; i++) {
+            Trans t = nth_possible(s, c, p, s.skip + i);
+            JSL_PUT(t.kind); JSL_PUT(t.comp); JSL_PUT(t.new_state); JSL_PUT(t.job);
+        }
+    }
+#undef JSL_PUT
+    return n;
+}
+
+}  // namespace jsl

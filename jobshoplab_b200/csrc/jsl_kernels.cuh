@@ -1,0 +1,287 @@
+// jsl_kernels.cuh -- the sm_100a kernels around jsl_engine.cuh and their typed launchers.
+//
+// Kernels (one warp per env, 4 warps per CTA, state staged in shared memory):
+//   k_reset   : env.reset for the masked envs, writes the HBM state image + first observation
+//   k_step    : HBM state -> smem (128-bit coalesced), one env.step, obs/reward/flags out, smem -> HBM
+//   k_rollout : persistent grid; each warp runs whole episodes with an in-kernel policy, state
+//               never leaves shared memory between steps
+//   k_digest  : canonical digest of one env (diagnostics / parity / render)
+// Each lane-word count JW (1, 2, 4 -> up to 32, 64, 128 jobs/transports) is instantiated in its own
+// translation unit (jsl_kernels_jw<N>.cu) so the three compile in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "jsl_engine.cuh"
+
+namespace jsl {
+
+constexpr int WARPS_PER_CTA = 4;
+
+struct BatchDev {
+    InstDev inst;
+    CfgDev cfg;
+    int64_t B;
+    uint8_t* state;      // [B][state_stride]
+    uint8_t* outs;       // [B][outs_stride] or nullptr
+    int32_t* op_log;     // [B][N][2] or nullptr
+    int state_stride, outs_stride;
+    uint64_t seed;
+    int64_t env_base;    // global index of env 0 (RANDOM policy stream id)
+};
+
+template <int JW>
+__device__ __forceinline__ void copy_in(void* dst, const void* src, int bytes) {
+    const int4* s = (const int4*)src;
+    int4* d = (int4*)dst;
+    for (int i = JSL_LANE; i < bytes / 16; i += 32) d[i] = s[i];
+    __syncwarp();
+}
+
+template <int JW>
+__device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env, void* outs_sm) {
+    const InstDev& I = bd.inst;
+    int64_t v = env % I.n_inst;
+    c.I = &bd.inst;
+    c.C = &bd.cfg;
+    c.op_mt = I.op_mt + v * I.N;
+    c.op_dur = I.op_dur + v * I.N;
+    c.op_log = bd.op_log ? bd.op_log + env * 2 * (int64_t)I.N : nullptr;
+    c.outs = outs_sm;
+    c.raise = 0;
+    c.now = 0;
+    c.lower_bound = I.lb_mat[2 * v];
+    c.max_allowed_time = I.lb_mat[2 * v + 1];
+}
+
+template <int JW>
+__device__ __forceinline__ void write_step_out(const EnvS<JW>& s, Ctx& c, const jsl_step_out& out, int64_t env,
+                                               double reward, int obs_bytes) {
+    const InstDev& I = *c.I;
+    if (out.obs && s.status <= JSL_ST_STEP_FAILED) {
+        uint8_t* o = out.obs + env * (int64_t)obs_bytes;
+        if (c.C->obs_kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o);
+        else if (c.C->obs_kind == JSL_OBS_OPERATION_ARRAY) write_obs_oparray(s, c, o);
+    }
+    int status = s.status;
+    if (c.raise && status <= JSL_ST_STEP_FAILED) status = c.raise;  // observation factory raised
+    int16_t cd[4] = {-1, -1, -1, 0};
+    int remaining = s.n_possible - s.skip;
+    if (out.cand && remaining > 0 && status <= JSL_ST_TRUNCATED) {
+        Poss<JW> p = compute_poss(s, c);
+        Trans t = nth_possible(s, c, p, s.skip);
+        cd[0] = (int16_t)t.kind; cd[1] = (int16_t)t.comp; cd[2] = (int16_t)t.job;
+        cd[3] = (int16_t)(remaining > 32767 ? 32767 : remaining);
+    }
+    if (JSL_LANE == 0) {
+        if (out.reward) out.reward[env] = reward;
+        if (out.terminated) out.terminated[env] = s.terminated;
+        if (out.truncated) out.truncated[env] = s.truncated;
+        if (out.status) out.status[env] = (uint8_t)status;
+        if (out.time) out.time[env] = s.time;
+        if (out.makespan) out.makespan[env] = s.terminated ? s.time : -1;
+        if (out.cand) {
+            int16_t* q = out.cand + env * 4;
+            q[0] = cd[0]; q[1] = cd[1]; q[2] = cd[2]; q[3] = cd[3];
+        }
+    }
+    (void)I;
+}
+
+template <int JW>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, jsl_step_out out, int obs_bytes) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+    if (env >= bd.B) return;
+    if (mask && !mask[env]) return;
+    EnvS<JW>& s = *(EnvS<JW>*)(smem + (size_t)warp * (bd.state_stride + bd.outs_stride));
+    void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
+    Ctx c;
+    make_ctx<JW>(c, bd, env, outs_sm);
+    env_reset(s, c);
+    __syncwarp();
+    write_step_out(s, c, out, env, 0.0, obs_bytes);
+    __syncwarp();
+    copy_in<JW>(bd.state + env * (int64_t)bd.state_stride, &s, bd.state_stride);
+    if (bd.outs) copy_in<JW>(bd.outs + env * (int64_t)bd.outs_stride, outs_sm, bd.outs_stride);
+}
+
+template <int JW>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions, jsl_step_out out, int obs_bytes) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+    if (env >= bd.B) return;
+    EnvS<JW>& s = *(EnvS<JW>*)(smem + (size_t)warp * (bd.state_stride + bd.outs_stride));
+    void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
+    uint8_t* g_state = bd.state + env * (int64_t)bd.state_stride;
+    uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
+    copy_in<JW>(&s, g_state, bd.state_stride);
+    if (g_outs) copy_in<JW>(outs_sm, g_outs, bd.outs_stride);
+    Ctx c;
+    make_ctx<JW>(c, bd, env, outs_sm);
+    const int action = actions[env];
+    double r = env_step(s, c, action);
+    __syncwarp();
+    if (s.status >= JSL_ST_STEP_FAILED) {
+        // success=False / an escaping exception: the reference keeps the OLD state (state.py:202-210);
+        // re-read the HBM image and carry over only the bookkeeping scalars.
+        int status = s.status, n_steps = s.n_steps, reward_noop = s.reward_noop, step_action = s.step_action,
+            step_noop = s.step_noop;
+        double ret = s.ret;
+        __syncwarp();
+        copy_in<JW>(&s, g_state, bd.state_stride);
+        if (g_outs) copy_in<JW>(outs_sm, g_outs, bd.outs_stride);
+        s.status = status;
+        if (status == JSL_ST_STEP_FAILED) {
+            s.truncated = 1; s.terminated = 0; s.obs_done = 1;
+            s.n_steps = n_steps; s.reward_noop = reward_noop; s.step_action = step_action; s.step_noop = step_noop;
+            s.ret = ret;
+        }
+        __syncwarp();
+    }
+    write_step_out(s, c, out, env, r, obs_bytes);
+    __syncwarp();
+    copy_in<JW>(g_state, &s, bd.state_stride);
+    if (g_outs) copy_in<JW>(g_outs, outs_sm, bd.outs_stride);
+}
+
+template <int JW>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __restrict__ tape, int64_t tape_stride,
+          int max_steps, int flags, jsl_rollout_out out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    EnvS<JW>& s = *(EnvS<JW>*)(smem + (size_t)warp * (bd.state_stride + bd.outs_stride));
+    void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
+    const int64_t stride = (int64_t)gridDim.x * WARPS_PER_CTA;
+    for (int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; env < bd.B; env += stride) {
+        uint8_t* g_state = bd.state + env * (int64_t)bd.state_stride;
+        uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
+        Ctx c;
+        make_ctx<JW>(c, bd, env, outs_sm);
+        if (flags & JSL_RO_RESET_FIRST) {
+            env_reset(s, c);
+        } else {
+            copy_in<JW>(&s, g_state, bd.state_stride);
+            if (g_outs) copy_in<JW>(outs_sm, g_outs, bd.outs_stride);
+        }
+        __syncwarp();
+        const int32_t* job_work = bd.inst.job_work + (env % bd.inst.n_inst) * bd.inst.J;
+        const uint8_t* my_tape = tape ? tape + env * tape_stride : nullptr;
+        int n = 0;
+        while (n < max_steps && s.status == JSL_ST_OK) {
+            int a;
+            if (policy == JSL_POLICY_TAPE) {
+                if (s.n_steps >= tape_stride) break;
+                a = my_tape[s.n_steps];
+            } else {
+                a = policy_action(s, c, policy, bd.seed, (uint64_t)(bd.env_base + env), job_work);
+            }
+            env_step(s, c, a);
+            __syncwarp();
+            n++;
+        }
+        if (JSL_LANE == 0) {
+            if (out.makespan) out.makespan[env] = s.time;
+            if (out.n_steps) out.n_steps[env] = s.n_steps;
+            if (out.ret) out.ret[env] = s.ret;
+            if (out.status) out.status[env] = (uint8_t)s.status;
+            if (out.no_op_count) out.no_op_count[env] = s.noop_count;
+        }
+        __syncwarp();
+        if (!(flags & JSL_RO_NO_WRITEBACK)) {
+            copy_in<JW>(g_state, &s, bd.state_stride);
+            if (g_outs) copy_in<JW>(g_outs, outs_sm, bd.outs_stride);
+        }
+        __syncwarp();
+    }
+}
+
+template <int JW>
+__global__ void __launch_bounds__(32)
+k_digest(const __grid_constant__ BatchDev bd, int64_t env, int32_t* out, int cap, int32_t* n_out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    EnvS<JW>& s = *(EnvS<JW>*)smem;
+    void* outs_sm = bd.outs ? (void*)(smem + bd.state_stride) : nullptr;
+    copy_in<JW>(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
+    if (bd.outs) copy_in<JW>(outs_sm, bd.outs + env * (int64_t)bd.outs_stride, bd.outs_stride);
+    Ctx c;
+    make_ctx<JW>(c, bd, env, outs_sm);
+    int n = write_digest(s, c, out, cap);
+    if (JSL_LANE == 0) *n_out = n;
+}
+
+// ------------------------------------------------------------------------------------ launchers
+struct LaunchCfg {
+    int grid, smem;
+    cudaStream_t stream;
+};
+
+template <int JW>
+cudaError_t launch_reset(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* mask, jsl_step_out out, int obs_bytes) {
+    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_reset<JW>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+    k_reset<JW><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, mask, out, obs_bytes);
+    return cudaGetLastError();
+}
+template <int JW>
+cudaError_t launch_step(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* actions, jsl_step_out out, int obs_bytes) {
+    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_step<JW>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+    k_step<JW><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, actions, out, obs_bytes);
+    return cudaGetLastError();
+}
+template <int JW>
+cudaError_t launch_rollout(const BatchDev& bd, const LaunchCfg& lc, int policy, const uint8_t* tape, int64_t tape_stride,
+                           int max_steps, int flags, jsl_rollout_out out) {
+    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+    k_rollout<JW><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, policy, tape, tape_stride, max_steps, flags, out);
+    return cudaGetLastError();
+}
+template <int JW>
+cudaError_t launch_digest(const BatchDev& bd, const LaunchCfg& lc, int64_t env, int32_t* out, int cap, int32_t* n_out) {
+    k_digest<JW><<<1, 32, lc.smem, lc.stream>>>(bd, env, out, cap, n_out);
+    return cudaGetLastError();
+}
+template <int JW>
+int rollout_occupancy(int smem) {  // resident CTAs per SM for the persistent rollout grid
+    int n = 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_rollout<JW>, WARPS_PER_CTA * 32, smem) != cudaSuccess) return 8;
+    return n > 0 ? n : 1;
+}
+
+// entry points defined by jsl_kernels_jw<N>.cu
+#define JSL_DECLARE_JW(N)                                                                                             \
+    cudaError_t launch_reset_jw##N(const BatchDev&, const LaunchCfg&, const uint8_t*, jsl_step_out, int);             \
+    cudaError_t launch_step_jw##N(const BatchDev&, const LaunchCfg&, const uint8_t*, jsl_step_out, int);              \
+    cudaError_t launch_rollout_jw##N(const BatchDev&, const LaunchCfg&, int, const uint8_t*, int64_t, int, int,      \
+                                     jsl_rollout_out);                                                                \
+    cudaError_t launch_digest_jw##N(const BatchDev&, const LaunchCfg&, int64_t, int32_t*, int, int32_t*);            \
+    int rollout_occupancy_jw##N(int smem);                                                                            \
+    int state_bytes_jw##N();                                                                                          \
+    int outs_bytes_jw##N();
+JSL_DECLARE_JW(1)
+JSL_DECLARE_JW(2)
+JSL_DECLARE_JW(4)
+
+#define JSL_DEFINE_JW(N)                                                                                              \
+    cudaError_t launch_reset_jw##N(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* m, jsl_step_out o, int ob) { \
+        return launch_reset<N>(bd, lc, m, o, ob);                                                                     \
+    }                                                                                                                 \
+    cudaError_t launch_step_jw##N(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* a, jsl_step_out o, int ob) { \
+        return launch_step<N>(bd, lc, a, o, ob);                                                                      \
+    }                                                                                                                 \
+    cudaError_t launch_rollout_jw##N(const BatchDev& bd, const LaunchCfg& lc, int p, const uint8_t* t, int64_t ts,    \
+                                     int ms, int f, jsl_rollout_out o) {                                              \
+        return launch_rollout<N>(bd, lc, p, t, ts, ms, f, o);                                                         \
+    }                                                                                                                 \
+    cudaError_t launch_digest_jw##N(const BatchDev& bd, const LaunchCfg& lc, int64_t e, int32_t* o, int c, int32_t* n) { \
+        return launch_digest<N>(bd, lc, e, o, c, n);                                                                  \
+    }                                                                                                                 \
+    int rollout_occupancy_jw##N(int smem) { return rollout_occupancy<N>(smem); }                                      \
+    int state_bytes_jw##N() { return (int)sizeof(EnvS<N>); }                                                          \
+    int outs_bytes_jw##N() { return (int)sizeof(OutS<N>); }
+
+}  // namespace jsl

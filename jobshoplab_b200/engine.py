@@ -1,0 +1,249 @@
+"""Thin host binding of the CUDA engine (csrc/libjsl_b200.so) through its C ABI.
+
+PyTorch is used for device memory and streams only: every array crossing the boundary is a raw
+device pointer (``tensor.data_ptr()``).  There is NO CPU execution path -- if the shared library or a
+CUDA device is missing, construction raises ``EngineUnavailable``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+from . import abi
+from .exceptions import EngineUnavailable, InvalidValue
+from .lowered import LoweredInstance
+
+LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libjsl_b200.so"
+_lib = None
+
+ABI_SYMBOLS = ("jsl_last_error", "jsl_abi_version", "jsl_instance_create", "jsl_instance_destroy", "jsl_batch_create",
+               "jsl_batch_create_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base",
+               "jsl_reset", "jsl_step", "jsl_rollout", "jsl_get_state", "jsl_get_op_log", "jsl_launch_count")
+
+RO_RESET_FIRST, RO_NO_WRITEBACK = 1, 2
+
+
+def load_library():
+    """dlopen the engine; raises EngineUnavailable (never falls back to anything else)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise EngineUnavailable(f"{LIB_PATH} is missing: build it with `python -m jobshoplab_b200.build` "
+                                "(there is no CPU fallback)")
+    L = C.CDLL(str(LIB_PATH))
+    L.jsl_last_error.restype = C.c_char_p
+    L.jsl_abi_version.restype = C.c_int
+    L.jsl_instance_create.restype = C.c_void_p
+    L.jsl_instance_create.argtypes = [C.POINTER(abi.InstanceDesc)]
+    L.jsl_instance_destroy.argtypes = [C.c_void_p]
+    L.jsl_batch_create.restype = C.c_void_p
+    L.jsl_batch_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int, C.c_uint64,
+                                   C.POINTER(abi.EnvCfg)]
+    L.jsl_batch_create_variants.restype = C.c_void_p
+    L.jsl_batch_create_variants.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int64, C.c_int, C.c_uint64, C.POINTER(abi.EnvCfg)]
+    L.jsl_batch_destroy.argtypes = [C.c_void_p]
+    L.jsl_batch_shape.argtypes = [C.c_void_p, C.POINTER(abi.Shape)]
+    L.jsl_batch_set_env_base.argtypes = [C.c_void_p, C.c_int64]
+    L.jsl_reset.argtypes = [C.c_void_p, C.c_void_p, abi.StepOut, C.c_void_p]
+    L.jsl_step.argtypes = [C.c_void_p, C.c_void_p, abi.StepOut, C.c_void_p]
+    L.jsl_rollout.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, abi.RolloutOut, C.c_void_p]
+    L.jsl_get_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+    L.jsl_get_op_log.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.jsl_launch_count.restype = C.c_int64
+    L.jsl_launch_count.argtypes = [C.c_void_p]
+    if L.jsl_abi_version() != abi.ABI_VERSION:
+        raise EngineUnavailable("libjsl_b200.so ABI version mismatch: rebuild it")
+    _lib = L
+    return L
+
+
+def _err(L) -> str:
+    return (L.jsl_last_error() or b"").decode()
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise EngineUnavailable("no CUDA device: the jobshoplab_b200 engine runs on the GPU only")
+    return torch
+
+
+class Instance:
+    """jsl_instance_t for one LoweredInstance."""
+
+    def __init__(self, lowered: LoweredInstance):
+        self.L = load_library()
+        self.lowered = lowered
+        self._desc = abi.make_desc(lowered)
+        self.h = self.L.jsl_instance_create(C.byref(self._desc))
+        if not self.h:
+            raise InvalidValue("instance", lowered.description, _err(self.L))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.jsl_instance_destroy(self.h)
+            self.h = None
+
+
+@dataclass
+class StepResult:
+    obs: "object"          # torch uint8 [B, obs_bytes] packed record (see Batch.unpack_obs)
+    reward: "object"       # f64 [B]
+    terminated: "object"   # u8 [B]
+    truncated: "object"    # u8 [B]
+    status: "object"       # u8 [B] JSL_ST_*
+    time: "object"         # i32 [B]
+    makespan: "object"     # i32 [B] (-1 unless terminated)
+    cand: "object"         # i16 [B, 4]: kind, component, job, n_remaining of possible_transitions[0]
+
+
+@dataclass
+class RolloutResult:
+    makespan: "object"
+    n_steps: "object"
+    ret: "object"
+    status: "object"
+    no_op_count: "object"
+
+
+class Batch:
+    """B envs on one CUDA device (jsl_batch_t).  Tensors are allocated once and reused."""
+
+    def __init__(self, lowered, B: int, device: int = 0, seed: int = 0, variants=None, **cfg):
+        torch = _torch()
+        self.torch = torch
+        self.L = load_library()
+        self.B = int(B)
+        self.device = int(device)
+        self.cfg = abi.make_cfg(**cfg)
+        if isinstance(lowered, LoweredInstance):
+            lowered = [lowered]
+        self.lowered = list(lowered)
+        self.instances = [Instance(li) for li in self.lowered]
+        if variants is not None:
+            om, od, lb, mat = (np.ascontiguousarray(a, dtype=np.int32) for a in variants)
+            n_inst = om.shape[0]
+            self.h = self.L.jsl_batch_create_variants(self.instances[0].h, n_inst, om.ctypes.data, od.ctypes.data,
+                                                      lb.ctypes.data, mat.ctypes.data, self.B, self.device, seed,
+                                                      C.byref(self.cfg))
+        else:
+            arr = (C.c_void_p * len(self.instances))(*[i.h for i in self.instances])
+            self.h = self.L.jsl_batch_create(arr, len(self.instances), self.B, self.device, seed, C.byref(self.cfg))
+        if not self.h:
+            raise InvalidValue("batch", None, _err(self.L))
+        self.shape = abi.Shape()
+        self.L.jsl_batch_shape(self.h, C.byref(self.shape))
+        dev = torch.device("cuda", self.device)
+        ob = max(self.shape.obs_bytes, 16)
+        self.out = StepResult(
+            obs=torch.zeros((self.B, ob), dtype=torch.uint8, device=dev),
+            reward=torch.zeros(self.B, dtype=torch.float64, device=dev),
+            terminated=torch.zeros(self.B, dtype=torch.uint8, device=dev),
+            truncated=torch.zeros(self.B, dtype=torch.uint8, device=dev),
+            status=torch.zeros(self.B, dtype=torch.uint8, device=dev),
+            time=torch.zeros(self.B, dtype=torch.int32, device=dev),
+            makespan=torch.zeros(self.B, dtype=torch.int32, device=dev),
+            cand=torch.zeros((self.B, 4), dtype=torch.int16, device=dev),
+        )
+        self.rout = RolloutResult(
+            makespan=torch.zeros(self.B, dtype=torch.int32, device=dev),
+            n_steps=torch.zeros(self.B, dtype=torch.int32, device=dev),
+            ret=torch.zeros(self.B, dtype=torch.float64, device=dev),
+            status=torch.zeros(self.B, dtype=torch.uint8, device=dev),
+            no_op_count=torch.zeros(self.B, dtype=torch.int32, device=dev),
+        )
+        o = self.out
+        self._step_out = abi.StepOut(o.obs.data_ptr() if self.shape.obs_bytes else None, o.reward.data_ptr(),
+                                     o.terminated.data_ptr(), o.truncated.data_ptr(), o.status.data_ptr(),
+                                     o.time.data_ptr(), o.makespan.data_ptr(), o.cand.data_ptr())
+        r = self.rout
+        self._roll_out = abi.RolloutOut(r.makespan.data_ptr(), r.n_steps.data_ptr(), r.ret.data_ptr(),
+                                        r.status.data_ptr(), r.no_op_count.data_ptr())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.jsl_batch_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise InvalidValue("engine call", rc, _err(self.L))
+
+    def set_env_base(self, env_base: int):
+        self._check(self.L.jsl_batch_set_env_base(self.h, int(env_base)))
+
+    def reset(self, mask=None) -> StepResult:
+        ptr = None
+        if mask is not None:
+            assert mask.dtype == self.torch.uint8 and mask.is_cuda and mask.numel() == self.B
+            ptr = mask.data_ptr()
+        self._check(self.L.jsl_reset(self.h, ptr, self._step_out, self._stream()))
+        return self.out
+
+    def step(self, actions) -> StepResult:
+        assert actions.dtype == self.torch.uint8 and actions.is_cuda and actions.numel() == self.B
+        self._check(self.L.jsl_step(self.h, actions.data_ptr(), self._step_out, self._stream()))
+        return self.out
+
+    def rollout(self, policy, tape=None, max_steps: int = 1 << 30, reset_first=False, writeback=True) -> RolloutResult:
+        pol = abi.POLICIES[policy] if isinstance(policy, str) else int(policy)
+        ptr, stride = None, 0
+        if tape is not None:
+            assert tape.dtype == self.torch.uint8 and tape.is_cuda and tape.dim() == 2 and tape.shape[0] == self.B
+            tape = tape.contiguous()
+            ptr, stride = tape.data_ptr(), tape.shape[1]
+        flags = (RO_RESET_FIRST if reset_first else 0) | (0 if writeback else RO_NO_WRITEBACK)
+        self._check(self.L.jsl_rollout(self.h, pol, ptr, stride, int(min(max_steps, (1 << 31) - 1)), flags,
+                                       self._roll_out, self._stream()))
+        return self.rout
+
+    def get_state(self, idx: int) -> np.ndarray:
+        """Canonical int32 digest of env idx (synchronises)."""
+        out = np.zeros(self.shape.digest_cap, dtype=np.int32)
+        n = self.L.jsl_get_state(self.h, int(idx), out.ctypes.data, len(out))
+        if n < 0:
+            raise InvalidValue("jsl_get_state", n, _err(self.L))
+        return out[:n].copy()
+
+    def get_op_log(self, idx: int) -> np.ndarray:
+        out = np.zeros((self.shape.n_ops, 2), dtype=np.int32)
+        self._check(self.L.jsl_get_op_log(self.h, int(idx), out.ctypes.data))
+        return out
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.jsl_launch_count(self.h))
+
+    # ---- observation record -> named views (zero copy) -------------------------------------------------
+    def unpack_obs(self, obs=None) -> dict:
+        """Views into the packed observation record, keyed like the reference's observation dict
+        (jobshoplab/env/factories/observations.py:388-409, :507)."""
+        torch = self.torch
+        obs = self.out.obs if obs is None else obs
+        J, M, N = self.shape.n_jobs, self.shape.n_machines, self.shape.n_ops
+        if self.cfg.obs_kind == abi.OBS_OPERATION_ARRAY:
+            f = obs[:, : 16 + 4 * N + 4 * J].view(torch.float32)
+            return {"operation_state": f[:, 4: 4 + N].unsqueeze(1), "job_locations": f[:, 4 + N: 4 + N + J].unsqueeze(1),
+                    "current_transition": f[:, 0:3]}
+        o = 16
+        f = obs[:, :16].view(torch.float32)
+        jprog = obs[:, o: o + 4 * J].view(torch.int32); o += 4 * J
+        mprog = obs[:, o: o + 4 * M].view(torch.int32); o += 4 * M
+        jrun = obs[:, o: o + J].view(torch.int8); o += J
+        avail = obs[:, o: o + J].view(torch.int8); o += J
+        mrun = obs[:, o: o + M].view(torch.int8); o += M
+        execd = obs[:, o: o + J * M].view(torch.int8).view(-1, J, M)
+        return {"job_running": jrun, "job_executed_on_machine": execd, "job_progression": jprog,
+                "machine_running": mrun, "machine_progression": mprog, "available_jobs": avail,
+                "current_time": f[:, 0:1], "current_transition": f[:, 1:4]}

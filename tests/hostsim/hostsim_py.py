@@ -1,0 +1,105 @@
+"""ctypes wrapper of tests/hostsim/jsl_hostsim.cpp -- the CUDA engine source compiled for the CPU with
+loop primitives.  DEBUG / TEST TOOLING ONLY (see the .cpp header); never imported by the product."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from jobshoplab_b200 import abi
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+LIB = HERE / "libjsl_hostsim.so"
+_lib = None
+
+
+def build(force=False):
+    srcs = [HERE / "jsl_hostsim.cpp", ROOT / "jobshoplab_b200" / "csrc" / "jsl_engine.cuh",
+            ROOT / "include" / "jobshoplab_b200.h"]
+    if not force and LIB.exists() and LIB.stat().st_mtime >= max(s.stat().st_mtime for s in srcs):
+        return LIB
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
+                           "-Wno-unknown-pragmas", "-o", str(LIB), str(srcs[0])])
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(LIB))
+        L.jsh_create.restype = C.c_void_p
+        L.jsh_create.argtypes = [C.POINTER(abi.InstanceDesc), C.POINTER(abi.EnvCfg), C.c_uint64]
+        L.jsh_destroy.argtypes = [C.c_void_p]
+        L.jsh_reset.argtypes = [C.c_void_p]
+        L.jsh_step.argtypes = [C.c_void_p, C.c_int]
+        L.jsh_digest.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.jsh_obs.argtypes = [C.c_void_p, C.c_void_p]
+        L.jsh_rollout.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64]
+        L.jsh_scalars.argtypes = [C.c_void_p, C.c_void_p]
+        L.jsh_reward.argtypes = [C.c_void_p]
+        L.jsh_reward.restype = C.c_double
+        L.jsh_return.argtypes = [C.c_void_p]
+        L.jsh_return.restype = C.c_double
+        L.jsh_state_bytes.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class HostSimEnv:
+    def __init__(self, lowered, seed=0, **cfg):
+        self.L = lib()
+        self.li = lowered
+        self._desc = abi.make_desc(lowered)
+        cfg.setdefault("record_ops", True)
+        self._cfg = abi.make_cfg(**cfg)
+        self.h = self.L.jsh_create(C.byref(self._desc), C.byref(self._cfg), seed)
+        if not self.h:
+            raise RuntimeError("hostsim: unsupported shape")
+        self._obs_n = 16 + 16 * (lowered.n_jobs * lowered.n_machines + 8 * (lowered.n_jobs + lowered.n_machines) + 4 * lowered.n_ops)
+        self.reset()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.jsh_destroy(self.h)
+            self.h = None
+
+    def reset(self): return self.L.jsh_reset(self.h)
+    def step(self, a): return self.L.jsh_step(self.h, int(a))
+
+    def _sc(self):
+        o = np.zeros(8, dtype=np.int32)
+        self.L.jsh_scalars(self.h, o.ctypes.data)
+        return o
+
+    time = property(lambda s: int(s._sc()[0]))
+    terminated = property(lambda s: bool(s._sc()[1]))
+    truncated = property(lambda s: bool(s._sc()[2]))
+    status = property(lambda s: int(s._sc()[3]))
+    n_steps = property(lambda s: int(s._sc()[4]))
+    noop_count = property(lambda s: int(s._sc()[5]))
+    n_possible = property(lambda s: int(s._sc()[6]))
+    reward = property(lambda s: s.L.jsh_reward(s.h))
+    ret = property(lambda s: s.L.jsh_return(s.h))
+    done = property(lambda s: s.terminated or s.truncated)
+
+    def digest(self):
+        out = np.zeros(200000, dtype=np.int32)
+        n = self.L.jsh_digest(self.h, out.ctypes.data, len(out))
+        return out[:n].copy()
+
+    def obs(self) -> bytes:
+        out = np.zeros(self._obs_n, dtype=np.uint8)
+        n = self.L.jsh_obs(self.h, out.ctypes.data)
+        if n < 0:
+            raise RuntimeError(f"obs raised status {-n}")
+        return out[:n].tobytes()
+
+    def rollout(self, policy, tape=None, max_steps=1 << 30, env_idx=0):
+        if tape is not None:
+            tape = np.ascontiguousarray(tape, dtype=np.uint8)
+            return self.L.jsh_rollout(self.h, policy, tape.ctypes.data, len(tape), max_steps, env_idx)
+        return self.L.jsh_rollout(self.h, policy, None, 0, max_steps, env_idx)

@@ -1,0 +1,152 @@
+"""GPU parity: the CUDA engine, driven through the C ABI (jobshoplab_b200.engine -> libjsl_b200.so),
+against the golden traces of the unmodified reference and against the CPU oracle.
+
+Bit-exact bar: canonical state digest (incl. candidate list), reward (f64), flags, packed observation.
+Run on the B200 box with `pytest -m gpu`.
+"""
+import numpy as np
+import pytest
+
+import _golden as G
+from jobshoplab_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _engine():
+    from jobshoplab_b200 import engine
+    return engine
+
+
+EXC_TO_STATUS = {"BufferFullError": abi.ST_BUFFER_FULL, "UnsuccessfulStateMachineResult": abi.ST_UNSUCCESSFUL,
+                 "InvalidValue": abi.ST_NO_POSSIBLE, "NotImplementedError": abi.ST_OTHER_INVALID}
+
+
+def step_replay(sc: G.Scenario, B=5):
+    """Step mode: every env of a small batch gets the golden tape; env 0 and env B-1 are checked each step."""
+    eng = _engine()
+    batch = eng.Batch(sc.lowered, B, record_ops=True, **sc.cfg)
+    out = batch.reset()
+    torch.cuda.synchronize()
+    probe = (0, B - 1)
+    for e in probe:
+        assert G.hash_i32(batch.get_state(e)) == int(sc.state_hash[0]), "reset state"
+    obs = out.obs.cpu().numpy()
+    for e in probe:
+        assert G.hash_bytes(obs[e].tobytes()) == int(sc.obs_hash[0]), "reset obs"
+    n = sc.meta["n_steps"]
+    acts = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    for i in range(n):
+        acts.fill_(int(sc.actions[i]))
+        out = batch.step(acts)
+        st = out.status.cpu().numpy()
+        assert (st <= abi.ST_STEP_FAILED).all(), (i, st)
+        rew = out.reward.cpu().numpy(); tm = out.time.cpu().numpy()
+        term = out.terminated.cpu().numpy(); trunc = out.truncated.cpu().numpy()
+        obs = out.obs.cpu().numpy(); cand = out.cand.cpu().numpy()
+        for e in probe:
+            assert G.hash_i32(batch.get_state(e)) == int(sc.state_hash[i + 1]), f"state after step {i}"
+            assert rew[e] == float(sc.reward[i]), f"reward at step {i}"
+            assert tm[e] == int(sc.time[i + 1])
+            assert (int(term[e]) | (int(trunc[e]) << 1)) == int(sc.flags[i])
+            assert int(cand[e, 3]) == min(int(sc.n_possible[i + 1]), 32767)
+            assert G.hash_bytes(obs[e].tobytes()) == int(sc.obs_hash[i + 1]), f"obs after step {i}"
+    if sc.exception:
+        acts.fill_(int(sc.actions[n]))
+        st = batch.step(acts).status.cpu().numpy()
+        assert (st == EXC_TO_STATUS[sc.exception]).all(), (sc.exception, st)
+    else:
+        assert np.array_equal(batch.get_state(0), sc.final_digest)
+        mk = batch.out.makespan.cpu().numpy()
+        assert (mk == sc.meta["makespan"]).all()
+        acts.fill_(1)
+        st = batch.step(acts).status.cpu().numpy()
+        assert (st == abi.ST_ENV_DONE).all()  # env.py:441
+    batch.close()
+
+
+def _deterministic(group):
+    return [n for n in G.names(group) if G.Scenario(group, n).lowered.is_deterministic]
+
+
+SHORT = {"classic": ["2x2/fifo", "3x3/random0", "ft06/fifo", "ft06/spt", "ft06/random0", "ft10/mwkr", "la16/random1",
+                     "ft20/spt", "ta01/random0", "ta41/fifo", "swv16/fifo", "yn1/random0"],
+         "solutions": ["3x3/solution", "ft06/solution", "ft10/solution", "la01/solution", "ta01/solution"]}
+
+
+@pytest.mark.parametrize("group", ["classic", "solutions", "transport", "buffers", "features", "truncation", "oparray"])
+def test_step_mode_matches_reference_traces(group):
+    if group in SHORT:
+        names = SHORT[group]
+    else:
+        names = _deterministic(group)
+        if group == "transport":
+            names = [n for n in names if not n.startswith(("ta41", "la21"))] + ["ta41-t/random0", "la21-t/noearly/spt"]
+        if group == "buffers":
+            names = names[::3]
+    for name in names:
+        try:
+            step_replay(G.Scenario(group, name))
+        except AssertionError as ex:
+            raise AssertionError(f"{group}:{name}: {ex}") from ex
+
+
+@pytest.mark.parametrize("group", ["classic", "solutions", "transport", "buffers", "features", "truncation"])
+def test_rollout_tape_matches_reference(group):
+    """Rollout mode (state resident in shared memory for the whole episode): every deterministic golden
+    scenario of an instance becomes one env of a TAPE-policy batch; final makespan / steps / return /
+    status / no-op count / final digest must equal the reference's."""
+    eng = _engine()
+    by_inst = {}
+    for name in _deterministic(group):
+        sc = G.Scenario(group, name)
+        key = (sc.source_text, tuple(sorted(sc.cfg.items())))
+        by_inst.setdefault(key, []).append(sc)
+    for scs in by_inst.values():
+        B = len(scs)
+        L = max(len(s.actions) for s in scs) + 1
+        tape = np.ones((B, L), dtype=np.uint8)
+        for i, s in enumerate(scs):
+            tape[i, : len(s.actions)] = s.actions
+        batch = eng.Batch(scs[0].lowered, B, record_ops=True, **scs[0].cfg)
+        batch.reset()
+        r = batch.rollout("tape", tape=torch.from_numpy(tape).cuda())
+        mk, ns = r.makespan.cpu().numpy(), r.n_steps.cpu().numpy()
+        ret, st, noop = r.ret.cpu().numpy(), r.status.cpu().numpy(), r.no_op_count.cpu().numpy()
+        for i, s in enumerate(scs):
+            tag = f"{group}:{s.name}"
+            if s.exception:
+                assert st[i] == EXC_TO_STATUS[s.exception], tag
+                continue
+            assert ns[i] == s.meta["n_steps"], tag
+            assert mk[i] == s.meta["makespan"], tag
+            assert noop[i] == s.meta["no_op_count"], tag
+            assert ret[i] == float(np.sum(s.reward[: 0]) + sum(float(x) for x in s.reward)), tag
+            assert st[i] in (abi.ST_DONE, abi.ST_TRUNCATED), tag
+            assert np.array_equal(batch.get_state(i), s.final_digest), tag
+        batch.close()
+
+
+def test_rollout_policies_match_reference_rules():
+    """In-kernel FIFO / SPT / MWKR / RANDOM policies (dipatching_benchmark.py:17-67) reproduce the
+    makespans and step counts the reference's own rule drivers produced."""
+    eng = _engine()
+    for group in ("classic", "transport"):
+        for name in G.names(group):
+            pol = name.rsplit("/", 1)[1]
+            sc = G.Scenario(group, name)
+            B = 7
+            batch = eng.Batch(sc.lowered, B, seed=sc.meta.get("seed", 0), **sc.cfg)
+            if pol.startswith("random"):
+                batch.set_env_base(sc.meta.get("env_idx", 0) - 3)  # env 3 draws the golden Philox stream
+                r = batch.rollout("random", reset_first=True)
+                probe = [3]
+            else:
+                r = batch.rollout(pol, reset_first=True)
+                probe = range(B)
+            mk, ns = r.makespan.cpu().numpy(), r.n_steps.cpu().numpy()
+            for e in probe:
+                assert ns[e] == sc.meta["n_steps"] and mk[e] == sc.meta["makespan"], f"{group}:{name} env {e}"
+            batch.close()
