@@ -201,6 +201,11 @@ jsl_batch_t* jsl_batch_create_variants(const jsl_instance_t* tmpl, int64_t n_ins
                                        const int32_t* op_duration, const int32_t* lower_bound,
                                        const int32_t* max_allowed_time, int64_t B, int device, uint64_t seed,
                                        const jsl_env_cfg* cfg);
+/* Replace the operation tables of all n_inst variants of a batch from HOST arrays (pinned memory makes
+ * the copies asynchronous): the per-pass input of a synthetic-batch rollout.  Layout as in
+ * jsl_batch_create_variants; packed on the device by a small kernel on `stream`. */
+int jsl_batch_load_variants(jsl_batch_t*, const int32_t* op_machine, const int32_t* op_duration,
+                            const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream);
 void jsl_batch_destroy(jsl_batch_t*);
 int jsl_batch_shape(const jsl_batch_t*, jsl_shape* out);
 /* Global index of env 0 of this batch: the RANDOM policy draws from Philox stream (env_base + b), so a

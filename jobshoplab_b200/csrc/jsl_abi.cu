@@ -60,9 +60,38 @@ struct jsl_batch {
     int sm_count = 148;
     int smem_per_warp = 0;
     int rollout_ctas_per_sm = 0;
+    int32_t* d_stage = nullptr;   // [2][n_inst*N] + [2][n_inst] staging for jsl_batch_load_variants
+    int32_t* d_op_tool = nullptr; // [N]
 };
 
 namespace {
+
+// packs staged (machine, duration) tables into the engine layout and recomputes the per-job work sums
+__global__ void k_pack_variants(int64_t n_inst, int N, int J, const int32_t* __restrict__ job_op_start,
+                                const int32_t* __restrict__ op_tool, const int32_t* __restrict__ st_m,
+                                const int32_t* __restrict__ st_d, const int32_t* __restrict__ st_lb,
+                                const int32_t* __restrict__ st_mat, int32_t* op_mt, int32_t* op_dur,
+                                int32_t* job_work, int32_t* lb_mat) {
+    const int64_t total = n_inst * N;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int o = (int)(i % N);
+        op_mt[i] = st_m[i] | (op_tool[o] << 16);
+        op_dur[i] = st_d[i];
+    }
+    const int64_t nj = n_inst * J;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nj; i += stride) {
+        int64_t v = i / J;
+        int j = (int)(i % J);
+        int w = 0;
+        for (int o = job_op_start[j]; o < job_op_start[j + 1]; o++) w += st_d[v * N + o];
+        job_work[i] = w;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_inst; i += stride) {
+        lb_mat[2 * i] = st_lb[i];
+        lb_mat[2 * i + 1] = st_mat[i];
+    }
+}
 
 bool spec_is_static(const jsl_time_spec& sp, int n) {
     if (!sp.kind) return true;
@@ -171,6 +200,7 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     std::vector<uint8_t> jl, ml;
     lex_order("j", t->J, jl);
     lex_order("m", t->M, ml);
+    { const int32_t* tmp = nullptr; rc |= upload(b, t->op_tool, &tmp); b->d_op_tool = (int32_t*)tmp; }
     rc |= upload(b, jl, &I.job_lex);
     rc |= upload(b, ml, &I.mach_lex);
     if (rc) { jsl_batch_destroy(b); return nullptr; }
@@ -295,6 +325,32 @@ jsl_batch_t* jsl_batch_create_variants(const jsl_instance_t* tmpl, int64_t n_ins
                                        const jsl_env_cfg* cfg) {
     if (!tmpl || !op_machine || !op_duration || !lower_bound || !max_allowed_time || !cfg) { set_err("bad arguments"); return nullptr; }
     return build_batch(tmpl, n_inst, op_machine, op_duration, lower_bound, max_allowed_time, B, device, seed, cfg);
+}
+
+int jsl_batch_load_variants(jsl_batch_t* b, const int32_t* op_machine, const int32_t* op_duration,
+                            const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream) {
+    if (!b || !op_machine || !op_duration || !lower_bound || !max_allowed_time) return JSL_E_INVALID;
+    CK(cudaSetDevice(b->device));
+    const InstDev& I = b->bd.inst;
+    const size_t n = (size_t)I.n_inst * I.N, ni = (size_t)I.n_inst;
+    if (!b->d_stage) {
+        void* p = nullptr;
+        CK(cudaMalloc(&p, (2 * n + 2 * ni) * sizeof(int32_t)));
+        b->allocs.push_back(p);
+        b->d_stage = (int32_t*)p;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *sm = b->d_stage, *sd = sm + n, *sl = sd + n, *sa = sl + ni;
+    CK(cudaMemcpyAsync(sm, op_machine, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sd, op_duration, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sl, lower_bound, ni * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sa, max_allowed_time, ni * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    k_pack_variants<<<b->sm_count * 8, 256, 0, st>>>(I.n_inst, I.N, I.J, I.job_op_start, b->d_op_tool, sm, sd, sl, sa,
+                                                     (int32_t*)I.op_mt, (int32_t*)I.op_dur, (int32_t*)I.job_work,
+                                                     (int32_t*)I.lb_mat);
+    b->launches++;
+    CK(cudaGetLastError());
+    return JSL_OK;
 }
 
 void jsl_batch_destroy(jsl_batch_t* b) {

@@ -20,7 +20,7 @@ LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libjsl_b200.so"
 _lib = None
 
 ABI_SYMBOLS = ("jsl_last_error", "jsl_abi_version", "jsl_instance_create", "jsl_instance_destroy", "jsl_batch_create",
-               "jsl_batch_create_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base",
+               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base",
                "jsl_reset", "jsl_step", "jsl_rollout", "jsl_get_state", "jsl_get_op_log", "jsl_launch_count")
 
 RO_RESET_FIRST, RO_NO_WRITEBACK = 1, 2
@@ -46,6 +46,7 @@ def load_library():
     L.jsl_batch_create_variants.restype = C.c_void_p
     L.jsl_batch_create_variants.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int64, C.c_int, C.c_uint64, C.POINTER(abi.EnvCfg)]
+    L.jsl_batch_load_variants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.jsl_batch_destroy.argtypes = [C.c_void_p]
     L.jsl_batch_shape.argtypes = [C.c_void_p, C.POINTER(abi.Shape)]
     L.jsl_batch_set_env_base.argtypes = [C.c_void_p, C.c_int64]
@@ -182,6 +183,19 @@ class Batch:
 
     def set_env_base(self, env_base: int):
         self._check(self.L.jsl_batch_set_env_base(self.h, int(env_base)))
+
+    def load_variants(self, op_machine, op_duration, lower_bound, max_allowed_time):
+        """Upload new operation tables for every variant from HOST int32 tensors/arrays (pinned torch
+        tensors make the copies asynchronous on the current stream)."""
+        ptrs = []
+        for a in (op_machine, op_duration, lower_bound, max_allowed_time):
+            if hasattr(a, "data_ptr"):
+                assert not a.is_cuda and a.dtype == self.torch.int32 and a.is_contiguous()
+                ptrs.append(a.data_ptr())
+            else:
+                assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+                ptrs.append(a.ctypes.data)
+        self._check(self.L.jsl_batch_load_variants(self.h, *ptrs, self._stream()))
 
     def reset(self, mask=None) -> StepResult:
         ptr = None

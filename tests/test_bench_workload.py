@@ -1,0 +1,38 @@
+"""bench.py's synthetic workload: vectorised Taillard bounds == the compiler's (reference utils.py:310-352),
+instance slices are shard-invariant, and the CPU reference arm prints a valid line."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+from jobshoplab_b200 import compiler  # noqa: E402
+
+
+def test_bounds_match_compiler():
+    om, od = bench.make_instances(5)
+    lb, mat = bench.taillard_bounds(om, od)
+    for i in range(5):
+        jos = np.arange(0, bench.J * bench.M + 1, bench.M)
+        assert compiler._taillard_lower_bound(jos, om[i], od[i]) == lb[i]
+        assert od[i].sum() == mat[i]
+        assert sorted(om[i, :bench.M].tolist()) == list(range(bench.M))
+    assert od.min() >= 1 and od.max() <= 99
+
+
+def test_instances_are_shard_invariant():
+    a_m, a_d = bench.make_instances(16384 + 7)
+    b_m, b_d = bench.make_instances(7, first=16384)
+    assert np.array_equal(a_m[16384:], b_m) and np.array_equal(a_d[16384:], b_d)
+
+
+def test_reference_arm_line():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
+    d = json.loads(out)
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
