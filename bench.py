@@ -34,19 +34,24 @@ SEED = 0
 
 
 # ------------------------------------------------------------------------------------------- workload
+BLOCK = 4096  # instances are generated in aligned blocks so that instance i never depends on the slice asked for
+
+
 def make_instances(n: int, first: int = 0):
     """Taillard-style random 30x20 JSSPs: per job a uniform random machine permutation, durations
-    uniform in 1..99.  Instance i depends only on (1234, i): a counter-based Philox generator keyed by
-    the instance index, so shards generate their own slice."""
+    uniform in 1..99.  Block k (instances k*BLOCK ..) comes from its own counter-based Philox stream
+    (key 1234, counter word 3 = k), so any shard regenerates exactly its own slice."""
     om = np.empty((n, J * M), dtype=np.int32)
     od = np.empty((n, J * M), dtype=np.int32)
-    chunk = 16384
-    for a in range(0, n, chunk):
-        b = min(n, a + chunk)
-        rng = np.random.Generator(np.random.Philox(key=1234, counter=[0, 0, 0, first + a]))
-        keys = rng.random((b - a, J, M))
-        om[a:b] = np.argsort(keys, axis=2).reshape(b - a, J * M).astype(np.int32)
-        od[a:b] = rng.integers(1, 100, size=(b - a, J * M), dtype=np.int32)
+    k0, k1 = first // BLOCK, (first + n - 1) // BLOCK
+    for k in range(k0, k1 + 1):
+        rng = np.random.Generator(np.random.Philox(key=1234, counter=[0, 0, 0, k]))
+        keys = rng.random((BLOCK, J, M))
+        bm = np.argsort(keys, axis=2).reshape(BLOCK, J * M).astype(np.int32)
+        bd = rng.integers(1, 100, size=(BLOCK, J * M), dtype=np.int32)
+        lo, hi = max(first, k * BLOCK), min(first + n, (k + 1) * BLOCK)
+        om[lo - first:hi - first] = bm[lo - k * BLOCK:hi - k * BLOCK]
+        od[lo - first:hi - first] = bd[lo - k * BLOCK:hi - k * BLOCK]
     return om, od
 
 

@@ -25,9 +25,12 @@ def test_bounds_match_compiler():
 
 
 def test_instances_are_shard_invariant():
-    a_m, a_d = bench.make_instances(16384 + 7)
-    b_m, b_d = bench.make_instances(7, first=16384)
-    assert np.array_equal(a_m[16384:], b_m) and np.array_equal(a_d[16384:], b_d)
+    a_m, a_d = bench.make_instances(bench.BLOCK + 300)
+    b_m, b_d = bench.make_instances(200, first=bench.BLOCK - 50)
+    assert np.array_equal(a_m[bench.BLOCK - 50:bench.BLOCK + 150], b_m)
+    assert np.array_equal(a_d[bench.BLOCK - 50:bench.BLOCK + 150], b_d)
+    c_m, _ = bench.make_instances(3, first=10)
+    assert np.array_equal(a_m[10:13], c_m)
 
 
 def test_reference_arm_line():
