@@ -121,6 +121,8 @@ struct alignas(16) EnvS {
     uint8_t terminated, truncated, last_action_empty, obs_done;
     int32_t pad0[2];
     double ret;               // sum of rewards
+    // candidate masks of the state as of the last state-machine call (possible_transitions, unexpanded)
+    uint32_t c_p1[JW], c_idle[JW], c_lr[JW], c_li[JW];
     // jobs
     int32_t j_start[MJ], j_end[MJ];  // of the PROCESSING op
     uint32_t j_seq[MJ];              // order stamp inside the current buffer
@@ -322,13 +324,13 @@ JSL_D int travel_time(const InstDev& I, int a, int b) { return I.travel ? I.trav
 
 // ------------------------------------------------------------------------------------ buffers as (loc, seq)
 template <int JW>
-JSL_D int buf_count(const EnvS<JW>& s, const InstDev& I, int b) {
+JSL_DN int buf_count(const EnvS<JW>& s, const InstDev& I, int b) {
     return wp_ballot<JW>(I.J, [&](int j) { return s.j_loc[j] == b; }).count();
 }
 
 // buffer_type_utils.py:236-262 get_next_job_from_buffer; -1 = None
 template <int JW>
-JSL_D int next_job_from_buffer(const EnvS<JW>& s, const InstDev& I, int b) {
+JSL_DN int next_job_from_buffer(const EnvS<JW>& s, const InstDev& I, int b) {
     int ty = buf_type(I, b);
     if (ty == JSL_BUF_FLEX) return -1;
     // seq stamps are unique per env, so the stamp identifies the job
@@ -345,7 +347,7 @@ JSL_D int next_job_from_buffer(const EnvS<JW>& s, const InstDev& I, int b) {
 
 // buffer_type_utils.py:328-353 is_job_ready_for_pickup_from_postbuffer (uniform j)
 template <int JW>
-JSL_D bool ready_for_pickup(const EnvS<JW>& s, const InstDev& I, int j) {
+JSL_DN bool ready_for_pickup(const EnvS<JW>& s, const InstDev& I, int j) {
     int b = s.j_loc[j];
     bool right = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
     if (!right) return false;
@@ -449,6 +451,27 @@ JSL_D Trans nth_possible(const EnvS<JW>& s, const Ctx& c, const Poss<JW>& p, int
     t.kind = 1; t.comp = p.idle.nth(a); t.new_state = JSL_T_WORKING;
     t.job = q < nr ? p.lr.nth(q) : p.li.nth(q - nr);
     return t;
+}
+
+template <int JW>
+JSL_D Poss<JW> cached_poss(const EnvS<JW>& s) {
+    Poss<JW> p;
+#pragma unroll
+    for (int w = 0; w < JW; w++) { p.p1.w[w] = s.c_p1[w]; p.idle.w[w] = s.c_idle[w]; p.lr.w[w] = s.c_lr[w]; p.li.w[w] = s.c_li[w]; }
+    return p;
+}
+template <int JW>
+JSL_D void store_poss(EnvS<JW>& s, const Poss<JW>& p, bool clear) {
+#pragma unroll
+    for (int w = 0; w < JW; w++) {
+        s.c_p1[w] = clear ? 0u : p.p1.w[w]; s.c_idle[w] = clear ? 0u : p.idle.w[w];
+        s.c_lr[w] = clear ? 0u : p.lr.w[w]; s.c_li[w] = clear ? 0u : p.li.w[w];
+    }
+}
+// the candidate the agent is looking at: possible_transitions[0] after `skip` dropped ones
+template <int JW>
+JSL_D Trans current_candidate(const EnvS<JW>& s, const Ctx& c) {
+    return nth_possible(s, c, cached_poss(s), s.skip);
 }
 
 // ------------------------------------------------------------------------------------ outages
@@ -836,88 +859,101 @@ JSL_D bool create_timed(EnvS<JW>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm) {
 // ------------------------------------------------------------------------------------ state.step
 constexpr int TM_JUMP = 0, TM_FORCE = 1;
 
-template <int JW>
-JSL_D bool any_possible(const EnvS<JW>& s, const Ctx& c) {
-    Poss<JW> p = compute_poss(s, c);
-    return p.p1.any() || (p.idle.any() && (p.lr.any() || p.li.any()));
-}
-
-// state.py:154-295.  Returns success (false = validation error -> success=False); escaping
-// exceptions are left in c.raise.  On return s.n_possible / s.skip describe the new candidate list.
+// state.py:154-295 as ONE loop with a single call site per phase (the whole hot path has to stay
+// inside the instruction cache):
+//   stage 0 : the action's transition (0 or 1) is queued like a timed transition and applied
+//   stage 1+: candidates -> time machine -> timed transitions (+ teleports in the first batch) -> apply
+// The candidate masks computed at the top of the last iteration describe the final state (nothing
+// was applied after them), so they double as the new possible_transitions.
+// Returns success (false = validation error -> StateMachineResult.success=False); escaping exceptions
+// are left in c.raise.
 template <int JW>
 JSL_D bool sm_step(EnvS<JW>& s, Ctx& c, bool has_action, Trans act, int time_machine) {
     const InstDev& I = *c.I;
     c.now = s.time;
-    if (has_action) {
-        bool ok = act.kind == 0 ? apply_machine(s, c, act.comp, act.new_state, act.job)
-                                : apply_transport(s, c, act.comp, act.new_state, act.job);
-        if (c.raise) return true;
-        if (!ok) return false;
-    }
-    if (time_machine == TM_FORCE) c.now = force_jump_to_event(s, c);
-    else if (!any_possible(s, c)) c.now = force_jump_to_event(s, c);
-    if (c.raise) return true;
     Mask<1> mm;
-    Mask<JW> tm;
-    bool have = create_timed(s, c, mm, tm);
-    if (c.raise) return true;
-    // teleports (state.py:229-232, :414-467): i-th idle AGV <- i-th lonely job with zero travel time
-    Mask<JW> tele_idle, zr, zi;
-    {
-        Poss<JW> p = compute_poss(s, c);
-        tele_idle = p.idle;
-        bool active = p.idle.any();
-        Mask<JW> badm;
-        auto zero_travel = [&](int j, bool& bad) {
-            int cur = place_of_buf(I, s.j_loc[j]);
-            int nxt = next_idle_place(s, c, j);
-            if (nxt < 0) nxt = I.out_buf < 0 ? -2 : I.M + (I.out_buf - 3 * I.M - I.T);
-            if (nxt == -2) { bad = true; return false; }
-            if (cur == nxt) return true;
-            if (cur < 0) { bad = true; return false; }
-            int tt = travel_time(I, cur, nxt);
-            if (tt == JSL_NO_TIME) { bad = true; return false; }
-            return tt == 0;
-        };
-        zr = wp_ballot<JW>(I.J, [&](int j) { bool b = false; return active && p.lr.test(j) && zero_travel(j, b); });
-        zi = wp_ballot<JW>(I.J, [&](int j) { bool b = false; return active && p.li.test(j) && zero_travel(j, b); });
-        badm = wp_ballot<JW>(I.J, [&](int j) {
-            bool b = false;
-            if (active && (p.lr.test(j) || p.li.test(j))) zero_travel(j, b);
-            return b;
-        });
-        if (badm.any()) { c.raise = JSL_ST_OTHER_INVALID; return true; }
-    }
+    Mask<JW> tm, tele;
+    Poss<JW> p;
+    mm.w[0] = 0;
+#pragma unroll
+    for (int w = 0; w < JW; w++) { tm.w[w] = 0; tele.w[w] = 0; p.p1.w[w] = 0; p.idle.w[w] = 0; p.lr.w[w] = 0; p.li.w[w] = 0; }
+    bool action_stage = has_action;
     bool first = true;
     int guard = 0;
-    while (have || (first && tele_idle.any() && (zr.any() || zi.any()))) {
+#pragma unroll 1
+    for (;;) {
+        if (action_stage) {
+            if (act.kind == 0) {
+                s.x_mkind[act.comp] = (uint8_t)act.new_state; s.x_mjob[act.comp] = (uint8_t)act.job;
+                mm.w[0] = 1u << act.comp;
+            } else {
+                s.x_tkind[act.comp] = (uint8_t)act.new_state; s.x_tcomp[act.comp] = (uint8_t)act.comp;
+                s.x_tjob[act.comp] = (uint8_t)act.job;
+                tm.w[act.comp >> 5] = 1u << (act.comp & 31);
+            }
+        } else {
+            p = compute_poss(s, c);
+            // time machine: jump_to_event keeps `now` while something is possible (time_machines.py:61-130)
+            const bool anyp = p.p1.any() || (p.idle.any() && (p.lr.any() || p.li.any()));
+            if ((first && time_machine == TM_FORCE) || !anyp) c.now = force_jump_to_event(s, c);
+            if (c.raise) return true;
+            const bool have = create_timed(s, c, mm, tm);
+            if (c.raise) return true;
+            if (first && p.idle.any() && (p.lr.any() || p.li.any())) {
+                // teleports (state.py:229-232, :414-467): i-th idle AGV <- i-th lonely job with zero travel time
+                auto zero_travel = [&](int j, bool& bad) {
+                    int cur = place_of_buf(I, s.j_loc[j]);
+                    int nxt = next_idle_place(s, c, j);
+                    if (nxt < 0) nxt = I.out_buf < 0 ? -2 : I.M + (I.out_buf - 3 * I.M - I.T);
+                    if (nxt == -2) { bad = true; return false; }
+                    if (cur == nxt) return true;
+                    if (cur < 0) { bad = true; return false; }
+                    int tt = travel_time(I, cur, nxt);
+                    if (tt == JSL_NO_TIME) { bad = true; return false; }
+                    return tt == 0;
+                };
+                Mask<JW> zr = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.lr.test(j) && zero_travel(j, bd); });
+                Mask<JW> zi = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.li.test(j) && zero_travel(j, bd); });
+                if (I.travel || I.out_buf < 0) {
+                    Mask<JW> badm = wp_ballot<JW>(I.J, [&](int j) {
+                        bool bd = false;
+                        if (p.lr.test(j) || p.li.test(j)) zero_travel(j, bd);
+                        return bd;
+                    });
+                    if (badm.any()) { c.raise = JSL_ST_OTHER_INVALID; return true; }
+                }
+                Mask<JW> idle = p.idle;
+                while (idle.any() && (zr.any() || zi.any())) {
+                    int t = idle.pop_first();
+                    int j = zr.any() ? zr.pop_first() : zi.pop_first();
+                    s.x_tkind[t] = JSL_T_WORKING; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = (uint8_t)j;
+                    tele.w[t >> 5] |= 1u << (t & 31);
+                }
+            }
+            if (!have && !tele.any()) break;
+        }
+        // apply: machines, then timed transports, then teleports -- in creation order
         while (mm.any()) {
             int m = mm.pop_first();
             bool ok = apply_machine(s, c, m, s.x_mkind[m], s.x_mjob[m]);
             if (c.raise) return true;
             if (!ok) return false;
         }
-        while (tm.any()) {
-            int t = tm.pop_first();
-            bool ok = apply_transport(s, c, s.x_tcomp[t], s.x_tkind[t], s.x_tjob[t]);
-            if (c.raise) return true;
-            if (!ok) return false;
-        }
-        if (first) {
-            while (tele_idle.any() && (zr.any() || zi.any())) {
-                int t = tele_idle.pop_first();
-                int j = zr.any() ? zr.pop_first() : zi.pop_first();
-                bool ok = apply_transport(s, c, t, JSL_T_WORKING, j);
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ph++) {
+            Mask<JW> cur = ph == 0 ? tm : tele;
+            while (cur.any()) {
+                int t = cur.pop_first();
+                bool ok = apply_transport(s, c, s.x_tcomp[t], s.x_tkind[t], s.x_tjob[t]);
                 if (c.raise) return true;
                 if (!ok) return false;
             }
-            first = false;
         }
+#pragma unroll
+        for (int w = 0; w < JW; w++) { tm.w[w] = 0; tele.w[w] = 0; }
         JSL_SYNCWARP();
-        if (!any_possible(s, c)) c.now = force_jump_to_event(s, c);
-        if (c.raise) return true;
-        have = create_timed(s, c, mm, tm);
-        if (c.raise) return true;
+        if (action_stage) action_stage = false;
+        else first = false;
         if (++guard > 100000) { c.raise = JSL_ST_OTHER_INVALID; return true; }  // the reference would spin
     }
     s.time = c.now;
@@ -928,8 +964,9 @@ JSL_D bool sm_step(EnvS<JW>& s, Ctx& c, bool has_action, Trans act, int time_mac
         if (s.max_done_end >= 0) s.time = s.max_done_end;
         s.n_possible = 0;
     } else {
-        s.n_possible = compute_poss(s, c).total();
+        s.n_possible = p.total();
     }
+    store_poss(s, p, done);
     return true;
 }
 
@@ -974,17 +1011,6 @@ JSL_D void env_init(EnvS<JW>& s, Ctx& c) {
     JSL_SYNCWARP();
 }
 
-// env.py:456-545 + middleware.py:264-290: init + one dummy step (jump_to_event, no transitions)
-template <int JW>
-JSL_D void env_reset(EnvS<JW>& s, Ctx& c) {
-    env_init(s, c);
-    if (c.op_log) wp_for_dyn(2 * c.I->N, [&](int i) { c.op_log[i] = -1; });
-    Trans none = {0, 0, 0, 0};
-    bool ok = sm_step(s, c, false, none, TM_JUMP);
-    if (c.raise) { s.status = c.raise; return; }
-    if (!ok) s.n_possible = 0;
-}
-
 // ------------------------------------------------------------------------------------ reward / step
 // rewards.py:118-148 BinaryActionJsspReward.make, IEEE double without contraction
 template <int JW>
@@ -1005,42 +1031,51 @@ JSL_D double make_reward(EnvS<JW>& s, const Ctx& c) {
 #endif
 }
 
-// env.py:427-454 step + middleware.py:384-431 step + :304-368 _get_no_op_result.
-// `snap` receives the pre-step state image when the caller wants reference-exact rollback on a
-// failed step (step mode keeps the HBM copy instead and passes nullptr).
+// env.py:427-454 step + middleware.py:384-431 step + :304-368 _get_no_op_result, split around the single
+// sm_step call site of run_env_op().
+struct StepPlan {
+    bool run_sm, has_action;
+    int time_machine;
+    Trans act;
+};
+
+// everything before the state machine: argument checks, SubTimeStepper, what to run.
+// returns false when env.step raises before touching the state machine (status is set).
 template <int JW>
-JSL_D double env_step(EnvS<JW>& s, Ctx& c, int action) {
-    if (s.status > JSL_ST_TRUNCATED) return 0.0;             // a raise already escaped env.step
-    if (s.terminated || s.truncated) { s.status = JSL_ST_ENV_DONE; return 0.0; }  // env.py:441
+JSL_D bool env_step_pre(EnvS<JW>& s, Ctx& c, int action, StepPlan& plan) {
+    plan.run_sm = false; plan.has_action = false; plan.time_machine = TM_JUMP;
+    plan.act.kind = 0; plan.act.comp = 0; plan.act.new_state = 0; plan.act.job = 0;
+    if (s.status > JSL_ST_TRUNCATED) return false;                                     // a raise already escaped
+    if (s.terminated || s.truncated) { s.status = JSL_ST_ENV_DONE; return false; }     // env.py:441
     const int remaining = s.n_possible - s.skip;
-    if (remaining <= 0) { s.status = JSL_ST_NO_POSSIBLE; return 0.0; }             // actions.py:141
-    if (action != 0 && action != 1) { s.status = JSL_ST_ACTION_OUT_OF_SPACE; return 0.0; }
-    bool success = true, failed_keep = false;
-    const bool action_empty = action == 0;
+    if (remaining <= 0) { s.status = JSL_ST_NO_POSSIBLE; return false; }                // actions.py:141
+    if (action != 0 && action != 1) { s.status = JSL_ST_ACTION_OUT_OF_SPACE; return false; }
     if (action == 0) {
         s.step_noop = s.step_noop + 1;
-        if (remaining == 1) {
-            Trans none = {0, 0, 0, 0};
-            success = sm_step(s, c, false, none, TM_FORCE);
-            if (c.raise) { s.status = c.raise; return 0.0; }
-            if (!success) { s.status = JSL_ST_UNSUCCESSFUL; return 0.0; }  // old state is never done here
-            if (s.n_possible == 0) {
-                bool fin = !wp_ballot<JW>(c.I->J, [&](int j) { return !is_output(*c.I, s.j_loc[j]); }).any();
-                if (!fin) { s.status = JSL_ST_UNSUCCESSFUL; return 0.0; }    // middleware.py:344
-            } else {
-                if (c.C->truncation_active && s.step_action == 0) s.joker = s.joker - 1;  // :347
-                s.step_noop = 1; s.step_action = 0;                                       // :351
-            }
-        } else {
-            s.skip = s.skip + 1;  // :355-368 drop the first candidate; state machine not called
-        }
+        if (remaining == 1) { plan.run_sm = true; plan.time_machine = TM_FORCE; }       // middleware.py:333-336
+        else s.skip = s.skip + 1;                                                       // :355-368
     } else {
         s.step_action = s.step_action + 1;
-        Poss<JW> p = compute_poss(s, c);
-        Trans cand = nth_possible(s, c, p, s.skip);
-        success = sm_step(s, c, true, cand, TM_JUMP);
-        if (c.raise) { s.status = c.raise; return 0.0; }
-        failed_keep = !success;
+        plan.run_sm = true; plan.has_action = true;
+        plan.act = current_candidate(s, c);
+    }
+    return true;
+}
+
+// everything after it: middleware bookkeeping, terminated/truncated, reward.
+template <int JW>
+JSL_D double env_step_post(EnvS<JW>& s, Ctx& c, int action, const StepPlan& plan, bool success) {
+    if (c.raise) { s.status = c.raise; return 0.0; }
+    const bool action_empty = action == 0;
+    if (action == 0 && plan.run_sm) {
+        if (!success) { s.status = JSL_ST_UNSUCCESSFUL; return 0.0; }  // failed result, old state is not done
+        if (s.n_possible == 0) {
+            bool fin = !wp_ballot<JW>(c.I->J, [&](int j) { return !is_output(*c.I, s.j_loc[j]); }).any();
+            if (!fin) { s.status = JSL_ST_UNSUCCESSFUL; return 0.0; }                   // middleware.py:344
+        } else {
+            if (c.C->truncation_active && s.step_action == 0) s.joker = s.joker - 1;    // :347
+            s.step_noop = 1; s.step_action = 0;                                         // :351
+        }
     }
     if (success) {
         s.last_action_empty = action_empty;
@@ -1052,12 +1087,35 @@ JSL_D double env_step(EnvS<JW>& s, Ctx& c, int action) {
         s.obs_done = 1;
         s.truncated = 1; s.terminated = 0;
     }
-    (void)failed_keep;
     double r = make_reward(s, c);
     s.ret = s.ret + r;
     s.n_steps = s.n_steps + 1;
     s.status = !success ? JSL_ST_STEP_FAILED : s.terminated ? JSL_ST_DONE : s.truncated ? JSL_ST_TRUNCATED : JSL_ST_OK;
     return r;
+}
+
+// One env operation: OP_RESET (env.reset: init + dummy step) or an env.step(action).  The only place
+// sm_step is instantiated.
+constexpr int OP_RESET = -1;
+template <int JW>
+JSL_D double run_env_op(EnvS<JW>& s, Ctx& c, int op) {
+    StepPlan plan;
+    if (op == OP_RESET) {
+        env_init(s, c);
+        if (c.op_log) wp_for_dyn(2 * c.I->N, [&](int i) { c.op_log[i] = -1; });
+        plan.run_sm = true; plan.has_action = false; plan.time_machine = TM_JUMP;
+        plan.act.kind = 0; plan.act.comp = 0; plan.act.new_state = 0; plan.act.job = 0;
+    } else if (!env_step_pre(s, c, op, plan)) {
+        return 0.0;
+    }
+    bool success = true;
+    if (plan.run_sm) success = sm_step(s, c, plan.has_action, plan.act, plan.time_machine);
+    if (op == OP_RESET) {
+        if (c.raise) s.status = c.raise;
+        else if (!success) { s.n_possible = 0; s.skip = 0; }
+        return 0.0;
+    }
+    return env_step_post(s, c, op, plan, success);
 }
 
 // ------------------------------------------------------------------------------------ policies
@@ -1083,8 +1141,7 @@ JSL_D int policy_action(const EnvS<JW>& s, const Ctx& c, int policy, uint64_t se
     const InstDev& I = *c.I;
     if (policy == JSL_POLICY_RANDOM) return (int)philox_bit(seed, env_idx, (uint32_t)s.n_steps);
     if (policy == JSL_POLICY_FIFO || s.n_possible - s.skip <= 0) return 1;
-    Poss<JW> p = compute_poss(s, c);
-    Trans cand = nth_possible(s, c, p, s.skip);
+    Trans cand = current_candidate(s, c);
     if (cand.kind == 1) return 1;
     const int pre = 3 * cand.comp, cj = cand.job;
     auto key = [&](int j) {
@@ -1118,8 +1175,7 @@ template <int JW>
 JSL_D void cand_floats(const EnvS<JW>& s, const Ctx& c, float* tr) {
     const InstDev& I = *c.I;
     if (!s.obs_done && s.n_possible - s.skip > 0) {
-        Poss<JW> p = compute_poss(s, c);
-        Trans cand = nth_possible(s, c, p, s.skip);
+        Trans cand = current_candidate(s, c);
         int comp_idx = cand.kind == 0 ? cand.comp : I.M + cand.comp;
         tr[0] = (float)((double)comp_idx / (double)(I.M + I.T));
         tr[1] = (float)((double)cand.job / (double)I.J);
@@ -1267,7 +1323,7 @@ JSL_D int write_digest(const EnvS<JW>& s, const Ctx& c, int32_t* out, int cap) {
     if (remaining < 0) remaining = 0;
     JSL_PUT(remaining);
     if (remaining > 0) {
-        Poss<JW> p = compute_poss(s, c);
+        Poss<JW> p = cached_poss(s);
         for (int i = 0; i < remaining; i++) {
             Trans t = nth_possible(s, c, p, s.skip + i);
             JSL_PUT(t.kind); JSL_PUT(t.comp); JSL_PUT(t.new_state); JSL_PUT(t.job);

@@ -67,8 +67,7 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW>& s, Ctx& c, const 
     int16_t cd[4] = {-1, -1, -1, 0};
     int remaining = s.n_possible - s.skip;
     if (out.cand && remaining > 0 && status <= JSL_ST_TRUNCATED) {
-        Poss<JW> p = compute_poss(s, c);
-        Trans t = nth_possible(s, c, p, s.skip);
+        Trans t = current_candidate(s, c);
         cd[0] = (int16_t)t.kind; cd[1] = (int16_t)t.comp; cd[2] = (int16_t)t.job;
         cd[3] = (int16_t)(remaining > 32767 ? 32767 : remaining);
     }
@@ -99,7 +98,7 @@ k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, j
     void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
     Ctx c;
     make_ctx<JW>(c, bd, env, outs_sm);
-    env_reset(s, c);
+    run_env_op(s, c, OP_RESET);
     __syncwarp();
     write_step_out(s, c, out, env, 0.0, obs_bytes);
     __syncwarp();
@@ -123,7 +122,7 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     Ctx c;
     make_ctx<JW>(c, bd, env, outs_sm);
     const int action = actions[env];
-    double r = env_step(s, c, action);
+    double r = run_env_op(s, c, action);
     __syncwarp();
     if (s.status >= JSL_ST_STEP_FAILED) {
         // success=False / an escaping exception: the reference keeps the OLD state (state.py:202-210);
@@ -162,9 +161,8 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
         uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
         Ctx c;
         make_ctx<JW>(c, bd, env, outs_sm);
-        if (flags & JSL_RO_RESET_FIRST) {
-            env_reset(s, c);
-        } else {
+        bool pending_reset = (flags & JSL_RO_RESET_FIRST) != 0;
+        if (!pending_reset) {
             copy_in<JW>(&s, g_state, bd.state_stride);
             if (g_outs) copy_in<JW>(outs_sm, g_outs, bd.outs_stride);
         }
@@ -172,17 +170,24 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
         const int32_t* job_work = bd.inst.job_work + (env % bd.inst.n_inst) * bd.inst.J;
         const uint8_t* my_tape = tape ? tape + env * tape_stride : nullptr;
         int n = 0;
-        while (n < max_steps && s.status == JSL_ST_OK) {
-            int a;
-            if (policy == JSL_POLICY_TAPE) {
-                if (s.n_steps >= tape_stride) break;
-                a = my_tape[s.n_steps];
+#pragma unroll 1
+        for (;;) {
+            int op;
+            if (pending_reset) {
+                op = OP_RESET;
             } else {
-                a = policy_action(s, c, policy, bd.seed, (uint64_t)(bd.env_base + env), job_work);
+                if (n >= max_steps || s.status != JSL_ST_OK) break;
+                if (policy == JSL_POLICY_TAPE) {
+                    if (s.n_steps >= tape_stride) break;
+                    op = my_tape[s.n_steps];
+                } else {
+                    op = policy_action(s, c, policy, bd.seed, (uint64_t)(bd.env_base + env), job_work);
+                }
+                n++;
             }
-            env_step(s, c, a);
+            run_env_op(s, c, op);
+            pending_reset = false;
             __syncwarp();
-            n++;
         }
         if (JSL_LANE == 0) {
             if (out.makespan) out.makespan[env] = s.time;

@@ -62,7 +62,7 @@ template <int JW> void make_ctx(Sim* s, Ctx& c) {
 template <int JW> int do_reset(Sim* s) {
     EnvS<JW>& st = *(EnvS<JW>*)s->state.data();
     Ctx c; make_ctx<JW>(s, c);
-    env_reset(st, c);
+    run_env_op(st, c, OP_RESET);
     s->last_reward = 0.0;
     return st.status;
 }
@@ -70,7 +70,7 @@ template <int JW> int do_step(Sim* s, int action) {
     EnvS<JW>& st = *(EnvS<JW>*)s->state.data();
     s->backup = s->state; s->outs_backup = s->outs;
     Ctx c; make_ctx<JW>(s, c);
-    double r = env_step(st, c, action);
+    double r = run_env_op(st, c, action);
     if (st.status >= JSL_ST_STEP_FAILED) {  // same rollback as k_step
         int status = st.status, n_steps = st.n_steps, rn = st.reward_noop, sa = st.step_action, sn = st.step_noop;
         double ret = st.ret;
@@ -102,7 +102,7 @@ template <int JW> int do_rollout(Sim* s, int policy, const uint8_t* tape, int n_
         int a;
         if (policy == JSL_POLICY_TAPE) { if (st.n_steps >= n_tape) break; a = tape[st.n_steps]; }
         else a = policy_action(st, c, policy, s->seed, env_idx, s->job_work.data());
-        env_step(st, c, a);
+        run_env_op(st, c, a);
         n++;
     }
     return n;
