@@ -16,7 +16,9 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 INCLUDE = Path(__file__).resolve().parent.parent / "include"
-LIB = CSRC / "libjsl_b200.so"
+LIB = Path(os.environ.get("JSL_LIB_OUT", CSRC / "libjsl_b200.so"))
+EXTRA = os.environ.get("JSL_NVCC_EXTRA", "").split()
+OBJ_TAG = os.environ.get("JSL_OBJ_TAG", "")
 UNITS = ["jsl_abi.cu", "jsl_kernels_jw1.cu", "jsl_kernels_jw2.cu", "jsl_kernels_jw4.cu"]
 HEADERS = [CSRC / "jsl_engine.cuh", CSRC / "jsl_kernels.cuh", INCLUDE / "jobshoplab_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
@@ -31,12 +33,12 @@ def nvcc() -> str:
 
 
 def _compile(unit: str, force: bool) -> Path:
-    src, obj = CSRC / unit, CSRC / (unit[:-3] + ".o")
+    src, obj = CSRC / unit, CSRC / (unit[:-3] + OBJ_TAG + ".o")
     newest = max(p.stat().st_mtime for p in [src, *HEADERS])
     if not force and obj.exists() and obj.stat().st_mtime >= newest:
         return obj
-    log = subprocess.run([nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
-    (CSRC / (unit[:-3] + ".ptxas.log")).write_text(log.stderr)
+    log = subprocess.run([nvcc(), *NVCC_FLAGS, *EXTRA, "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
+    (CSRC / (unit[:-3] + OBJ_TAG + ".ptxas.log")).write_text(log.stderr)
     if log.returncode != 0:
         raise RuntimeError(f"nvcc failed for {unit}:\n{log.stderr[-4000:]}")
     return obj
@@ -46,7 +48,8 @@ def build(force: bool = False) -> Path:
     with ThreadPoolExecutor(len(UNITS)) as ex:
         objs = list(ex.map(lambda u: _compile(u, force), UNITS))
     if force or not LIB.exists() or LIB.stat().st_mtime < max(o.stat().st_mtime for o in objs):
-        subprocess.check_call([nvcc(), "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"])
+        subprocess.check_call([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB),
+                               *map(str, objs), "-lcudart"])
     return LIB
 
 

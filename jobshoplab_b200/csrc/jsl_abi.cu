@@ -141,6 +141,7 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
                          const jsl_env_cfg* cfg) {
     if (B <= 0 || n_inst <= 0) { set_err("B and n_inst must be positive"); return nullptr; }
     if (t->M > 32) { set_err("unsupported: more than 32 machines"); return nullptr; }
+    if (t->S > 32) { set_err("unsupported: more than 32 standalone buffers"); return nullptr; }
     int jt = t->J > t->T ? t->J : t->T;
     if (jt > 128 || t->J > 250 || t->T > 250) { set_err("unsupported: more than 128 jobs/transports"); return nullptr; }
     if (3 * t->M + t->T + t->S > 65000) { set_err("unsupported: too many buffers"); return nullptr; }
@@ -215,6 +216,10 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
         if (t->sbuf_role[s] == JSL_ROLE_OUTPUT) { I.out_buf = 3 * t->M + t->T + s; break; }
     I.default_tool = t->default_tool;
     I.start_time = t->start_time;
+    I.sb0 = 3 * t->M + t->T;
+    I.out_mask = 0;
+    for (int sb = 0; sb < t->S; sb++)
+        if (t->sbuf_role[sb] == JSL_ROLE_OUTPUT) I.out_mask |= 1u << sb;
     I.flex_pre = all_equal(t->pre_type, JSL_BUF_FLEX);
     I.flex_post = all_equal(t->post_type, JSL_BUF_FLEX) && all_equal(t->sbuf_type, JSL_BUF_FLEX);
     I.caps_inf = all_equal(t->pre_cap, JSL_CAP_INF) && all_equal(t->post_cap, JSL_CAP_INF) && all_equal(t->sbuf_cap, JSL_CAP_INF);

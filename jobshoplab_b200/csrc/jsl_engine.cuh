@@ -94,6 +94,8 @@ struct InstDev {
     int flex_post;    // every postbuffer and standalone buffer is FLEX -> "ready" needs no position test
     int caps_inf;     // no finite capacity anywhere
     int has_m_out, has_t_out;
+    int sb0;           // 3M+T: index of the first standalone buffer
+    uint32_t out_mask; // bit s set: standalone buffer s has the OUTPUT role (S <= 32)
 };
 
 struct CfgDev {
@@ -119,7 +121,8 @@ struct alignas(16) EnvS {
     int32_t max_done_end;     // max end_time over DONE ops (state.py:270-275)
     int32_t status;           // JSL_ST_*
     uint8_t terminated, truncated, last_action_empty, obs_done;
-    int32_t pad0[2];
+    int32_t all_out;          // core_utils.is_done of the current state
+    int32_t pad0[1];
     double ret;               // sum of rewards
     // candidate masks of the state as of the last state-machine call (possible_transitions, unexpanded)
     uint32_t c_p1[JW], c_idle[JW], c_lr[JW], c_li[JW];
@@ -164,6 +167,7 @@ struct Ctx {
     int raise;              // JSL_ST_* of an escaping exception, 0 = none
     int now;
     int lower_bound, max_allowed_time;
+    double neg_inv_n;       // -1.0 / N: the dense reward of a penalised step (rewards.py:135-138)
 };
 
 #define JSL_RAISE(c, code)          \
@@ -308,11 +312,9 @@ JSL_D int buf_cap(const InstDev& I, int b) {
     if (b < 3 * I.M + I.T) return 1;
     return I.sbuf_cap[b - 3 * I.M - I.T];
 }
-JSL_D bool is_standalone(const InstDev& I, int b) { return b >= 3 * I.M + I.T; }
+JSL_D bool is_standalone(const InstDev& I, int b) { return b >= I.sb0; }
 JSL_D bool is_agv_buf(const InstDev& I, int b) { return b >= 3 * I.M && b < 3 * I.M + I.T; }
-JSL_D bool is_output(const InstDev& I, int b) {
-    return b >= 3 * I.M + I.T && I.sbuf_role[b - 3 * I.M - I.T] == JSL_ROLE_OUTPUT;
-}
+JSL_D bool is_output(const InstDev& I, int b) { return b >= I.sb0 && ((I.out_mask >> (b - I.sb0)) & 1u); }
 // place of a buffer: machine for machine buffers, M+s for standalone, -1 for an AGV buffer
 JSL_D int place_of_buf(const InstDev& I, int b) {
     if (b < 3 * I.M) return b / 3;
@@ -610,12 +612,14 @@ JSL_D int t_general(int st) { return st == JSL_T_IDLE ? 0 : st == JSL_T_OUTAGE ?
 // validate.py:85-118 + transitions.py:82-107,161-186
 template <int JW>
 JSL_D bool transport_valid(const EnvS<JW>& s, int t, int to) {
-    int from = s.t_state[t];
-    if (from == to && from != JSL_T_WAITINGPICKUP) return false;
-    int gf = t_general(from), gt = t_general(to);
-    if (gf == 0) return gt == 1;
-    if (gf == 1) return gt == 2 || gt == 1;
-    return gt == 0;
+    // bit (from*6 + to): idle->running, running->running|outage (same state only for WAITINGPICKUP), outage->idle
+    constexpr uint64_t R = (1ull << JSL_T_WORKING) | (1ull << JSL_T_PICKUP) | (1ull << JSL_T_TRANSIT) | (1ull << JSL_T_WAITINGPICKUP);
+    constexpr uint64_t RO = R | (1ull << JSL_T_OUTAGE);
+    constexpr uint64_t TABLE = (R << (6 * JSL_T_IDLE)) | ((RO & ~(1ull << JSL_T_WORKING)) << (6 * JSL_T_WORKING)) |
+                               ((RO & ~(1ull << JSL_T_PICKUP)) << (6 * JSL_T_PICKUP)) |
+                               ((RO & ~(1ull << JSL_T_TRANSIT)) << (6 * JSL_T_TRANSIT)) |
+                               ((1ull << JSL_T_IDLE) << (6 * JSL_T_OUTAGE)) | (RO << (6 * JSL_T_WAITINGPICKUP));
+    return (TABLE >> (s.t_state[t] * 6 + to)) & 1ull;
 }
 
 JSL_D int output_place(Ctx& c) {
@@ -799,42 +803,34 @@ JSL_D bool create_timed(EnvS<JW>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm) {
             }
         }
     }
-    {   // a due machine with an empty buffer: machine.buffer.store[0] raises IndexError
-        Mask<1> bad = wp_ballot<1>(I.M, [&](int m) { return mm.test(m) && s.x_mjob[m] == NONE8; });
-        if (bad.any()) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, false);
-    }
-    // transports
-    Mask<JW> need_ready, td, bad_t;
+    // (a due machine with an empty buffer -- IndexError in the reference -- is caught by the handlers: job == NONE8)
+    // transports (a PICKUP/WAITINGPICKUP transport without a job or a TRANSIT one without cargo -- raises in
+    // the reference -- is caught by the handlers: job == NONE8)
+    Mask<JW> need_ready, td;
+    const bool flex_post = I.flex_post != 0;
     tm = wp_ballot<JW>(I.T, [&](int t) {
         s.x_tkind[t] = NONE8;
         if (s.t_occkind[t] != OCC_TIME || s.t_occ[t] > now) return false;
         int st = s.t_state[t];
-        if (st == JSL_T_PICKUP) { s.x_tkind[t] = JSL_T_WAITINGPICKUP; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = s.t_job[t]; return true; }
-        if (st == JSL_T_WAITINGPICKUP) { s.x_tkind[t] = JSL_T_WAITINGPICKUP; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = s.t_job[t]; return true; }
-        if (st == JSL_T_TRANSIT) { s.x_tkind[t] = JSL_T_OUTAGE; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = s.t_carry[t]; return true; }
-        if (st == JSL_T_OUTAGE) { s.x_tkind[t] = JSL_T_IDLE; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = NONE8; return true; }
-        return false;
+        if (st == JSL_T_IDLE || st == JSL_T_WORKING) return false;
+        int kind = JSL_T_WAITINGPICKUP, job = s.t_job[t];
+        if (st == JSL_T_WAITINGPICKUP) {
+            if (flex_post && job != NONE8) {  // handler.py:191-252: ready <=> in a postbuffer / standalone buffer
+                int b = s.j_loc[job];
+                if (is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1)) kind = JSL_T_TRANSIT;
+            }
+        } else if (st == JSL_T_TRANSIT) { kind = JSL_T_OUTAGE; job = s.t_carry[t]; }
+        else if (st == JSL_T_OUTAGE) { kind = JSL_T_IDLE; job = NONE8; }
+        s.x_tkind[t] = (uint8_t)kind; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = (uint8_t)job;
+        return true;
     });
     JSL_SYNCWARP();
-    need_ready = wp_ballot<JW>(I.T, [&](int t) { return tm.test(t) && s.t_state[t] == JSL_T_WAITINGPICKUP; });
-    bad_t = wp_ballot<JW>(I.T, [&](int t) {
-        if (s.t_occkind[t] == OCC_TIME && s.t_occ[t] <= now && s.t_state[t] == JSL_T_WORKING) return true;
-        if (!tm.test(t)) return false;
-        int st = s.t_state[t];
-        if ((st == JSL_T_PICKUP || st == JSL_T_WAITINGPICKUP) && s.t_job[t] == NONE8) return true;  // TransportJobError
-        if (st == JSL_T_TRANSIT && s.t_carry[t] == NONE8) return true;
-        return false;
-    });
-    if (bad_t.any()) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, false);
-    while (need_ready.any()) {  // handler.py:191-252: WAITINGPICKUP & ready -> TRANSIT
-        int t = need_ready.pop_first();
-        int j = s.t_job[t];
-        bool ready;
-        if (I.flex_post) {
-            int b = s.j_loc[j];
-            ready = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
-        } else ready = ready_for_pickup(s, I, j);
-        if (ready) s.x_tkind[t] = JSL_T_TRANSIT;
+    if (!flex_post) {
+        need_ready = wp_ballot<JW>(I.T, [&](int t) { return tm.test(t) && s.t_state[t] == JSL_T_WAITINGPICKUP && s.t_job[t] != NONE8; });
+        while (need_ready.any()) {  // handler.py:191-252: WAITINGPICKUP & ready -> TRANSIT
+            int t = need_ready.pop_first();
+            if (ready_for_pickup(s, I, s.t_job[t])) s.x_tkind[t] = JSL_T_TRANSIT;
+        }
     }
     if (!I.flex_post) {  // handler.py:278-326,356-359 resolved TimeDependency -> stored transition
         td = wp_ballot<JW>(I.T, [&](int t) { return s.t_occkind[t] == OCC_TD; });
@@ -966,6 +962,7 @@ JSL_D bool sm_step(EnvS<JW>& s, Ctx& c, bool has_action, Trans act, int time_mac
     } else {
         s.n_possible = p.total();
     }
+    s.all_out = done ? 1 : 0;
     store_poss(s, p, done);
     return true;
 }
@@ -976,7 +973,7 @@ JSL_D void env_init(EnvS<JW>& s, Ctx& c) {
     const InstDev& I = *c.I;
     s.time = I.start_time; s.seq_ctr = 0; s.n_possible = 0; s.skip = 0;
     s.joker = c.C->truncation_joker; s.step_noop = 0; s.step_action = 0; s.reward_noop = 0;
-    s.n_steps = 0; s.noop_count = 0; s.max_done_end = -1; s.status = JSL_ST_OK;
+    s.n_steps = 0; s.noop_count = 0; s.max_done_end = -1; s.status = JSL_ST_OK; s.all_out = 0;
     s.terminated = 0; s.truncated = 0; s.last_action_empty = 1; s.obs_done = 0;
     s.ret = 0.0;
     JSL_SYNCWARP();
@@ -1021,7 +1018,7 @@ JSL_D double make_reward(EnvS<JW>& s, const Ctx& c) {
     else sr = (double)(c.max_allowed_time - s.time) / (double)(c.max_allowed_time - c.lower_bound);
     if (s.last_action_empty) s.reward_noop = s.reward_noop + 1;
     else s.reward_noop = 0;
-    double dr = (double)(-(s.reward_noop >= c.I->J ? 1 : 0)) / (double)c.I->N;
+    const double dr = s.reward_noop >= c.I->J ? c.neg_inv_n : 0.0;  // -int(flag) / N
 #if defined(__CUDACC__) && !defined(JSL_HOST_SIM)
     return __dadd_rn(__dmul_rn(sr, c.C->sparse_bias), __dmul_rn(dr, c.C->dense_bias));
 #else
@@ -1070,8 +1067,7 @@ JSL_D double env_step_post(EnvS<JW>& s, Ctx& c, int action, const StepPlan& plan
     if (action == 0 && plan.run_sm) {
         if (!success) { s.status = JSL_ST_UNSUCCESSFUL; return 0.0; }  // failed result, old state is not done
         if (s.n_possible == 0) {
-            bool fin = !wp_ballot<JW>(c.I->J, [&](int j) { return !is_output(*c.I, s.j_loc[j]); }).any();
-            if (!fin) { s.status = JSL_ST_UNSUCCESSFUL; return 0.0; }                   // middleware.py:344
+            if (!s.all_out) { s.status = JSL_ST_UNSUCCESSFUL; return 0.0; }             // middleware.py:344
         } else {
             if (c.C->truncation_active && s.step_action == 0) s.joker = s.joker - 1;    // :347
             s.step_noop = 1; s.step_action = 0;                                         // :351
@@ -1081,7 +1077,7 @@ JSL_D double env_step_post(EnvS<JW>& s, Ctx& c, int action, const StepPlan& plan
         s.last_action_empty = action_empty;
         s.obs_done = (s.n_possible - s.skip) == 0;
         s.noop_count = s.noop_count + (action_empty ? 1 : 0);
-        s.terminated = !wp_ballot<JW>(c.I->J, [&](int j) { return !is_output(*c.I, s.j_loc[j]); }).any();
+        s.terminated = s.all_out != 0;
         s.truncated = s.joker < 0;
     } else {
         s.obs_done = 1;

@@ -16,6 +16,12 @@
 namespace jsl {
 
 constexpr int WARPS_PER_CTA = 4;
+#ifndef JSL_ROLLOUT_MIN_CTAS
+#define JSL_ROLLOUT_MIN_CTAS 10  // resident CTAs per SM the rollout kernel is register-budgeted for
+#endif
+#ifndef JSL_STEP_MIN_CTAS
+#define JSL_STEP_MIN_CTAS 12
+#endif
 
 struct BatchDev {
     InstDev inst;
@@ -51,6 +57,7 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
     c.now = 0;
     c.lower_bound = I.lb_mat[2 * v];
     c.max_allowed_time = I.lb_mat[2 * v + 1];
+    c.neg_inv_n = -1.0 / (double)I.N;
 }
 
 template <int JW>
@@ -107,7 +114,7 @@ k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, j
 }
 
 template <int JW>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_STEP_MIN_CTAS)
 k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
@@ -148,7 +155,7 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
 }
 
 template <int JW>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_ROLLOUT_MIN_CTAS)
 k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __restrict__ tape, int64_t tape_stride,
           int max_steps, int flags, jsl_rollout_out out) {
     extern __shared__ __align__(16) uint8_t smem[];

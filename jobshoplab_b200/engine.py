@@ -16,7 +16,9 @@ from . import abi
 from .exceptions import EngineUnavailable, InvalidValue
 from .lowered import LoweredInstance
 
-LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libjsl_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("JSL_LIB", Path(__file__).resolve().parent / "csrc" / "libjsl_b200.so"))
 _lib = None
 
 ABI_SYMBOLS = ("jsl_last_error", "jsl_abi_version", "jsl_instance_create", "jsl_instance_destroy", "jsl_batch_create",

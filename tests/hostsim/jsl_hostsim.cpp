@@ -56,7 +56,7 @@ template <int JW> void make_ctx(Sim* s, Ctx& c) {
     c.I = &s->I; c.C = &s->C; c.op_mt = s->op_mt.data(); c.op_dur = s->op_dur.data();
     c.op_log = s->C.record_ops ? s->op_log.data() : nullptr;
     c.outs = s->outs_bytes ? (void*)s->outs.data() : nullptr;
-    c.raise = 0; c.now = 0; c.lower_bound = s->lb_mat[0]; c.max_allowed_time = s->lb_mat[1];
+    c.raise = 0; c.now = 0; c.lower_bound = s->lb_mat[0]; c.max_allowed_time = s->lb_mat[1]; c.neg_inv_n = -1.0 / (double)s->I.N;
 }
 
 template <int JW> int do_reset(Sim* s) {
@@ -162,6 +162,8 @@ void* jsh_create(const jsl_instance_desc* d, const jsl_env_cfg* cfg, uint64_t se
     I.out_buf = -1;
     for (int b = 0; b < I.S; b++) if (s->sbuf_role[b] == JSL_ROLE_OUTPUT) { I.out_buf = 3 * I.M + I.T + b; break; }
     I.default_tool = d->default_tool; I.start_time = d->start_time;
+    I.sb0 = 3 * I.M + I.T; I.out_mask = 0;
+    for (int b = 0; b < I.S && b < 32; b++) if (s->sbuf_role[b] == JSL_ROLE_OUTPUT) I.out_mask |= 1u << b;
     I.flex_pre = all_eq8(s->pre_type, JSL_BUF_FLEX);
     I.flex_post = all_eq8(s->post_type, JSL_BUF_FLEX) && all_eq8(s->sbuf_type, JSL_BUF_FLEX);
     I.caps_inf = all_eq(s->pre_cap, JSL_CAP_INF) && all_eq(s->post_cap, JSL_CAP_INF) && all_eq(s->sbuf_cap, JSL_CAP_INF);
