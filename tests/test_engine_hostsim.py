@@ -1,0 +1,66 @@
+"""CPU-side check of the CUDA engine SOURCE: jobshoplab_b200/csrc/jsl_engine.cuh compiled with loop
+primitives (tests/hostsim) must reproduce the oracle / the reference traces step by step.  This catches
+logic errors in the kernel code without a GPU; the GPU parity tests (test_cuda_parity.py) then cover the
+real warp execution.  The product never loads this build."""
+import numpy as np
+import pytest
+
+import _golden as G
+from hostsim.hostsim_py import HostSimEnv
+from jobshoplab_b200 import abi
+
+PICK = {
+    "classic": ["2x2/fifo", "3x3/random0", "ft06/spt", "ft06/random1", "ft10/mwkr", "la16/random0", "ft20/fifo",
+                "ta01/random0", "ta41/spt", "swv16/fifo", "yn1/random0"],
+    "solutions": ["3x3/solution", "ft06/solution", "ft10/solution", "la16/solution", "ta01/solution", "dmu35/solution"],
+    "transport": ["ft06-t/fifo", "ft06-t/noearly/random0", "ft10-t/spt", "la01-t/noearly/mwkr", "ft20-t/random1",
+                  "ta41-t/noearly/random0"],
+}
+EXC_TO_STATUS = {"BufferFullError": abi.ST_BUFFER_FULL, "UnsuccessfulStateMachineResult": abi.ST_UNSUCCESSFUL,
+                 "InvalidValue": abi.ST_NO_POSSIBLE, "NotImplementedError": abi.ST_OTHER_INVALID}
+
+
+def replay(sc):
+    e = HostSimEnv(sc.lowered, **sc.cfg)
+    assert G.hash_i32(e.digest()) == int(sc.state_hash[0]), "reset"
+    assert G.hash_bytes(e.obs()) == int(sc.obs_hash[0]), "reset obs"
+    n = sc.meta["n_steps"]
+    for i in range(n):
+        st = e.step(int(sc.actions[i]))
+        assert st <= abi.ST_STEP_FAILED
+        assert G.hash_i32(e.digest()) == int(sc.state_hash[i + 1]), f"state after step {i}"
+        assert e.reward == float(sc.reward[i]), f"reward at step {i}"
+        assert (int(e.terminated) | (int(e.truncated) << 1)) == int(sc.flags[i])
+        assert e.n_possible == int(sc.n_possible[i + 1])
+        assert G.hash_bytes(e.obs()) == int(sc.obs_hash[i + 1]), f"obs after step {i}"
+    if sc.exception:
+        assert e.step(int(sc.actions[n])) == EXC_TO_STATUS[sc.exception]
+    else:
+        assert np.array_equal(e.digest(), sc.final_digest)
+        assert e.noop_count == sc.meta["no_op_count"]
+
+
+@pytest.mark.parametrize("group", ["classic", "solutions", "transport", "buffers", "features", "truncation", "oparray"])
+def test_engine_source_matches_reference_traces(group):
+    names = PICK.get(group)
+    if names is None:
+        names = [n for n in G.names(group) if G.Scenario(group, n).lowered.is_deterministic]
+        if group == "buffers":
+            names = names[::2]
+    for name in names:
+        try:
+            replay(G.Scenario(group, name))
+        except AssertionError as ex:
+            raise AssertionError(f"{group}:{name}: {ex}") from ex
+
+
+def test_engine_policies():
+    for name in ("ft06/spt", "ft10/mwkr", "la16/spt", "ta01/fifo", "ft06/random2"):
+        sc = G.Scenario("classic", name)
+        pol = name.rsplit("/", 1)[1]
+        e = HostSimEnv(sc.lowered, seed=sc.meta.get("seed", 0))
+        if pol.startswith("random"):
+            e.rollout(abi.POLICY_RANDOM, env_idx=sc.meta["env_idx"])
+        else:
+            e.rollout(abi.POLICIES[pol])
+        assert e.n_steps == sc.meta["n_steps"] and e.time == sc.meta["makespan"], name

@@ -1,0 +1,121 @@
+"""JobShopLabEnv / BatchedJobShopLabEnv on the GPU, used the way the reference's own tests use
+jobshoplab.JobShopLabEnv (tests/end_to_end_tests/test_env_end_to_end.py, tests/unit_tests/test_env.py)."""
+import random
+
+import numpy as np
+import pytest
+
+import _golden as G
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _env(group, name, **cfg_over):
+    from jobshoplab_b200 import Config, JobShopLabEnv
+    from jobshoplab_b200 import compiler as C
+
+    sc = G.Scenario(group, name)
+    cfg = Config()
+    for k, v in cfg_over.items():
+        if k == "allow_early_transport":
+            cfg.state_machine.allow_early_transport = v
+    repo = C.DslStrRepository(sc.source_text) if sc.kind != "spec" else None
+    comp = C.Compiler(cfg, repo=repo) if repo else C.compile_spec_text(sc.source_text)
+    return JobShopLabEnv(config=cfg, compiler=comp), sc
+
+
+def test_optimal_solution_replay_protocol():
+    """test_env_end_to_end.py:72-105 against the env API, with the solution sequence recovered from the
+    golden tape's accepted (machine, job, time) triples."""
+    env, sc = _env("solutions", "ft06/solution")
+    terminated = False
+    for a in sc.actions.tolist():
+        ev = env.state.possible_transitions[0]
+        assert ev.component_id.startswith(("m-", "t-")) and ev.job_id.startswith("j-")
+        obs, reward, terminated, truncated, info = env.step(int(a))
+    assert terminated and not truncated
+    assert env.state.state.time.time == 55 == info["makespan"]  # ft06 optimum, BASELINE.md 2b
+    assert info["no_op_count"] == sc.meta["no_op_count"]
+    from jobshoplab_b200.exceptions import EnvDone
+    with pytest.raises(EnvDone):
+        env.step(1)
+    log = env.op_log()
+    assert log.shape == (36, 2) and (log[:, 1] > log[:, 0]).all() and log[:, 1].max() == 55
+    env.close()
+
+
+def test_random_episodes_terminate_and_reset():
+    """test_env_end_to_end.py:42-55: random actions, terminated != truncated, reset, repeat."""
+    env, _ = _env("classic", "3x3/fifo")
+    rng = random.Random(0)
+    for _ in range(5):
+        while not env.done:
+            obs, r, term, trunc, info = env.step(rng.randint(0, 1))
+        assert term != trunc
+        assert set(obs) == {"job_running", "job_executed_on_machine", "job_progression", "machine_running",
+                            "machine_progression", "available_jobs", "current_time", "current_transition"}
+        assert obs["current_transition"].tolist() == [1.0, 1.0, 1.0]
+        env.reset()
+        assert not env.done
+    env.close()
+
+
+def test_buffer_full_escapes_step_like_the_reference():
+    from jobshoplab_b200.exceptions import BufferFullError
+
+    name = next(n for n in G.names("buffers") if G.Scenario("buffers", n).exception == "BufferFullError")
+    env, sc = _env("buffers", name, allow_early_transport=sc_cfg(name))
+    with pytest.raises(BufferFullError):
+        for a in sc.actions.tolist():
+            env.step(int(a))
+    env.close()
+
+
+def sc_cfg(name):
+    return G.Scenario("buffers", name).cfg.get("allow_early_transport", True)
+
+
+def test_batched_env_auto_reset_and_views():
+    from jobshoplab_b200 import BatchedJobShopLabEnv, Config
+
+    sc = G.Scenario("classic", "ft06/fifo")
+    B = 257
+    env = BatchedJobShopLabEnv(Config(), num_envs=B, instances=sc.lowered, auto_reset=True)
+    obs, out = env.reset()
+    assert obs["job_executed_on_machine"].shape == (B, 6, 6) and obs["current_time"].shape == (B, 1)
+    acts = torch.ones(B, dtype=torch.uint8, device="cuda")
+    finished = 0
+    for _ in range(36 * 3):
+        obs, rew, term, trunc, out = env.step(acts)
+        finished += int(term.sum())
+        mk = out.makespan[term.bool()]
+        assert (mk == 68).all()  # ft06 always-accept makespan, BASELINE.md 2a
+    assert finished == 3 * B
+    assert int(out.status.max()) <= 1
+    r = env.rollout("mwkr", reset_first=True)
+    assert (r.makespan == 83).all() and (r.n_steps == 46).all()
+    assert env.state(5).state.time.time == 83
+    env.close()
+
+
+def test_multi_instance_batch_and_variants():
+    """Several same-shaped instances in one batch: env b runs instance b % n_inst."""
+    from jobshoplab_b200 import engine
+
+    a = G.Scenario("classic", "ft10/spt")
+    b = G.Scenario("classic", "la16/spt")
+    batch = engine.Batch([a.lowered, b.lowered], 10)
+    r = batch.rollout("spt", reset_first=True)
+    mk = r.makespan.cpu().numpy()
+    assert (mk[0::2] == 1074).all() and (mk[1::2] == 1156).all()
+    om = np.stack([a.lowered.op_machine, b.lowered.op_machine, a.lowered.op_machine])
+    od = np.stack([a.lowered.op_duration, b.lowered.op_duration, a.lowered.op_duration])
+    lb = np.array([a.lowered.lower_bound, b.lowered.lower_bound, a.lowered.lower_bound], dtype=np.int32)
+    mat = np.array([a.lowered.max_allowed_time, b.lowered.max_allowed_time, a.lowered.max_allowed_time], dtype=np.int32)
+    v = engine.Batch(a.lowered, 9, variants=(om, od, lb, mat))
+    mk = v.rollout("fifo", reset_first=True).makespan.cpu().numpy()
+    assert mk.tolist() == [1262, 1230, 1262] * 3
+    v.load_variants(torch.from_numpy(od * 0 + om).pin_memory(), torch.from_numpy(od[::-1].copy()).pin_memory(),
+                    torch.from_numpy(lb), torch.from_numpy(mat))
+    batch.close(); v.close()

