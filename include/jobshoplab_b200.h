@@ -131,6 +131,12 @@ typedef struct jsl_instance_desc {
     const int32_t* t_outage_dur;   /* [n_t_outages] */
     /* stochastic behaviour of each family (index-aligned with the arrays above) */
     jsl_time_spec op_spec, setup_spec, travel_spec, m_ofreq_spec, m_odur_spec, t_ofreq_spec, t_odur_spec;
+    /* sample tables of the stochastic time objects (jobshoplab_b200/stochastic.py): value of a time object
+     * for numpy seed k = sample_table[sample_row[obj]][k]; obj in flat order ops | setup | travel | machine
+     * outage freq | dur | transport outage freq | dur.  NULL for deterministic instances. */
+    const int32_t* sample_table; /* [n_sample_rows][sample_depth] */
+    const int32_t* sample_row;   /* [n time objects], -1 = static */
+    int32_t n_sample_rows, sample_depth;
     /* constants computed once on the host (utils.py:310-352) */
     int32_t lower_bound;
     int32_t max_allowed_time;
@@ -208,6 +214,15 @@ int jsl_batch_load_variants(jsl_batch_t*, const int32_t* op_machine, const int32
                             const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream);
 void jsl_batch_destroy(jsl_batch_t*);
 int jsl_batch_shape(const jsl_batch_t*, jsl_shape* out);
+/* Stochastic instances (stochasticy_models.py): by default every StochasticTimeConfig.update() draws from
+ * the reference's own sample function (first variate of numpy default_rng(start seed + n), tabulated).  For bit-exact replay against
+ * the reference, hand in the recorded update() results instead: dev int32 [B][stride], consumed in call
+ * order (NULL switches back to Philox).  Takes effect at the next jsl_reset. */
+int jsl_batch_set_sample_tape(jsl_batch_t*, const int32_t* dev_tape, int64_t stride);
+/* numpy start seeds (stochasticy_models.py:12) of every time object, dev int32 [B][n time objects] in the
+ * flat order above (-1 / ignored for static objects): makes a free-running episode reproduce the reference
+ * run that had these seeds.  NULL (default): seeds are drawn uniformly from 0..30 per env from Philox. */
+int jsl_batch_set_start_seeds(jsl_batch_t*, const int32_t* dev_seeds);
 /* Global index of env 0 of this batch: the RANDOM policy draws from Philox stream (env_base + b), so a
  * job sharded over several GPUs reproduces the single-GPU action streams. */
 int jsl_batch_set_env_base(jsl_batch_t*, int64_t env_base);

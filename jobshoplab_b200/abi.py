@@ -42,6 +42,7 @@ class InstanceDesc(C.Structure):
         ("op_spec", TimeSpecC), ("setup_spec", TimeSpecC), ("travel_spec", TimeSpecC),
         ("m_ofreq_spec", TimeSpecC), ("m_odur_spec", TimeSpecC), ("t_ofreq_spec", TimeSpecC),
         ("t_odur_spec", TimeSpecC),
+        ("sample_table", _i32p), ("sample_row", _i32p), ("n_sample_rows", C.c_int32), ("sample_depth", C.c_int32),
         ("lower_bound", C.c_int32), ("max_allowed_time", C.c_int32),
     ]
 
@@ -100,6 +101,13 @@ def make_desc(li: LoweredInstance) -> InstanceDesc:
     for name in ("op_spec", "setup_spec", "travel_spec", "m_ofreq_spec", "m_odur_spec",
                  "t_ofreq_spec", "t_odur_spec"):
         setattr(d, name, _spec(getattr(li, name)))
+    if not li.is_deterministic:
+        if getattr(li, "_sample_tables", None) is None:
+            from .stochastic import sample_tables
+            li._sample_tables = sample_tables(li)
+        table, row = li._sample_tables
+        d.sample_table, d.sample_row = _p(table), _p(row)
+        d.n_sample_rows, d.sample_depth = table.shape
     d.lower_bound, d.max_allowed_time = li.lower_bound, li.max_allowed_time
     return d
 

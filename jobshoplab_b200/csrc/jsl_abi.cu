@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "jsl_kernels.cuh"
+#include "jsl_tobj.hpp"
 
 using namespace jsl;
 
@@ -45,6 +46,7 @@ struct jsl_instance {
         m_outage_start, m_outage_freq, m_outage_dur, t_outage_freq, t_outage_dur;
     int default_tool, start_time, lower_bound, max_allowed_time;
     bool stochastic;
+    TobjTables tobj;
 };
 
 struct jsl_batch {
@@ -147,7 +149,7 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     if (3 * t->M + t->T + t->S > 65000) { set_err("unsupported: too many buffers"); return nullptr; }
     for (int j = 0; j < t->J; j++)
         if (t->job_op_start[j + 1] - t->job_op_start[j] > 250) { set_err("unsupported: more than 250 ops per job"); return nullptr; }
-    if (t->stochastic) { set_err("unsupported: stochastic time behaviour on device (deterministic instances only)"); return nullptr; }
+    if (t->stochastic && n_inst != 1) { set_err("unsupported: stochastic instances need a single-instance batch"); return nullptr; }
     if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); return nullptr; }
     jsl_batch* b = new jsl_batch();
     b->device = device;
@@ -202,6 +204,19 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     lex_order("j", t->J, jl);
     lex_order("m", t->M, ml);
     { const int32_t* tmp = nullptr; rc |= upload(b, t->op_tool, &tmp); b->d_op_tool = (int32_t*)tmp; }
+    if (t->stochastic) {
+        rc |= upload(b, t->tobj.kind, &I.tobj_kind);
+        rc |= upload(b, t->tobj.base, &I.tobj_base);
+        rc |= upload(b, t->tobj.param, &I.tobj_param);
+        rc |= upload(b, t->tobj.init, &I.tobj_init);
+        I.n_tobj = t->tobj.n; I.off_setup = t->tobj.off_setup; I.off_travel = t->tobj.off_travel;
+        I.off_mof = t->tobj.off_mof; I.off_mod = t->tobj.off_mod; I.off_tof = t->tobj.off_tof; I.off_tod = t->tobj.off_tod;
+        if (t->tobj.sample_depth > 0) {
+            rc |= upload(b, t->tobj.sample_table, &I.sample_table);
+            rc |= upload(b, t->tobj.sample_row, &I.sample_row);
+            I.sample_depth = t->tobj.sample_depth;
+        }
+    }
     rc |= upload(b, jl, &I.job_lex);
     rc |= upload(b, ml, &I.mach_lex);
     if (rc) { jsl_batch_destroy(b); return nullptr; }
@@ -240,6 +255,13 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     if (b->bd.outs_stride) {
         if (cudaMalloc(&p, (size_t)B * os) != cudaSuccess) { set_err("cudaMalloc(outs) failed"); jsl_batch_destroy(b); return nullptr; }
         b->allocs.push_back(p); b->bd.outs = (uint8_t*)p;
+    }
+    if (t->stochastic) {
+        if (cudaMalloc(&p, (size_t)B * t->tobj.n * sizeof(int32_t)) != cudaSuccess) { set_err("cudaMalloc(tcur) failed"); jsl_batch_destroy(b); return nullptr; }
+        b->allocs.push_back(p); b->bd.tcur = (int32_t*)p;
+        if (cudaMalloc(&p, (size_t)B * t->tobj.n * sizeof(uint16_t)) != cudaSuccess) { set_err("cudaMalloc(tseed) failed"); jsl_batch_destroy(b); return nullptr; }
+        b->allocs.push_back(p); b->bd.tseed = (uint16_t*)p;
+        cudaMemset(p, 0, (size_t)B * t->tobj.n * sizeof(uint16_t));
     }
     if (cfg->record_ops) {
         if (cudaMalloc(&p, (size_t)B * N * 2 * sizeof(int32_t)) != cudaSuccess) { set_err("cudaMalloc(op_log) failed"); jsl_batch_destroy(b); return nullptr; }
@@ -285,6 +307,7 @@ jsl_instance_t* jsl_instance_create(const jsl_instance_desc* d) {
     cp(t->t_outage_freq, d->t_outage_freq, d->n_t_outages); cp(t->t_outage_dur, d->t_outage_dur, d->n_t_outages);
     t->default_tool = d->default_tool; t->start_time = d->start_time;
     t->lower_bound = d->lower_bound; t->max_allowed_time = d->max_allowed_time;
+    t->tobj = make_tobj(*d);
     t->stochastic = !(spec_is_static(d->op_spec, t->N) && spec_is_static(d->setup_spec, t->M * t->NT * t->NT) &&
                       spec_is_static(d->travel_spec, NP * NP) && spec_is_static(d->m_ofreq_spec, n_mo) &&
                       spec_is_static(d->m_odur_spec, n_mo) && spec_is_static(d->t_ofreq_spec, d->n_t_outages) &&
@@ -371,6 +394,19 @@ int jsl_batch_shape(const jsl_batch_t* b, jsl_shape* out) {
     out->n_jobs = I.J; out->n_machines = I.M; out->n_transports = I.T; out->n_sbuf = I.S; out->n_ops = I.N;
     out->n_tools = I.NT; out->obs_bytes = b->obs_bytes; out->state_bytes = b->bd.state_stride + b->bd.outs_stride;
     out->digest_cap = b->digest_cap;
+    return JSL_OK;
+}
+
+int jsl_batch_set_sample_tape(jsl_batch_t* b, const int32_t* dev_tape, int64_t stride) {
+    if (!b || (dev_tape && stride <= 0)) return JSL_E_INVALID;
+    b->bd.tape = dev_tape;
+    b->bd.tape_stride = dev_tape ? stride : 0;
+    return JSL_OK;
+}
+
+int jsl_batch_set_start_seeds(jsl_batch_t* b, const int32_t* dev_seeds) {
+    if (!b) return JSL_E_INVALID;
+    b->bd.start_seeds = dev_seeds;
     return JSL_OK;
 }
 

@@ -28,7 +28,7 @@
 #if defined(__CUDACC__) && !defined(JSL_HOST_SIM)
 #define JSL_D __device__ __forceinline__
 #define JSL_M __device__ __forceinline__
-#define JSL_DN __device__ __noinline__
+#define JSL_DN static __device__ __noinline__
 #define JSL_LANE ((int)(threadIdx.x & 31))
 #define JSL_SYNCWARP() __syncwarp()
 #define JSL_POPC(x) __popc(x)
@@ -94,6 +94,17 @@ struct InstDev {
     int flex_post;    // every postbuffer and standalone buffer is FLEX -> "ready" needs no position test
     int caps_inf;     // no finite capacity anywhere
     int has_m_out, has_t_out;
+    // stochastic time objects (stochasticy_models.py): one flat table over every time object of the
+    // instance -- ops [0,N), setup, travel, machine-outage freq/dur, transport-outage freq/dur.
+    // nullptr for deterministic instances (the static tables above are used directly).
+    const uint8_t* tobj_kind;   // [n_tobj] JSL_TIME_*
+    const int32_t* tobj_base;   // [n_tobj] base_time
+    const float* tobj_param;    // [n_tobj] offset | std | scale
+    const int32_t* tobj_init;   // [n_tobj] .time at compile time
+    const int32_t* sample_table; // [rows][sample_depth]: value of a time object for numpy seed k
+    const int32_t* sample_row;   // [n_tobj] row of each object, -1 = static
+    int sample_depth;
+    int n_tobj, off_setup, off_travel, off_mof, off_mod, off_tof, off_tod;
     int sb0;           // 3M+T: index of the first standalone buffer
     uint32_t out_mask; // bit s set: standalone buffer s has the OUTPUT role (S <= 32)
 };
@@ -122,7 +133,7 @@ struct alignas(16) EnvS {
     int32_t status;           // JSL_ST_*
     uint8_t terminated, truncated, last_action_empty, obs_done;
     int32_t all_out;          // core_utils.is_done of the current state
-    int32_t pad0[1];
+    int32_t draw_ctr;         // StochasticTimeConfig.update() calls so far (tape position / Philox counter)
     double ret;               // sum of rewards
     // candidate masks of the state as of the last state-machine call (possible_transitions, unexpanded)
     uint32_t c_p1[JW], c_idle[JW], c_lr[JW], c_li[JW];
@@ -168,6 +179,12 @@ struct Ctx {
     int now;
     int lower_bound, max_allowed_time;
     double neg_inv_n;       // -1.0 / N: the dense reward of a penalised step (rewards.py:135-138)
+    int32_t* tcur;          // [n_tobj] this env's current .time of every time object, or nullptr (deterministic)
+    uint16_t* tseed;        // [n_tobj] this env's current numpy seed of every stochastic time object
+    const int32_t* start_seeds;  // [n_tobj] recorded start seeds, or nullptr (drawn 0..30 from Philox)
+    const int32_t* tape;    // replayed update() results, or nullptr (table mode)
+    int tape_len;
+    uint64_t seed, env_id;  // Philox key / stream of this env
 };
 
 #define JSL_RAISE(c, code)          \
@@ -476,17 +493,143 @@ JSL_D Trans current_candidate(const EnvS<JW>& s, const Ctx& c) {
     return nth_possible(s, c, cached_poss(s), s.skip);
 }
 
+// ------------------------------------------------------------------------------------ time objects
+// .time of a time object (no resample)
+JSL_D int op_duration(const Ctx& c, int o) { return c.tcur ? c.tcur[o] : c.op_dur[o]; }
+JSL_D int setup_time_cur(const Ctx& c, int i) {
+    if (c.tcur) return c.tcur[c.I->off_setup + i];
+    return c.I->setup ? c.I->setup[i] : 0;
+}
+JSL_D int travel_time_cur(const Ctx& c, int a, int b) {
+    if (c.tcur) return c.tcur[c.I->off_travel + a * c.I->NP + b];
+    return c.I->travel ? c.I->travel[a * c.I->NP + b] : 0;
+}
+
+struct Rng4 { uint32_t x, y, z, w; };
+JSL_D Rng4 philox4(uint64_t seed, uint64_t stream, uint32_t c0, uint32_t c1) {
+    uint32_t a = c0, b = c1, cc = (uint32_t)stream, d = (uint32_t)(stream >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll 1
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * a;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * cc;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ b ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ d ^ k1;
+        b = (uint32_t)p1; d = (uint32_t)p0; a = n0; cc = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Rng4 o = {a, b, cc, d};
+    return o;
+}
+JSL_D double u01(uint32_t r) { return ((double)r + 0.5) * (1.0 / 4294967296.0); }
+
+// one draw of a stochastic time object in Philox mode: stochasticy_models.py:44-121, then max(0, .)
+// (:15,:30).  Distribution-exact, not stream-compatible with numpy; uses sub-counter k
+// of draw `n` of stream `env` for rejection loops.
+JSL_DN int draw_time(uint64_t seed, uint64_t env, uint32_t n, int kind, int base, float param) {
+    double v = (double)base;
+    if (kind == JSL_TIME_UNIFORM) {
+        Rng4 r = philox4(seed, env, n, 1u << 16);
+        double lo = (double)base - (double)param, hi = (double)base + (double)param;
+        v = trunc(lo + (hi - lo) * u01(r.x));
+    } else if (kind == JSL_TIME_GAUSSIAN) {
+        Rng4 r = philox4(seed, env, n, 1u << 16);
+        double z = sqrt(-2.0 * log(u01(r.x))) * cos(6.283185307179586 * u01(r.y));
+        v = trunc((double)base + (double)param * z);
+    } else if (kind == JSL_TIME_POISSON) {
+        const double lam = (double)base + 0.5;
+        int k = 0;
+        if (lam < 10.0) {  // inversion by sequential search
+            Rng4 r = philox4(seed, env, n, 1u << 16);
+            double u = u01(r.x), p = exp(-lam), cdf = p;
+            while (u > cdf && k < 1000) { k++; p *= lam / (double)k; cdf += p; }
+        } else {  // PTRS, Hoermann 1993
+            const double slam = sqrt(lam), loglam = log(lam);
+            const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+            const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+            for (uint32_t it = 0;; it++) {
+                Rng4 r = philox4(seed, env, n, (1u << 16) + it);
+                double U = u01(r.x) - 0.5, V = u01(r.y);
+                double us = 0.5 - fabs(U);
+                k = (int)floor((2.0 * a / us + b) * U + lam + 0.43);
+                if (us >= 0.07 && V <= vr) break;
+                if (k < 0 || (us < 0.013 && V > us)) { if (it > 64) { k = (int)lam; break; } continue; }
+                if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + (double)k * loglam - lgamma((double)k + 1.0)) break;
+                if (it > 64) { k = (int)lam; break; }
+            }
+        }
+        v = (double)base + (double)k;
+    } else if (kind == JSL_TIME_GAMMA) {  // gamma(shape = base_time, scale): Marsaglia & Tsang 2000
+        double shape = (double)base, g = 0.0;
+        if (shape > 0.0) {
+            const bool boost = shape < 1.0;
+            const double sh = boost ? shape + 1.0 : shape;
+            const double dd = sh - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+            for (uint32_t it = 0;; it++) {
+                Rng4 r = philox4(seed, env, n, (1u << 16) + it);
+                double z = sqrt(-2.0 * log(u01(r.x))) * cos(6.283185307179586 * u01(r.y));
+                double t = 1.0 + cc * z;
+                if (t <= 0.0) { if (it > 64) { g = dd; break; } continue; }
+                t = t * t * t;
+                double u = u01(r.z);
+                if (log(u) < 0.5 * z * z + dd - dd * t + dd * log(t) || it > 64) {
+                    g = dd * t;
+                    if (boost) g *= pow(u01(r.w), 1.0 / shape);
+                    break;
+                }
+            }
+        }
+        v = rint((double)base + g * (double)param);  // Python round(): half to even
+    }
+    if (!(v > 0.0)) v = 0.0;
+    if (v > 2.0e9) v = 2.0e9;
+    return (int)v;
+}
+
+// StochasticTimeConfig.update() of time object `idx` (stochasticy_models.py:27-30): a new sample becomes
+// its .time.  Static objects just return their time.
+JSL_D int tobj_update(Ctx& c, int32_t& draw_ctr, int idx, int static_value) {
+    if (!c.tcur) return static_value;
+    const int kind = c.I->tobj_kind[idx];
+    if (kind == JSL_TIME_STATIC) return c.tcur[idx];
+    int v;
+    if (c.tape) {
+        if (draw_ctr >= c.tape_len) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, 0);
+        v = c.tape[draw_ctr];
+    } else {
+        // stochasticy_models.py:22-30: seed += 1; time = max(0, first variate of default_rng(seed))
+        const int sd = (int)c.tseed[idx] + 1;
+        c.tseed[idx] = (uint16_t)sd;
+        const int row = c.I->sample_row ? c.I->sample_row[idx] : -1;
+        if (row >= 0 && sd < c.I->sample_depth) v = c.I->sample_table[row * c.I->sample_depth + sd];
+        else v = draw_time(c.seed, c.env_id, (uint32_t)draw_ctr, kind, c.I->tobj_base[idx], c.I->tobj_param[idx]);
+    }
+    draw_ctr = draw_ctr + 1;
+    c.tcur[idx] = v;
+    return v;
+}
+
 // ------------------------------------------------------------------------------------ outages
 // outage_utils.py:20-131: sample, occupied time; static frequencies/durations (stochastic: TODO tape)
-JSL_D int sample_outages(Ctx& c, int now, int n, const int32_t* freq, const int32_t* dur, uint8_t* active,
-                         int32_t* a, int32_t* b) {
+JSL_D int sample_outages(Ctx& c, int32_t& draw_ctr, int now, int n, const int32_t* freq, const int32_t* dur,
+                         int freq_obj, int dur_obj, uint8_t* active, int32_t* a, int32_t* b) {
     int occupied = 0;
     for (int i = 0; i < n; i++) {
         if (active[i]) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, 0);
         int last = a[i] < 0 ? 0 : a[i];
         int elapsed = now - last;
-        if (freq[i] >= elapsed) {  // sic, outage_utils.py:48
-            active[i] = 1; a[i] = now; b[i] = now + dur[i];
+        bool apply;
+        if (c.tcur && c.I->tobj_kind[freq_obj + i] != JSL_TIME_STATIC) {
+            apply = elapsed > c.tcur[freq_obj + i];  // outage_utils.py:32-42 _sample_frq
+            if (apply) tobj_update(c, draw_ctr, freq_obj + i, 0);
+        } else {
+            apply = freq[i] >= elapsed;  // sic, outage_utils.py:48
+        }
+        if (c.raise) return 0;
+        if (apply) {
+            int d = tobj_update(c, draw_ctr, dur_obj + i, dur[i]);
+            if (c.raise) return 0;
+            active[i] = 1; a[i] = now; b[i] = now + d;
         }
     }
     bool any = false;
@@ -531,9 +674,12 @@ JSL_D void machine_idle_to_setup(EnvS<JW>& s, Ctx& c, int m, int j) {
     int o = I.job_op_start[j] + s.j_k[j];
     int tool = (c.op_mt[o] >> 16) & 0xffff;
     int setup = 0;
-    if (I.setup) {
-        setup = I.setup[(m * I.NT + s.m_tool[m]) * I.NT + tool];
-        if (setup == JSL_NO_TIME) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    if (I.setup || c.tcur) {
+        const int si = (m * I.NT + s.m_tool[m]) * I.NT + tool;
+        setup = setup_time_cur(c, si);
+        if (setup == JSL_NO_TIME && !(c.tcur && I.tobj_kind[I.off_setup + si] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+        setup = tobj_update(c, s.draw_ctr, I.off_setup + si, setup);
+        if (c.raise) return;
     }
     if (s.m_job[m] != NONE8) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
     s.j_proc[j] = 1; s.j_start[j] = c.now; s.j_end[j] = c.now + setup;
@@ -546,7 +692,9 @@ template <int JW>
 JSL_D void machine_setup_to_working(EnvS<JW>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8 || s.j_loc[j] != 3 * m + 2) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
-    int dur = c.op_dur[I.job_op_start[j] + s.j_k[j]];
+    const int o = I.job_op_start[j] + s.j_k[j];
+    int dur = tobj_update(c, s.draw_ctr, o, c.op_dur[o]);
+    if (c.raise) return;
     s.j_proc[j] = 1; s.j_start[j] = c.now; s.j_end[j] = c.now + dur;
     s.m_state[m] = JSL_M_WORKING; s.m_occ[m] = c.now + dur;
 }
@@ -558,8 +706,8 @@ JSL_D void machine_working_to_outage(EnvS<JW>& s, Ctx& c, int m, int j) {
     if (I.has_m_out) {
         int b = I.m_out_start[m], n = I.m_out_start[m + 1] - b;
         OutS<JW>& o = *(OutS<JW>*)c.outs;
-        occupied_for = sample_outages(c, c.now, n, I.m_out_freq + b, I.m_out_dur + b, o.mo_active + m * MAX_OUT,
-                                      o.mo_a + m * MAX_OUT, o.mo_b + m * MAX_OUT);
+        occupied_for = sample_outages(c, s.draw_ctr, c.now, n, I.m_out_freq + b, I.m_out_dur + b, I.off_mof + b,
+                                      I.off_mod + b, o.mo_active + m * MAX_OUT, o.mo_a + m * MAX_OUT, o.mo_b + m * MAX_OUT);
         if (c.raise) return;
     }
     s.m_state[m] = JSL_M_OUTAGE; s.m_occ[m] = c.now + occupied_for;
@@ -639,7 +787,7 @@ JSL_D void agv_idle_to_working(EnvS<JW>& s, Ctx& c, int t, int j) {
     int loc = s.j_loc[j];
     int src = place_of_buf(I, loc);
     if (src < 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TransportConfigError
-    int ttp = travel_time(I, s.t_loc0[t], src);        // no resample (handler.py:876-885)
+    int ttp = travel_time_cur(c, s.t_loc0[t], src);    // no resample (handler.py:876-885)
     if (ttp == JSL_NO_TIME) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     s.t_occkind[t] = OCC_TIME; s.t_occ[t] = c.now + ttp;
     s.t_lockind[t] = 1; s.t_loc1[t] = (uint16_t)loc; s.t_loc2[t] = (uint8_t)target;
@@ -696,8 +844,11 @@ JSL_D void agv_to_transit(EnvS<JW>& s, Ctx& c, int t, int j) {
     else dst = s.j_mach[j];  // get_next_not_done_operation(job).machine_id
     if (c.raise) return;
     if (!(src < I.M || dst < I.M)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
-    int travel = travel_time(I, src, dst);
-    if (travel == JSL_NO_TIME) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TravelTimeError
+    int travel = travel_time_cur(c, src, dst);
+    const int tobj = I.off_travel + src * I.NP + dst;
+    if (travel == JSL_NO_TIME && !(c.tcur && I.tobj_kind[tobj] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TravelTimeError
+    travel = tobj_update(c, s.draw_ctr, tobj, travel);  // resampled (time_utils.py:15)
+    if (c.raise) return;
     if (s.t_carry[t] != NONE8) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
     if (loc % 3 == 2 && loc < 3 * I.M) s.m_job[loc / 3] = NONE8;  // lifted out of a machine buffer
     s.j_loc[j] = (uint16_t)(3 * I.M + t);
@@ -721,8 +872,8 @@ JSL_D void agv_transit_to_outage(EnvS<JW>& s, Ctx& c, int t, int j) {
     int occupied_for = 0;
     if (I.has_t_out) {
         OutS<JW>& o = *(OutS<JW>*)c.outs;
-        occupied_for = sample_outages(c, c.now, I.n_t_out, I.t_out_freq, I.t_out_dur, o.to_active + t * MAX_OUT,
-                                      o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
+        occupied_for = sample_outages(c, s.draw_ctr, c.now, I.n_t_out, I.t_out_freq, I.t_out_dur, I.off_tof, I.off_tod,
+                                      o.to_active + t * MAX_OUT, o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
         if (c.raise) return;
     }
     s.t_state[t] = JSL_T_OUTAGE;
@@ -904,13 +1055,13 @@ JSL_D bool sm_step(EnvS<JW>& s, Ctx& c, bool has_action, Trans act, int time_mac
                     if (nxt == -2) { bad = true; return false; }
                     if (cur == nxt) return true;
                     if (cur < 0) { bad = true; return false; }
-                    int tt = travel_time(I, cur, nxt);
+                    int tt = travel_time_cur(c, cur, nxt);
                     if (tt == JSL_NO_TIME) { bad = true; return false; }
                     return tt == 0;
                 };
                 Mask<JW> zr = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.lr.test(j) && zero_travel(j, bd); });
                 Mask<JW> zi = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.li.test(j) && zero_travel(j, bd); });
-                if (I.travel || I.out_buf < 0) {
+                if (I.travel || c.tcur || I.out_buf < 0) {
                     Mask<JW> badm = wp_ballot<JW>(I.J, [&](int j) {
                         bool bd = false;
                         if (p.lr.test(j) || p.li.test(j)) zero_travel(j, bd);
@@ -1005,6 +1156,31 @@ JSL_D void env_init(EnvS<JW>& s, Ctx& c) {
         });
     }
     s.seq_ctr = EnvS<JW>::MJ;
+    s.draw_ctr = 0;
+    if (c.tcur) {
+        // .time of every time object as compiled; in Philox mode the non-op stochastic objects get their
+        // construction-time sample (stochasticy_models.py:15) from the env's own stream
+        // .time of every time object as compiled.  Free-running mode: each stochastic object gets a numpy
+        // start seed (recorded, or uniform 0..30 like np.random.randint(0, 31), stochasticy_models.py:12) and
+        // its construction-time sample table[row][seed] (:15).
+        const bool table_mode = c.tape == nullptr && I.sample_row != nullptr;
+        wp_for_dyn(I.n_tobj, [&](int i) {
+            int v = I.tobj_init[i];
+            if (table_mode) {
+                const int row = I.sample_row[i];
+                if (row >= 0) {
+                    int sd;
+                    if (c.start_seeds) sd = c.start_seeds[i];
+                    else sd = (int)(philox4(c.seed, c.env_id, (uint32_t)i, 2u << 16).x % 31u);
+                    if (sd < 0) sd = 0;
+                    if (sd >= I.sample_depth) sd = I.sample_depth - 1;
+                    c.tseed[i] = (uint16_t)sd;
+                    if (!c.start_seeds) v = I.sample_table[row * I.sample_depth + sd];
+                }
+            }
+            c.tcur[i] = v;
+        });
+    }
     JSL_SYNCWARP();
 }
 
@@ -1141,7 +1317,11 @@ JSL_D int policy_action(const EnvS<JW>& s, const Ctx& c, int policy, uint64_t se
     if (cand.kind == 1) return 1;
     const int pre = 3 * cand.comp, cj = cand.job;
     auto key = [&](int j) {
-        return policy == JSL_POLICY_SPT ? c.op_dur[I.job_op_start[j] + s.j_k[j]] : job_work[j];
+        if (policy == JSL_POLICY_SPT) return op_duration(c, I.job_op_start[j] + s.j_k[j]);
+        if (!c.tcur) return (int)job_work[j];
+        int w = 0;
+        for (int o = I.job_op_start[j]; o < I.job_op_start[j + 1]; o++) w += c.tcur[o];
+        return w;
     };
     const int ck = key(cj);
     const uint32_t cs = s.j_seq[cj];

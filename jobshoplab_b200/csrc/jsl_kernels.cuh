@@ -33,6 +33,11 @@ struct BatchDev {
     int state_stride, outs_stride;
     uint64_t seed;
     int64_t env_base;    // global index of env 0 (RANDOM policy stream id)
+    int32_t* tcur;       // [B][n_tobj] current .time of every time object (stochastic instances) or nullptr
+    const int32_t* tape; // [B][tape_stride] replayed update() results or nullptr
+    int64_t tape_stride;
+    uint16_t* tseed;     // [B][n_tobj] numpy seed of every stochastic time object
+    const int32_t* start_seeds;  // [B][n_tobj] or nullptr
 };
 
 template <int JW>
@@ -58,6 +63,13 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
     c.lower_bound = I.lb_mat[2 * v];
     c.max_allowed_time = I.lb_mat[2 * v + 1];
     c.neg_inv_n = -1.0 / (double)I.N;
+    c.tcur = bd.tcur ? bd.tcur + env * (int64_t)I.n_tobj : nullptr;
+    c.tape = bd.tape ? bd.tape + env * bd.tape_stride : nullptr;
+    c.tape_len = (int)bd.tape_stride;
+    c.tseed = bd.tseed ? bd.tseed + env * (int64_t)I.n_tobj : nullptr;
+    c.start_seeds = bd.start_seeds ? bd.start_seeds + env * (int64_t)I.n_tobj : nullptr;
+    c.seed = bd.seed;
+    c.env_id = (uint64_t)(bd.env_base + env);
 }
 
 template <int JW>

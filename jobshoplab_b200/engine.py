@@ -22,7 +22,7 @@ LIB_PATH = Path(os.environ.get("JSL_LIB", Path(__file__).resolve().parent / "csr
 _lib = None
 
 ABI_SYMBOLS = ("jsl_last_error", "jsl_abi_version", "jsl_instance_create", "jsl_instance_destroy", "jsl_batch_create",
-               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base",
+               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
                "jsl_reset", "jsl_step", "jsl_rollout", "jsl_get_state", "jsl_get_op_log", "jsl_launch_count")
 
 RO_RESET_FIRST, RO_NO_WRITEBACK = 1, 2
@@ -52,6 +52,8 @@ def load_library():
     L.jsl_batch_destroy.argtypes = [C.c_void_p]
     L.jsl_batch_shape.argtypes = [C.c_void_p, C.POINTER(abi.Shape)]
     L.jsl_batch_set_env_base.argtypes = [C.c_void_p, C.c_int64]
+    L.jsl_batch_set_sample_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.jsl_batch_set_start_seeds.argtypes = [C.c_void_p, C.c_void_p]
     L.jsl_reset.argtypes = [C.c_void_p, C.c_void_p, abi.StepOut, C.c_void_p]
     L.jsl_step.argtypes = [C.c_void_p, C.c_void_p, abi.StepOut, C.c_void_p]
     L.jsl_rollout.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, abi.RolloutOut, C.c_void_p]
@@ -198,6 +200,25 @@ class Batch:
                 assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
                 ptrs.append(a.ctypes.data)
         self._check(self.L.jsl_batch_load_variants(self.h, *ptrs, self._stream()))
+
+    def set_sample_tape(self, tape=None):
+        """Replay recorded StochasticTimeConfig.update() results (int32 CUDA tensor [B, L]) instead of drawing
+        from the Philox streams; None switches back.  Applies from the next reset."""
+        if tape is None:
+            self._tape = None
+            self._check(self.L.jsl_batch_set_sample_tape(self.h, None, 0))
+            return
+        assert tape.dtype == self.torch.int32 and tape.is_cuda and tape.dim() == 2 and tape.shape[0] == self.B
+        self._tape = tape.contiguous()
+        self._check(self.L.jsl_batch_set_sample_tape(self.h, self._tape.data_ptr(), self._tape.shape[1]))
+
+    def set_start_seeds(self, seeds=None):
+        """numpy start seeds of every time object (int32 CUDA tensor [B, n_time_objects], flat order of
+        jobshoplab_b200.stochastic.flat_specs); None: drawn per env.  Applies from the next reset."""
+        self._seeds = None if seeds is None else seeds.contiguous()
+        if seeds is not None:
+            assert seeds.dtype == self.torch.int32 and seeds.is_cuda and seeds.shape[0] == self.B
+        self._check(self.L.jsl_batch_set_start_seeds(self.h, None if seeds is None else self._seeds.data_ptr()))
 
     def reset(self, mask=None) -> StepResult:
         ptr = None

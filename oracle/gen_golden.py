@@ -63,6 +63,8 @@ def pack_lowered(li) -> dict:
                                     li.default_tool, li.start_time, li.lower_bound, li.max_allowed_time],
                                    dtype=np.int64)
     out["li/tools"] = np.asarray(json.dumps(li.tools))
+    if getattr(li, "start_seeds", None) is not None:
+        out["li/start_seeds"] = li.start_seeds
     for name in SPEC_NAMES:
         sp = getattr(li, name)
         if sp.kind is not None:
@@ -303,7 +305,9 @@ def _safe(sc):
 
 
 def main(argv):
-    groups = argv or list(GROUPS)
+    groups = [g for g in argv if g != "ks"] if argv else list(GROUPS)
+    if argv and not groups:
+        return
     OUT.mkdir(parents=True, exist_ok=True)
     for g in groups:
         scs = GROUPS[g]()
@@ -328,3 +332,57 @@ def main(argv):
 
 if __name__ == "__main__":
     main(sys.argv[1:])
+
+
+# ------------------------------------------------------------------ distribution fixtures (KS tests)
+def _ks_episode(args):
+    import ref_harness as rh
+
+    text, seed, policy = args
+    env = rh.make_env("dslstr", text, seed=seed)
+    n = 0
+    while not env.done:
+        a = 1 if policy == "fifo" else rh.random_action(seed, 0, n)
+        env.step(a)
+        n += 1
+    return int(env.state.state.time.time), n, int(env.terminated)
+
+
+def ks_sources():
+    full = (TDATA / "full_feature_3x3_instance.yaml").read_text()
+    d = yaml.safe_load((DATA / "transport" / "ft20.yaml").read_text())
+    ic = d["instance_config"]
+    ic["logistics"]["time_behavior"] = {"type": "poisson"}
+    ic["outages"] = [{"component": "m", "type": "breakdown", "duration": 5,
+                      "frequency": {"type": "gamma", "scale": 5, "base": 10}}]
+    tools = ["tl-0", "tl-1", "tl-2"]
+    ic["instance"]["tool_usage"] = [{"job": f"j{j}", "operation_tools": [tools[(j + k) % 3] for k in range(5)]}
+                                    for j in range(20)]
+    ic["setup_times"] = [{"machine": f"m-{m}", "specification": "tl-0|tl-1|tl-2\ntl-0|0 2 5\ntl-1|2 0 8\ntl-2|5 2 0\n",
+                          "time_behavior": {"type": "uni", "offset": 2}} for m in range(5)]
+    return {"full_feature_3x3": (full, 3000), "ft20-t_features": (yaml.safe_dump(d, sort_keys=False), 1200)}
+
+
+def gen_ks():
+    import ref_harness as rh
+
+    out = {}
+    for name, (text, n) in ks_sources().items():
+        t0 = time.time()
+        with mp.Pool(min(8, os.cpu_count() or 1)) as pool:
+            res = pool.map(_ks_episode, [(text, s, "fifo") for s in range(n)], chunksize=8)
+        mk = np.asarray([r[0] for r in res], dtype=np.int32)
+        env = rh.make_env("dslstr", text, seed=0)
+        for k, v in pack_lowered(env.jsl_rc.lowered).items():
+            out[f"{name}|{k}"] = v
+        out[f"{name}|makespan"] = np.sort(mk)
+        out[f"{name}|n_steps"] = np.asarray([r[1] for r in res], dtype=np.int32)
+        out[f"{name}|terminated"] = np.asarray([r[2] for r in res], dtype=np.uint8)
+        out[f"{name}|source_text"] = np.asarray(text)
+        print(f"ks/{name}: {n} reference episodes, makespan mean {mk.mean():.1f} std {mk.std():.1f}, {time.time() - t0:.0f}s")
+    out["__names__"] = np.asarray(json.dumps(list(ks_sources())))
+    np.savez_compressed(OUT / "ks.npz", **out)
+
+
+if __name__ == "__main__" and "ks" in sys.argv[1:]:
+    gen_ks()

@@ -369,8 +369,12 @@ def lower_reference(instance, init_state):
     def cap(c):
         return L.CAP_INF if c >= L.CAP_INF else int(c)
 
+    seeds_all = []
+
     def tspec(objs):
         """list of time objects (or None) -> (time array, TimeSpec)"""
+        seeds_all.extend(-1 if (o is None or isinstance(o, DeterministicTimeConfig)) else int(o._current_seed)
+                         for o in objs)
         time = np.full(len(objs), L.NO_TIME, dtype=np.int32)
         kind = np.zeros(len(objs), dtype=np.int32)
         base = np.zeros(len(objs), dtype=np.int32)
@@ -430,7 +434,7 @@ def lower_reference(instance, init_state):
     for t in init_state.transports:
         assert isinstance(t.location.location, str)
         agv_place.append(ix.place(t.location.location))
-    return L.LoweredInstance(
+    li = L.LoweredInstance(
         description=str(instance.description),
         n_jobs=J, n_machines=M, n_transports=T, n_sbuf=S, n_tools=nt,
         job_op_start=job_op_start,
@@ -458,3 +462,7 @@ def lower_reference(instance, init_state):
         m_ofreq_spec=m_ofreq_spec, m_odur_spec=m_odur_spec,
         t_ofreq_spec=t_ofreq_spec, t_odur_spec=t_odur_spec,
     )
+    # numpy start seeds of the stochastic objects, in the engine's flat time-object order (ops, setup, travel,
+    # machine-outage freq, dur, transport-outage freq, dur) -- tspec() is called in exactly that order
+    li.start_seeds = np.asarray(seeds_all, dtype=np.int32)
+    return li

@@ -76,6 +76,7 @@ class Scenario:
             n_tools=int(sc[4]), default_tool=int(sc[5]), start_time=int(sc[6]), lower_bound=int(sc[7]),
             max_allowed_time=int(sc[8]), tools=json.loads(str(g("li/tools"))),
             **{k: g(f"li/{k}") for k in fields}, **specs)
+        self.start_seeds = g("li/start_seeds") if f"{name}|li/start_seeds" in z.files else None
 
     @property
     def cfg(self) -> dict:
@@ -91,6 +92,32 @@ class Scenario:
     @property
     def exception(self):
         return self.meta["exception"]
+
+
+class KsFixture:
+    """Reference makespan sample of a stochastic instance (oracle/gen_golden.py ks)."""
+
+    def __init__(self, name):
+        z = _load("ks")
+        g = lambda k: z[f"{name}|{k}"]
+        self.name = name
+        self.makespan = g("makespan")
+        self.n_steps = g("n_steps")
+        self.source_text = str(g("source_text"))
+        sc = g("li/scalars")
+        specs = {}
+        for sp in ("op_spec", "setup_spec", "travel_spec", "m_ofreq_spec", "m_odur_spec", "t_ofreq_spec", "t_odur_spec"):
+            if f"{name}|li/{sp}/kind" in z.files:
+                specs[sp] = L.TimeSpec(g(f"li/{sp}/kind"), g(f"li/{sp}/base"), g(f"li/{sp}/param"))
+        fields = ("job_op_start", "op_machine", "op_tool", "op_duration", "pre_type", "pre_cap", "post_type",
+                  "post_cap", "setup_time", "sbuf_type", "sbuf_cap", "sbuf_role", "buf_ref_id", "travel_time",
+                  "agv_init_place", "job_init_buf", "m_outage_start", "m_outage_freq", "m_outage_dur",
+                  "t_outage_freq", "t_outage_dur")
+        self.lowered = L.LoweredInstance(
+            description=name, n_jobs=int(sc[0]), n_machines=int(sc[1]), n_transports=int(sc[2]), n_sbuf=int(sc[3]),
+            n_tools=int(sc[4]), default_tool=int(sc[5]), start_time=int(sc[6]), lower_bound=int(sc[7]),
+            max_allowed_time=int(sc[8]), tools=json.loads(str(g("li/tools"))),
+            **{k: g(f"li/{k}") for k in fields}, **specs)
 
 
 def all_scenarios(groups=GROUPS):

@@ -18,6 +18,7 @@ _lib = None
 
 def build(force=False):
     srcs = [HERE / "jsl_hostsim.cpp", ROOT / "jobshoplab_b200" / "csrc" / "jsl_engine.cuh",
+            ROOT / "jobshoplab_b200" / "csrc" / "jsl_tobj.hpp",
             ROOT / "include" / "jobshoplab_b200.h"]
     if not force and LIB.exists() and LIB.stat().st_mtime >= max(s.stat().st_mtime for s in srcs):
         return LIB
@@ -45,6 +46,10 @@ def lib():
         L.jsh_return.argtypes = [C.c_void_p]
         L.jsh_return.restype = C.c_double
         L.jsh_state_bytes.argtypes = [C.c_void_p]
+        L.jsh_set_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.jsh_set_env_id.argtypes = [C.c_void_p, C.c_uint64]
+        L.jsh_set_start_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.jsh_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_float]
         _lib = L
     return _lib
 
@@ -66,6 +71,16 @@ class HostSimEnv:
         if getattr(self, "h", None):
             self.L.jsh_destroy(self.h)
             self.h = None
+
+    def set_tape(self, samples):
+        t = np.ascontiguousarray(samples, dtype=np.int32)
+        self.L.jsh_set_tape(self.h, t.ctypes.data, len(t))
+
+    def set_start_seeds(self, seeds):
+        t = np.ascontiguousarray(seeds, dtype=np.int32)
+        self.L.jsh_set_start_seeds(self.h, t.ctypes.data, len(t))
+
+    def set_env_id(self, i): self.L.jsh_set_env_id(self.h, int(i))
 
     def reset(self): return self.L.jsh_reset(self.h)
     def step(self, a): return self.L.jsh_step(self.h, int(a))

@@ -10,7 +10,9 @@
 #include <string>
 #include <vector>
 
+#include <cmath>
 #include "../../jobshoplab_b200/csrc/jsl_engine.cuh"
+#include "../../jobshoplab_b200/csrc/jsl_tobj.hpp"
 
 using namespace jsl;
 
@@ -29,6 +31,10 @@ struct Sim {
     int state_bytes, outs_bytes;
     uint64_t seed;
     double last_reward;
+    TobjTables tobj;
+    std::vector<int32_t> tcur, tape, start_seeds;
+    std::vector<uint16_t> tseed;
+    uint64_t env_id = 0;
 };
 
 template <class T, class U>
@@ -57,6 +63,11 @@ template <int JW> void make_ctx(Sim* s, Ctx& c) {
     c.op_log = s->C.record_ops ? s->op_log.data() : nullptr;
     c.outs = s->outs_bytes ? (void*)s->outs.data() : nullptr;
     c.raise = 0; c.now = 0; c.lower_bound = s->lb_mat[0]; c.max_allowed_time = s->lb_mat[1]; c.neg_inv_n = -1.0 / (double)s->I.N;
+    c.tcur = s->tobj.stochastic ? s->tcur.data() : nullptr;
+    c.tape = s->tape.empty() ? nullptr : s->tape.data(); c.tape_len = (int)s->tape.size();
+    c.seed = s->seed; c.env_id = s->env_id;
+    c.tseed = s->tobj.stochastic ? s->tseed.data() : nullptr;
+    c.start_seeds = s->start_seeds.empty() ? nullptr : s->start_seeds.data();
 }
 
 template <int JW> int do_reset(Sim* s) {
@@ -176,9 +187,22 @@ void* jsh_create(const jsl_instance_desc* d, const jsl_env_cfg* cfg, uint64_t se
     s->state.assign(s->state_bytes + 16, 0); s->outs.assign(s->outs_bytes + 16, 0);
     s->op_log.assign((size_t)2 * I.N + 2, -1);
     s->seed = seed; s->last_reward = 0.0;
+    s->tobj = make_tobj(*d);
+    if (s->tobj.stochastic) {
+        s->tcur.assign(s->tobj.n + 1, 0); s->tseed.assign(s->tobj.n + 1, 0);
+        if (s->tobj.sample_depth > 0) { I.sample_table = s->tobj.sample_table.data(); I.sample_row = s->tobj.sample_row.data(); I.sample_depth = s->tobj.sample_depth; }
+        I.tobj_kind = s->tobj.kind.data(); I.tobj_base = s->tobj.base.data(); I.tobj_param = s->tobj.param.data();
+        I.tobj_init = s->tobj.init.data(); I.n_tobj = s->tobj.n; I.off_setup = s->tobj.off_setup;
+        I.off_travel = s->tobj.off_travel; I.off_mof = s->tobj.off_mof; I.off_mod = s->tobj.off_mod;
+        I.off_tof = s->tobj.off_tof; I.off_tod = s->tobj.off_tod;
+    }
     return s;
 }
 void jsh_destroy(void* h) { delete (Sim*)h; }
+void jsh_set_tape(void* h, const int32_t* t, int n) { Sim* s = (Sim*)h; s->tape.assign(t, t + n); }
+void jsh_set_env_id(void* h, uint64_t id) { ((Sim*)h)->env_id = id; }
+void jsh_set_start_seeds(void* h, const int32_t* t, int n) { Sim* s = (Sim*)h; s->start_seeds.assign(t, t + n); }
+int jsh_draw(uint64_t seed, uint64_t env, uint32_t n, int kind, int base, float param) { return draw_time(seed, env, n, kind, base, param); }
 int jsh_reset(void* h) { Sim* s = (Sim*)h; return DISPATCH(s, do_reset, s); }
 int jsh_step(void* h, int a) { Sim* s = (Sim*)h; return DISPATCH(s, do_step, s, a); }
 int jsh_digest(void* h, int32_t* out, int cap) { Sim* s = (Sim*)h; return DISPATCH(s, do_digest, s, out, cap); }

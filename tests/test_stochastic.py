@@ -1,0 +1,186 @@
+"""Stochastic time behaviour: samplers, bit-exact sample-tape replay and the makespan
+distribution of free-running (Philox) episodes against the reference's.
+
+CPU part: the engine SOURCE through tests/hostsim.  GPU part (-m gpu): the CUDA engine through the C ABI.
+Tolerance for distributions: two-sample Kolmogorov-Smirnov, alpha = 0.01 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+from scipy import stats
+
+import _golden as G
+from hostsim import hostsim_py as hs
+from jobshoplab_b200 import abi
+from jobshoplab_b200 import lowered as L
+
+ALPHA = 0.01
+
+
+def _draws(kind, base, param, n=20000, seed=7):
+    lib = hs.lib()
+    return np.array([lib.jsh_draw(seed, 3, i, kind, base, param) for i in range(n)])
+
+
+def test_samplers_match_numpy_distributions():
+    """stochasticy_models.py:44-121: Poisson base+P(base+.5), int(U(base-off,base+off)), int(N(base,std)),
+    int(round(base+Gamma(shape=base, scale))), each clipped at 0."""
+    rng = np.random.default_rng(123)
+    n = 20000
+    cases = [
+        (L.TIME_POISSON, 5, 0.0, lambda: 5 + rng.poisson(5.5, n)),
+        (L.TIME_POISSON, 40, 0.0, lambda: 40 + rng.poisson(40.5, n)),
+        (L.TIME_UNIFORM, 50, 20.0, lambda: rng.uniform(30, 70, n).astype(np.int64)),
+        (L.TIME_GAUSSIAN, 10, 5.0, lambda: np.maximum(0, np.trunc(rng.normal(10, 5, n)))),
+        (L.TIME_GAUSSIAN, 100000, 5000.0, lambda: np.trunc(rng.normal(100000, 5000, n))),
+        (L.TIME_GAMMA, 10, 5.0, lambda: np.rint(10 + rng.gamma(10, 5.0, n))),
+        (L.TIME_GAMMA, 2, 0.5, lambda: np.rint(2 + rng.gamma(2, 0.5, n))),
+    ]
+    for kind, base, param, ref in cases:
+        mine, want = _draws(kind, base, param, n), ref()
+        assert mine.min() >= 0
+        p = stats.ks_2samp(mine, want).pvalue
+        assert p > ALPHA, (kind, base, param, p, mine.mean(), want.mean())
+        assert abs(mine.mean() - want.mean()) < 4 * want.std() / np.sqrt(n) + 0.51
+
+
+def test_engine_source_tape_replay_is_bit_exact():
+    """Every stochastic golden scenario replays bit-exactly when the engine is fed the reference's recorded
+    update() results (setup, processing, travel, outage frequency/duration draws in call order)."""
+    count = 0
+    for name in G.names("features"):
+        sc = G.Scenario("features", name)
+        if sc.lowered.is_deterministic:
+            continue
+        e = hs.HostSimEnv(sc.lowered, **sc.cfg)
+        e.set_tape(sc.samples)
+        e.reset()
+        assert G.hash_i32(e.digest()) == int(sc.state_hash[0]), name
+        for i in range(sc.meta["n_steps"]):
+            e.step(int(sc.actions[i]))
+            assert G.hash_i32(e.digest()) == int(sc.state_hash[i + 1]), (name, i)
+            assert e.reward == float(sc.reward[i])
+        assert np.array_equal(e.digest(), sc.final_digest), name
+        count += 1
+    assert count >= 50
+
+
+def test_engine_source_start_seed_replay_is_bit_exact():
+    """Free-running mode (no tape): given the numpy start seeds the reference's time objects had
+    (stochasticy_models.py:12), the engine's sample tables reproduce every draw, so whole stochastic
+    episodes -- setup, processing, travel, breakdown frequency/duration -- match bit-exactly."""
+    count = 0
+    for name in G.names("features"):
+        sc = G.Scenario("features", name)
+        if sc.lowered.is_deterministic:
+            continue
+        e = hs.HostSimEnv(sc.lowered, **sc.cfg)
+        e.set_start_seeds(sc.start_seeds)
+        e.reset()
+        assert G.hash_i32(e.digest()) == int(sc.state_hash[0]), name
+        for i in range(sc.meta["n_steps"]):
+            e.step(int(sc.actions[i]))
+            assert G.hash_i32(e.digest()) == int(sc.state_hash[i + 1]), (name, i)
+            assert e.reward == float(sc.reward[i])
+        assert np.array_equal(e.digest(), sc.final_digest), name
+        count += 1
+    assert count >= 50
+
+
+def test_sample_tables_are_numpy_first_variates():
+    from jobshoplab_b200.stochastic import sample_tables, flat_specs
+
+    fx = G.KsFixture("full_feature_3x3")
+    table, row = sample_tables(fx.lowered, depth=40)
+    kind, base, param = flat_specs(fx.lowered)
+    i = int(np.nonzero(kind == L.TIME_UNIFORM)[0][0])
+    want = [max(0, int(np.random.default_rng(s).uniform(base[i] - param[i], base[i] + param[i]))) for s in range(40)]
+    assert table[row[i]].tolist() == want
+    i = int(np.nonzero(kind == L.TIME_GAMMA)[0][0])
+    want = [max(0, int(round(base[i] + np.random.default_rng(s).gamma(base[i], param[i])))) for s in range(40)]
+    assert table[row[i]].tolist() == want
+    assert (row[kind == L.TIME_STATIC] == -1).all()
+
+
+@pytest.mark.parametrize("name", ["full_feature_3x3"])
+def test_engine_source_philox_makespans_match_reference_distribution(name):
+    fx = G.KsFixture(name)
+    e = hs.HostSimEnv(fx.lowered, seed=11)
+    mk = []
+    for i in range(3000):
+        e.set_env_id(i)
+        e.reset()
+        e.rollout(abi.POLICY_FIFO)
+        assert e.terminated
+        mk.append(e.time)
+    p = stats.ks_2samp(np.array(mk), fx.makespan).pvalue
+    assert p > ALPHA, (p, np.mean(mk), fx.makespan.mean())
+
+
+# ------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_gpu_tape_replay_is_bit_exact():
+    torch = pytest.importorskip("torch")
+    from jobshoplab_b200 import engine
+
+    by_inst = {}
+    for name in G.names("features"):
+        sc = G.Scenario("features", name)
+        if not sc.lowered.is_deterministic:
+            by_inst.setdefault((sc.source_text, tuple(sorted(sc.cfg.items()))), []).append(sc)
+    checked = 0
+    for scs in by_inst.values():
+        # the lowered instance of a stochastic scenario carries that episode's construction-time samples,
+        # so every scenario gets its own batch; rollout mode (TAPE policy) + step mode for the first one
+        for k, sc in enumerate(scs):
+            B = 3
+            batch = engine.Batch(sc.lowered, B, record_ops=True, **sc.cfg)
+            tape = torch.from_numpy(np.tile(sc.samples, (B, 1)).astype(np.int32)).cuda()
+            if tape.shape[1] == 0:
+                tape = torch.zeros((B, 1), dtype=torch.int32, device="cuda")
+            batch.set_sample_tape(tape)
+            acts = torch.from_numpy(np.tile(np.append(sc.actions, 1), (B, 1)).astype(np.uint8)).cuda()
+            if k == 1:  # free-running table mode with the reference's start seeds: bit-exact without a tape
+                batch.set_sample_tape(None)
+                batch.set_start_seeds(torch.from_numpy(np.tile(sc.start_seeds, (B, 1)).astype(np.int32)).cuda())
+                batch.reset()
+                r = batch.rollout("tape", tape=acts)
+                assert (r.makespan.cpu().numpy() == sc.meta["makespan"]).all(), sc.name
+                assert np.array_equal(batch.get_state(1), sc.final_digest), sc.name
+                batch.set_start_seeds(None)
+                batch.set_sample_tape(tape)
+            if k == 0:
+                batch.reset()
+                assert G.hash_i32(batch.get_state(1)) == int(sc.state_hash[0])
+                for i in range(sc.meta["n_steps"]):
+                    out = batch.step(acts[:, i].contiguous())
+                    assert G.hash_i32(batch.get_state(2)) == int(sc.state_hash[i + 1]), (sc.name, i)
+                    assert float(out.reward[0]) == float(sc.reward[i])
+            batch.reset()
+            r = batch.rollout("tape", tape=acts)
+            assert (r.makespan.cpu().numpy() == sc.meta["makespan"]).all(), sc.name
+            assert (r.n_steps.cpu().numpy() == sc.meta["n_steps"]).all(), sc.name
+            assert np.array_equal(batch.get_state(0), sc.final_digest), sc.name
+            batch.close()
+            checked += 1
+    assert checked >= 50
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,B", [("full_feature_3x3", 20000), ("ft20-t_features", 20000)])
+def test_gpu_philox_makespans_match_reference_distribution(name, B):
+    """BASELINE config 5: setup times + breakdowns + stochastic times, free-running Philox streams on device;
+    makespan distribution of B episodes vs >= 1000 reference episodes, two-sample KS at alpha 0.01."""
+    pytest.importorskip("torch")
+    from jobshoplab_b200 import engine
+
+    fx = G.KsFixture(name)
+    batch = engine.Batch(fx.lowered, B, seed=5)
+    r = batch.rollout("fifo", reset_first=True)
+    st = r.status.cpu().numpy()
+    assert (st == abi.ST_DONE).all(), np.unique(st, return_counts=True)
+    mk = r.makespan.cpu().numpy()
+    p = stats.ks_2samp(mk, fx.makespan).pvalue
+    assert p > ALPHA, (p, mk.mean(), fx.makespan.mean(), mk.std(), fx.makespan.std())
+    # reproducible: same seed, same streams
+    mk2 = batch.rollout("fifo", reset_first=True).makespan.cpu().numpy()
+    assert np.array_equal(mk, mk2)
+    batch.close()
