@@ -117,7 +117,7 @@ struct CfgDev {
 // ------------------------------------------------------------------------------------ state
 // Mutable state of one env.  JW = ceil(max(J,T)/32) lane words; machines <= 32.
 // The same struct is the HBM image (step mode) and the shared-memory working copy.
-template <int JW>
+template <int JW, bool ST = false>
 struct alignas(16) EnvS {
     static constexpr int MJ = 32 * JW, MT = 32 * JW, MM = 32;
     // scalars (uniform)
@@ -167,24 +167,30 @@ struct alignas(16) OutS {
     uint8_t mo_active[MM * MAX_OUT], to_active[MT * MAX_OUT];
 };
 
-// per-call context: uniform values kept in registers
+// Rarely used per-env constants: kept in the env's shared-memory slot, not in registers.
+struct alignas(16) EnvAux {
+    int32_t* op_log;             // [N][2] or nullptr
+    void* outs;                  // OutS<JW>* or nullptr
+    int32_t* tcur;               // [n_tobj] current .time of every time object (stochastic instances) or nullptr
+    uint16_t* tseed;             // [n_tobj] current numpy seed of every stochastic time object
+    const int32_t* start_seeds;  // [n_tobj] recorded start seeds, or nullptr (drawn 0..30 from Philox)
+    const int32_t* tape;         // replayed update() results, or nullptr (table mode)
+    uint64_t seed, env_id;       // Philox key / stream of this env
+    double neg_inv_n;            // -1.0 / N: the dense reward of a penalised step (rewards.py:135-138)
+    int32_t tape_len;
+    int32_t lower_bound, max_allowed_time;
+    int32_t pad;
+};
+
+// per-call context: the few uniform values the hot loop keeps in registers
 struct Ctx {
     const InstDev* I;
     const CfgDev* C;
     const int32_t* op_mt;   // this env's variant
     const int32_t* op_dur;
-    int32_t* op_log;        // [N][2] or nullptr
-    void* outs;             // OutS<JW>* or nullptr
+    EnvAux* aux;
     int raise;              // JSL_ST_* of an escaping exception, 0 = none
     int now;
-    int lower_bound, max_allowed_time;
-    double neg_inv_n;       // -1.0 / N: the dense reward of a penalised step (rewards.py:135-138)
-    int32_t* tcur;          // [n_tobj] this env's current .time of every time object, or nullptr (deterministic)
-    uint16_t* tseed;        // [n_tobj] this env's current numpy seed of every stochastic time object
-    const int32_t* start_seeds;  // [n_tobj] recorded start seeds, or nullptr (drawn 0..30 from Philox)
-    const int32_t* tape;    // replayed update() results, or nullptr (table mode)
-    int tape_len;
-    uint64_t seed, env_id;  // Philox key / stream of this env
 };
 
 #define JSL_RAISE(c, code)          \
@@ -342,14 +348,14 @@ JSL_D int job_nops(const InstDev& I, int j) { return I.job_op_start[j + 1] - I.j
 JSL_D int travel_time(const InstDev& I, int a, int b) { return I.travel ? I.travel[a * I.NP + b] : 0; }
 
 // ------------------------------------------------------------------------------------ buffers as (loc, seq)
-template <int JW>
-JSL_DN int buf_count(const EnvS<JW>& s, const InstDev& I, int b) {
+template <int JW, bool ST>
+JSL_DN int buf_count(const EnvS<JW, ST>& s, const InstDev& I, int b) {
     return wp_ballot<JW>(I.J, [&](int j) { return s.j_loc[j] == b; }).count();
 }
 
 // buffer_type_utils.py:236-262 get_next_job_from_buffer; -1 = None
-template <int JW>
-JSL_DN int next_job_from_buffer(const EnvS<JW>& s, const InstDev& I, int b) {
+template <int JW, bool ST>
+JSL_DN int next_job_from_buffer(const EnvS<JW, ST>& s, const InstDev& I, int b) {
     int ty = buf_type(I, b);
     if (ty == JSL_BUF_FLEX) return -1;
     // seq stamps are unique per env, so the stamp identifies the job
@@ -365,8 +371,8 @@ JSL_DN int next_job_from_buffer(const EnvS<JW>& s, const InstDev& I, int b) {
 }
 
 // buffer_type_utils.py:328-353 is_job_ready_for_pickup_from_postbuffer (uniform j)
-template <int JW>
-JSL_DN bool ready_for_pickup(const EnvS<JW>& s, const InstDev& I, int j) {
+template <int JW, bool ST>
+JSL_DN bool ready_for_pickup(const EnvS<JW, ST>& s, const InstDev& I, int j) {
     int b = s.j_loc[j];
     bool right = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
     if (!right) return false;
@@ -378,8 +384,8 @@ JSL_DN bool ready_for_pickup(const EnvS<JW>& s, const InstDev& I, int j) {
     return !wp_ballot<JW>(I.J, [&](int q) { return s.j_loc[q] == b && s.j_seq[q] < sq; }).any();
 }
 // same test evaluated by one lane for its own job (serial scan; only used when early transport is off)
-template <int JW>
-JSL_D bool ready_for_pickup_lane(const EnvS<JW>& s, const InstDev& I, int j) {
+template <int JW, bool ST>
+JSL_D bool ready_for_pickup_lane(const EnvS<JW, ST>& s, const InstDev& I, int j) {
     int b = s.j_loc[j];
     bool right = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
     if (!right) return false;
@@ -393,8 +399,8 @@ JSL_D bool ready_for_pickup_lane(const EnvS<JW>& s, const InstDev& I, int j) {
 }
 
 // buffer_type_utils.py:77-105 put_in_buffer (multi-slot buffers)
-template <int JW>
-JSL_D void put_in_buffer(EnvS<JW>& s, Ctx& c, int b, int j) {
+template <int JW, bool ST>
+JSL_D void put_in_buffer(EnvS<JW, ST>& s, Ctx& c, int b, int j) {
     const InstDev& I = *c.I;
     if (!I.caps_inf) {
         int cap = buf_cap(I, b);
@@ -417,16 +423,16 @@ struct Poss {
 };
 
 // machine of the next IDLE op of job j and whether it has one (lane-local)
-template <int JW>
-JSL_D int next_idle_place(const EnvS<JW>& s, const Ctx& c, int j) {  // -1 = none -> output buffer
+template <int JW, bool ST>
+JSL_D int next_idle_place(const EnvS<JW, ST>& s, const Ctx& c, int j) {  // -1 = none -> output buffer
     const InstDev& I = *c.I;
     int k = s.j_k[j] + (s.j_proc[j] ? 1 : 0);
     if (k >= job_nops(I, j)) return -1;
     return c.op_mt[I.job_op_start[j] + k] & 0xffff;
 }
 
-template <int JW>
-JSL_D Poss<JW> compute_poss(const EnvS<JW>& s, const Ctx& c) {
+template <int JW, bool ST>
+JSL_D Poss<JW> compute_poss(const EnvS<JW, ST>& s, const Ctx& c) {
     const InstDev& I = *c.I;
     Poss<JW> p;
     // possible_transition_utils.py:68-118 is_action_possible
@@ -456,8 +462,8 @@ struct Trans {
 };
 
 // idx-th element of get_possible_transitions(state) (state.py:298-341 ordering)
-template <int JW>
-JSL_D Trans nth_possible(const EnvS<JW>& s, const Ctx& c, const Poss<JW>& p, int idx) {
+template <int JW, bool ST>
+JSL_D Trans nth_possible(const EnvS<JW, ST>& s, const Ctx& c, const Poss<JW>& p, int idx) {
     Trans t;
     int n1 = p.p1.count();
     if (idx < n1) {
@@ -472,15 +478,15 @@ JSL_D Trans nth_possible(const EnvS<JW>& s, const Ctx& c, const Poss<JW>& p, int
     return t;
 }
 
-template <int JW>
-JSL_D Poss<JW> cached_poss(const EnvS<JW>& s) {
+template <int JW, bool ST>
+JSL_D Poss<JW> cached_poss(const EnvS<JW, ST>& s) {
     Poss<JW> p;
 #pragma unroll
     for (int w = 0; w < JW; w++) { p.p1.w[w] = s.c_p1[w]; p.idle.w[w] = s.c_idle[w]; p.lr.w[w] = s.c_lr[w]; p.li.w[w] = s.c_li[w]; }
     return p;
 }
-template <int JW>
-JSL_D void store_poss(EnvS<JW>& s, const Poss<JW>& p, bool clear) {
+template <int JW, bool ST>
+JSL_D void store_poss(EnvS<JW, ST>& s, const Poss<JW>& p, bool clear) {
 #pragma unroll
     for (int w = 0; w < JW; w++) {
         s.c_p1[w] = clear ? 0u : p.p1.w[w]; s.c_idle[w] = clear ? 0u : p.idle.w[w];
@@ -488,20 +494,23 @@ JSL_D void store_poss(EnvS<JW>& s, const Poss<JW>& p, bool clear) {
     }
 }
 // the candidate the agent is looking at: possible_transitions[0] after `skip` dropped ones
-template <int JW>
-JSL_D Trans current_candidate(const EnvS<JW>& s, const Ctx& c) {
+template <int JW, bool ST>
+JSL_D Trans current_candidate(const EnvS<JW, ST>& s, const Ctx& c) {
     return nth_possible(s, c, cached_poss(s), s.skip);
 }
 
 // ------------------------------------------------------------------------------------ time objects
 // .time of a time object (no resample)
-JSL_D int op_duration(const Ctx& c, int o) { return c.tcur ? c.tcur[o] : c.op_dur[o]; }
+template <bool ST>
+JSL_D int op_duration(const Ctx& c, int o) { return ST ? c.aux->tcur[o] : c.op_dur[o]; }
+template <bool ST>
 JSL_D int setup_time_cur(const Ctx& c, int i) {
-    if (c.tcur) return c.tcur[c.I->off_setup + i];
+    if (ST) return c.aux->tcur[c.I->off_setup + i];
     return c.I->setup ? c.I->setup[i] : 0;
 }
+template <bool ST>
 JSL_D int travel_time_cur(const Ctx& c, int a, int b) {
-    if (c.tcur) return c.tcur[c.I->off_travel + a * c.I->NP + b];
+    if (ST) return c.aux->tcur[c.I->off_travel + a * c.I->NP + b];
     return c.I->travel ? c.I->travel[a * c.I->NP + b] : 0;
 }
 
@@ -587,30 +596,67 @@ JSL_DN int draw_time(uint64_t seed, uint64_t env, uint32_t n, int kind, int base
 }
 
 // StochasticTimeConfig.update() of time object `idx` (stochasticy_models.py:27-30): a new sample becomes
-// its .time.  Static objects just return their time.
-JSL_D int tobj_update(Ctx& c, int32_t& draw_ctr, int idx, int static_value) {
-    if (!c.tcur) return static_value;
-    const int kind = c.I->tobj_kind[idx];
-    if (kind == JSL_TIME_STATIC) return c.tcur[idx];
+// its .time.  Out of line and free of Ctx so the deterministic hot path only pays a null test.
+// Returns the new time; *raise is set when the replay tape runs out.
+JSL_DN int stoch_update(const InstDev* I, int32_t* tcur, uint16_t* tseed, const int32_t* tape, int tape_len,
+                        int32_t* draw_ctr, uint64_t seed, uint64_t env, int idx, int* raise) {
+    const int kind = I->tobj_kind[idx];
+    if (kind == JSL_TIME_STATIC) return tcur[idx];
+    const int n = *draw_ctr;
     int v;
-    if (c.tape) {
-        if (draw_ctr >= c.tape_len) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, 0);
-        v = c.tape[draw_ctr];
+    if (tape) {
+        if (n >= tape_len) { if (!*raise) *raise = JSL_ST_OTHER_INVALID; return 0; }
+        v = tape[n];
     } else {
         // stochasticy_models.py:22-30: seed += 1; time = max(0, first variate of default_rng(seed))
-        const int sd = (int)c.tseed[idx] + 1;
-        c.tseed[idx] = (uint16_t)sd;
-        const int row = c.I->sample_row ? c.I->sample_row[idx] : -1;
-        if (row >= 0 && sd < c.I->sample_depth) v = c.I->sample_table[row * c.I->sample_depth + sd];
-        else v = draw_time(c.seed, c.env_id, (uint32_t)draw_ctr, kind, c.I->tobj_base[idx], c.I->tobj_param[idx]);
+        const int sd = (int)tseed[idx] + 1;
+        tseed[idx] = (uint16_t)sd;
+        const int row = I->sample_row ? I->sample_row[idx] : -1;
+        if (row >= 0 && sd < I->sample_depth) v = I->sample_table[row * I->sample_depth + sd];
+        else v = draw_time(seed, env, (uint32_t)n, kind, I->tobj_base[idx], I->tobj_param[idx]);
     }
-    draw_ctr = draw_ctr + 1;
-    c.tcur[idx] = v;
+    *draw_ctr = n + 1;
+    tcur[idx] = v;
     return v;
+}
+template <bool ST>
+JSL_D int tobj_update(Ctx& c, int32_t& draw_ctr, int idx, int static_value) {
+    if (!ST) return static_value;
+    int raise = 0;
+    int32_t ctr = draw_ctr;
+    int v = stoch_update(c.I, c.aux->tcur, c.aux->tseed, c.aux->tape, c.aux->tape_len, &ctr, c.aux->seed, c.aux->env_id, idx, &raise);
+    draw_ctr = ctr;
+    if (raise && !c.raise) c.raise = raise;
+    return v;
+}
+
+// .time of every time object as compiled.  Free-running mode: each stochastic object gets a numpy start seed
+// (recorded, or uniform 0..30 like np.random.randint(0, 31), stochasticy_models.py:12) and its
+// construction-time sample table[row][seed] (:15).  Executed by all lanes of the env's warp.
+JSL_DN void stoch_init(const InstDev* I, int32_t* tcur, uint16_t* tseed, const int32_t* start_seeds,
+                       const int32_t* tape, uint64_t seed, uint64_t env) {
+    const bool table_mode = tape == nullptr && I->sample_row != nullptr;
+    wp_for_dyn(I->n_tobj, [&](int i) {
+        int v = I->tobj_init[i];
+        if (table_mode) {
+            const int row = I->sample_row[i];
+            if (row >= 0) {
+                int sd;
+                if (start_seeds) sd = start_seeds[i];
+                else sd = (int)(philox4(seed, env, (uint32_t)i, 2u << 16).x % 31u);
+                if (sd < 0) sd = 0;
+                if (sd >= I->sample_depth) sd = I->sample_depth - 1;
+                tseed[i] = (uint16_t)sd;
+                if (!start_seeds) v = I->sample_table[row * I->sample_depth + sd];
+            }
+        }
+        tcur[i] = v;
+    });
 }
 
 // ------------------------------------------------------------------------------------ outages
 // outage_utils.py:20-131: sample, occupied time; static frequencies/durations (stochastic: TODO tape)
+template <bool ST>
 JSL_D int sample_outages(Ctx& c, int32_t& draw_ctr, int now, int n, const int32_t* freq, const int32_t* dur,
                          int freq_obj, int dur_obj, uint8_t* active, int32_t* a, int32_t* b) {
     int occupied = 0;
@@ -619,18 +665,20 @@ JSL_D int sample_outages(Ctx& c, int32_t& draw_ctr, int now, int n, const int32_
         int last = a[i] < 0 ? 0 : a[i];
         int elapsed = now - last;
         bool apply;
-        if (c.tcur && c.I->tobj_kind[freq_obj + i] != JSL_TIME_STATIC) {
-            apply = elapsed > c.tcur[freq_obj + i];  // outage_utils.py:32-42 _sample_frq
-            if (apply) tobj_update(c, draw_ctr, freq_obj + i, 0);
-        } else {
-            apply = freq[i] >= elapsed;  // sic, outage_utils.py:48
-        }
-        if (c.raise) return 0;
-        if (apply) {
-            int d = tobj_update(c, draw_ctr, dur_obj + i, dur[i]);
+        int d = dur[i];
+        if (ST) {
+            if (c.I->tobj_kind[freq_obj + i] != JSL_TIME_STATIC) {
+                apply = elapsed > c.aux->tcur[freq_obj + i];  // outage_utils.py:32-42 _sample_frq
+                if (apply) tobj_update<ST>(c, draw_ctr, freq_obj + i, 0);
+            } else {
+                apply = freq[i] >= elapsed;  // sic, outage_utils.py:48
+            }
+            if (apply) d = tobj_update<ST>(c, draw_ctr, dur_obj + i, d);
             if (c.raise) return 0;
-            active[i] = 1; a[i] = now; b[i] = now + d;
+        } else {
+            apply = freq[i] >= elapsed;
         }
+        if (apply) { active[i] = 1; a[i] = now; b[i] = now + d; }
     }
     bool any = false;
     for (int i = 0; i < n; i++)
@@ -648,8 +696,8 @@ JSL_D void release_outages(int n, uint8_t* active, int32_t* a, int32_t* b) {
 
 // ------------------------------------------------------------------------------------ machine handlers
 // validate.py:30-82.  returns false on a validation error (StateMachineResult.success = False)
-template <int JW>
-JSL_D bool machine_valid(const EnvS<JW>& s, Ctx& c, int m, int to, int job) {
+template <int JW, bool ST>
+JSL_D bool machine_valid(const EnvS<JW, ST>& s, Ctx& c, int m, int to, int job) {
     int from = s.m_state[m];
     if (from == to) return false;
     bool ok = from == JSL_M_IDLE ? to == JSL_M_SETUP
@@ -666,19 +714,19 @@ JSL_D bool machine_valid(const EnvS<JW>& s, Ctx& c, int m, int to, int job) {
 }
 
 // handler.py:414-457 + manipulate.py:378-444
-template <int JW>
-JSL_D void machine_idle_to_setup(EnvS<JW>& s, Ctx& c, int m, int j) {
+template <int JW, bool ST>
+JSL_D void machine_idle_to_setup(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     if (s.j_loc[j] != 3 * m) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     int o = I.job_op_start[j] + s.j_k[j];
     int tool = (c.op_mt[o] >> 16) & 0xffff;
     int setup = 0;
-    if (I.setup || c.tcur) {
+    if (I.setup || ST) {
         const int si = (m * I.NT + s.m_tool[m]) * I.NT + tool;
-        setup = setup_time_cur(c, si);
-        if (setup == JSL_NO_TIME && !(c.tcur && I.tobj_kind[I.off_setup + si] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
-        setup = tobj_update(c, s.draw_ctr, I.off_setup + si, setup);
+        setup = setup_time_cur<ST>(c, si);
+        if (setup == JSL_NO_TIME && !(ST && I.tobj_kind[I.off_setup + si] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+        setup = tobj_update<ST>(c, s.draw_ctr, I.off_setup + si, setup);
         if (c.raise) return;
     }
     if (s.m_job[m] != NONE8) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
@@ -688,25 +736,25 @@ JSL_D void machine_idle_to_setup(EnvS<JW>& s, Ctx& c, int m, int j) {
     s.m_state[m] = JSL_M_SETUP; s.m_occ[m] = c.now + setup; s.m_tool[m] = (uint8_t)tool;
 }
 // handler.py:460-503 + manipulate.py:225-276
-template <int JW>
-JSL_D void machine_setup_to_working(EnvS<JW>& s, Ctx& c, int m, int j) {
+template <int JW, bool ST>
+JSL_D void machine_setup_to_working(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8 || s.j_loc[j] != 3 * m + 2) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     const int o = I.job_op_start[j] + s.j_k[j];
-    int dur = tobj_update(c, s.draw_ctr, o, c.op_dur[o]);
+    int dur = tobj_update<ST>(c, s.draw_ctr, o, c.op_dur[o]);
     if (c.raise) return;
     s.j_proc[j] = 1; s.j_start[j] = c.now; s.j_end[j] = c.now + dur;
     s.m_state[m] = JSL_M_WORKING; s.m_occ[m] = c.now + dur;
 }
 // handler.py:506-543 + manipulate.py:328-375
-template <int JW>
-JSL_D void machine_working_to_outage(EnvS<JW>& s, Ctx& c, int m, int j) {
+template <int JW, bool ST>
+JSL_D void machine_working_to_outage(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     int occupied_for = 0;
     if (I.has_m_out) {
         int b = I.m_out_start[m], n = I.m_out_start[m + 1] - b;
-        OutS<JW>& o = *(OutS<JW>*)c.outs;
-        occupied_for = sample_outages(c, s.draw_ctr, c.now, n, I.m_out_freq + b, I.m_out_dur + b, I.off_mof + b,
+        OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
+        occupied_for = sample_outages<ST>(c, s.draw_ctr, c.now, n, I.m_out_freq + b, I.m_out_dur + b, I.off_mof + b,
                                       I.off_mod + b, o.mo_active + m * MAX_OUT, o.mo_a + m * MAX_OUT, o.mo_b + m * MAX_OUT);
         if (c.raise) return;
     }
@@ -715,16 +763,16 @@ JSL_D void machine_working_to_outage(EnvS<JW>& s, Ctx& c, int m, int j) {
     s.j_end[j] = c.now + occupied_for;
 }
 // handler.py:546-574 + manipulate.py:117-193
-template <int JW>
-JSL_D void machine_outage_to_idle(EnvS<JW>& s, Ctx& c, int m) {
+template <int JW, bool ST>
+JSL_D void machine_outage_to_idle(EnvS<JW, ST>& s, Ctx& c, int m) {
     const InstDev& I = *c.I;
     int j = s.m_job[m];
     if (j == NONE8 || !s.j_proc[j]) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     int k = s.j_k[j];
-    if (c.op_log) {
+    if (c.aux->op_log) {
         int o = I.job_op_start[j] + k;
-        c.op_log[2 * o] = s.j_start[j];
-        c.op_log[2 * o + 1] = c.now;
+        c.aux->op_log[2 * o] = s.j_start[j];
+        c.aux->op_log[2 * o + 1] = c.now;
     }
     s.j_k[j] = (uint8_t)(k + 1);
     s.j_proc[j] = 0;
@@ -735,7 +783,7 @@ JSL_D void machine_outage_to_idle(EnvS<JW>& s, Ctx& c, int m) {
     put_in_buffer(s, c, 3 * m + 1, j);
     if (c.raise) return;
     if (I.has_m_out) {
-        OutS<JW>& o = *(OutS<JW>*)c.outs;
+        OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
         release_outages(I.m_out_start[m + 1] - I.m_out_start[m], o.mo_active + m * MAX_OUT, o.mo_a + m * MAX_OUT,
                         o.mo_b + m * MAX_OUT);
     }
@@ -743,8 +791,8 @@ JSL_D void machine_outage_to_idle(EnvS<JW>& s, Ctx& c, int m) {
 }
 
 // process one machine transition (validate + handle); false = validation error
-template <int JW>
-JSL_D bool apply_machine(EnvS<JW>& s, Ctx& c, int m, int to, int job) {
+template <int JW, bool ST>
+JSL_D bool apply_machine(EnvS<JW, ST>& s, Ctx& c, int m, int to, int job) {
     if (!machine_valid(s, c, m, to, job)) return false;
     if (c.raise) return true;
     int from = s.m_state[m];
@@ -758,8 +806,8 @@ JSL_D bool apply_machine(EnvS<JW>& s, Ctx& c, int m, int to, int job) {
 // ------------------------------------------------------------------------------------ transport handlers
 JSL_D int t_general(int st) { return st == JSL_T_IDLE ? 0 : st == JSL_T_OUTAGE ? 2 : 1; }
 // validate.py:85-118 + transitions.py:82-107,161-186
-template <int JW>
-JSL_D bool transport_valid(const EnvS<JW>& s, int t, int to) {
+template <int JW, bool ST>
+JSL_D bool transport_valid(const EnvS<JW, ST>& s, int t, int to) {
     // bit (from*6 + to): idle->running, running->running|outage (same state only for WAITINGPICKUP), outage->idle
     constexpr uint64_t R = (1ull << JSL_T_WORKING) | (1ull << JSL_T_PICKUP) | (1ull << JSL_T_TRANSIT) | (1ull << JSL_T_WAITINGPICKUP);
     constexpr uint64_t RO = R | (1ull << JSL_T_OUTAGE);
@@ -776,8 +824,8 @@ JSL_D int output_place(Ctx& c) {
 }
 
 // handler.py:808-902 idle -> working (PICKUP)
-template <int JW>
-JSL_D void agv_idle_to_working(EnvS<JW>& s, Ctx& c, int t, int j) {
+template <int JW, bool ST>
+JSL_D void agv_idle_to_working(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     if (s.t_lockind[t] != 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -787,7 +835,7 @@ JSL_D void agv_idle_to_working(EnvS<JW>& s, Ctx& c, int t, int j) {
     int loc = s.j_loc[j];
     int src = place_of_buf(I, loc);
     if (src < 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TransportConfigError
-    int ttp = travel_time_cur(c, s.t_loc0[t], src);    // no resample (handler.py:876-885)
+    int ttp = travel_time_cur<ST>(c, s.t_loc0[t], src);    // no resample (handler.py:876-885)
     if (ttp == JSL_NO_TIME) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     s.t_occkind[t] = OCC_TIME; s.t_occ[t] = c.now + ttp;
     s.t_lockind[t] = 1; s.t_loc1[t] = (uint16_t)loc; s.t_loc2[t] = (uint8_t)target;
@@ -797,8 +845,8 @@ JSL_D void agv_idle_to_working(EnvS<JW>& s, Ctx& c, int t, int j) {
 }
 
 // handler.py:577-639 _get_waiting_time, :642-702, :989-1030
-template <int JW>
-JSL_D void agv_to_waitingpickup(EnvS<JW>& s, Ctx& c, int t, int j) {
+template <int JW, bool ST>
+JSL_D void agv_to_waitingpickup(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     int loc = s.j_loc[j];
@@ -831,8 +879,8 @@ JSL_D void agv_to_waitingpickup(EnvS<JW>& s, Ctx& c, int t, int j) {
 }
 
 // handler.py:705-805 (waiting)pickup -> transit
-template <int JW>
-JSL_D void agv_to_transit(EnvS<JW>& s, Ctx& c, int t, int j) {
+template <int JW, bool ST>
+JSL_D void agv_to_transit(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     int loc = s.j_loc[j];
@@ -844,10 +892,10 @@ JSL_D void agv_to_transit(EnvS<JW>& s, Ctx& c, int t, int j) {
     else dst = s.j_mach[j];  // get_next_not_done_operation(job).machine_id
     if (c.raise) return;
     if (!(src < I.M || dst < I.M)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
-    int travel = travel_time_cur(c, src, dst);
+    int travel = travel_time_cur<ST>(c, src, dst);
     const int tobj = I.off_travel + src * I.NP + dst;
-    if (travel == JSL_NO_TIME && !(c.tcur && I.tobj_kind[tobj] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TravelTimeError
-    travel = tobj_update(c, s.draw_ctr, tobj, travel);  // resampled (time_utils.py:15)
+    if (travel == JSL_NO_TIME && !(ST && I.tobj_kind[tobj] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TravelTimeError
+    travel = tobj_update<ST>(c, s.draw_ctr, tobj, travel);  // resampled (time_utils.py:15)
     if (c.raise) return;
     if (s.t_carry[t] != NONE8) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
     if (loc % 3 == 2 && loc < 3 * I.M) s.m_job[loc / 3] = NONE8;  // lifted out of a machine buffer
@@ -858,8 +906,8 @@ JSL_D void agv_to_transit(EnvS<JW>& s, Ctx& c, int t, int j) {
 }
 
 // handler.py:905-958 + manipulate.py:45-114 transit -> outage (drop-off)
-template <int JW>
-JSL_D void agv_transit_to_outage(EnvS<JW>& s, Ctx& c, int t, int j) {
+template <int JW, bool ST>
+JSL_D void agv_transit_to_outage(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     if (s.t_lockind[t] != 1) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -871,8 +919,8 @@ JSL_D void agv_transit_to_outage(EnvS<JW>& s, Ctx& c, int t, int j) {
     if (c.raise) return;
     int occupied_for = 0;
     if (I.has_t_out) {
-        OutS<JW>& o = *(OutS<JW>*)c.outs;
-        occupied_for = sample_outages(c, s.draw_ctr, c.now, I.n_t_out, I.t_out_freq, I.t_out_dur, I.off_tof, I.off_tod,
+        OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
+        occupied_for = sample_outages<ST>(c, s.draw_ctr, c.now, I.n_t_out, I.t_out_freq, I.t_out_dur, I.off_tof, I.off_tod,
                                       o.to_active + t * MAX_OUT, o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
         if (c.raise) return;
     }
@@ -884,8 +932,8 @@ JSL_D void agv_transit_to_outage(EnvS<JW>& s, Ctx& c, int t, int j) {
 }
 
 // process one transport transition; false = validation error
-template <int JW>
-JSL_D bool apply_transport(EnvS<JW>& s, Ctx& c, int t, int to, int job) {
+template <int JW, bool ST>
+JSL_D bool apply_transport(EnvS<JW, ST>& s, Ctx& c, int t, int to, int job) {
     if (!transport_valid(s, t, to)) return false;
     int from = s.t_state[t];
     if (from == JSL_T_IDLE && to == JSL_T_WORKING) agv_idle_to_working(s, c, t, job);
@@ -894,7 +942,7 @@ JSL_D bool apply_transport(EnvS<JW>& s, Ctx& c, int t, int to, int job) {
     else if ((from == JSL_T_WORKING || from == JSL_T_TRANSIT) && to == JSL_T_OUTAGE) agv_transit_to_outage(s, c, t, job);
     else if (from == JSL_T_OUTAGE && to == JSL_T_IDLE) {  // handler.py:961-986
         if (c.I->has_t_out) {
-            OutS<JW>& o = *(OutS<JW>*)c.outs;
+            OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
             release_outages(c.I->n_t_out, o.to_active + t * MAX_OUT, o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
         }
         s.t_state[t] = JSL_T_IDLE;
@@ -905,8 +953,8 @@ JSL_D bool apply_transport(EnvS<JW>& s, Ctx& c, int t, int to, int job) {
 
 // ------------------------------------------------------------------------------------ time machines
 // time_machines.py:133-221
-template <int JW>
-JSL_D int force_jump_to_event(const EnvS<JW>& s, Ctx& c) {
+template <int JW, bool ST>
+JSL_D int force_jump_to_event(const EnvS<JW, ST>& s, Ctx& c) {
     const InstDev& I = *c.I;
     int bj = wp_min<JW>(I.J, [&](int j) { return s.j_proc[j] ? s.j_end[j] : INT_BIG; });
     bool bad = false;
@@ -929,8 +977,8 @@ JSL_D int force_jump_to_event(const EnvS<JW>& s, Ctx& c) {
 // ------------------------------------------------------------------------------------ timed transitions
 // handler.py:55-153, :329-379: evaluate on the current snapshot into the x_* scratch arrays.
 // returns true when at least one transition was created.
-template <int JW>
-JSL_D bool create_timed(EnvS<JW>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm) {
+template <int JW, bool ST>
+JSL_D bool create_timed(EnvS<JW, ST>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm) {
     const InstDev& I = *c.I;
     const int now = c.now;
     // machines: occupied_till reached -> next state
@@ -1014,8 +1062,8 @@ constexpr int TM_JUMP = 0, TM_FORCE = 1;
 // was applied after them), so they double as the new possible_transitions.
 // Returns success (false = validation error -> StateMachineResult.success=False); escaping exceptions
 // are left in c.raise.
-template <int JW>
-JSL_D bool sm_step(EnvS<JW>& s, Ctx& c, bool has_action, Trans act, int time_machine) {
+template <int JW, bool ST>
+JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time_machine) {
     const InstDev& I = *c.I;
     c.now = s.time;
     Mask<1> mm;
@@ -1055,13 +1103,13 @@ JSL_D bool sm_step(EnvS<JW>& s, Ctx& c, bool has_action, Trans act, int time_mac
                     if (nxt == -2) { bad = true; return false; }
                     if (cur == nxt) return true;
                     if (cur < 0) { bad = true; return false; }
-                    int tt = travel_time_cur(c, cur, nxt);
+                    int tt = travel_time_cur<ST>(c, cur, nxt);
                     if (tt == JSL_NO_TIME) { bad = true; return false; }
                     return tt == 0;
                 };
                 Mask<JW> zr = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.lr.test(j) && zero_travel(j, bd); });
                 Mask<JW> zi = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.li.test(j) && zero_travel(j, bd); });
-                if (I.travel || c.tcur || I.out_buf < 0) {
+                if (I.travel || ST || I.out_buf < 0) {
                     Mask<JW> badm = wp_ballot<JW>(I.J, [&](int j) {
                         bool bd = false;
                         if (p.lr.test(j) || p.li.test(j)) zero_travel(j, bd);
@@ -1119,8 +1167,8 @@ JSL_D bool sm_step(EnvS<JW>& s, Ctx& c, bool has_action, Trans act, int time_mac
 }
 
 // ------------------------------------------------------------------------------------ reset
-template <int JW>
-JSL_D void env_init(EnvS<JW>& s, Ctx& c) {
+template <int JW, bool ST>
+JSL_D void env_init(EnvS<JW, ST>& s, Ctx& c) {
     const InstDev& I = *c.I;
     s.time = I.start_time; s.seq_ctr = 0; s.n_possible = 0; s.skip = 0;
     s.joker = c.C->truncation_joker; s.step_noop = 0; s.step_action = 0; s.reward_noop = 0;
@@ -1128,7 +1176,7 @@ JSL_D void env_init(EnvS<JW>& s, Ctx& c) {
     s.terminated = 0; s.truncated = 0; s.last_action_empty = 1; s.obs_done = 0;
     s.ret = 0.0;
     JSL_SYNCWARP();
-    wp_for<JW>(EnvS<JW>::MJ, [&](int j) {
+    wp_for<JW>(EnvS<JW, ST>::MJ, [&](int j) {
         bool live = j < I.J;
         s.j_start[j] = -1; s.j_end[j] = -1;
         s.j_seq[j] = (uint32_t)j;  // initial stores list jobs in job order (mapper.py:1296-1321)
@@ -1140,61 +1188,38 @@ JSL_D void env_init(EnvS<JW>& s, Ctx& c) {
         s.m_occ[m] = JSL_NO_TIME; s.m_done[m] = 0; s.m_state[m] = JSL_M_IDLE;
         s.m_tool[m] = (uint8_t)I.default_tool; s.m_job[m] = NONE8; s.x_mkind[m] = 0; s.x_mjob[m] = NONE8;
     });
-    wp_for<JW>(EnvS<JW>::MT, [&](int t) {
+    wp_for<JW>(EnvS<JW, ST>::MT, [&](int t) {
         s.t_occ[t] = -1; s.t_loc1[t] = 0; s.t_tdbuf[t] = 0;
         s.t_state[t] = JSL_T_IDLE; s.t_job[t] = NONE8; s.t_carry[t] = NONE8; s.t_occkind[t] = OCC_NOTIME;
         s.t_lockind[t] = 0; s.t_loc0[t] = t < I.T ? I.agv_init_place[t] : 0; s.t_loc2[t] = 0;
         s.t_tdcomp[t] = NONE8; s.t_tdjob[t] = NONE8; s.x_tkind[t] = NONE8; s.x_tcomp[t] = 0; s.x_tjob[t] = NONE8;
     });
-    if (c.outs) {
-        OutS<JW>& o = *(OutS<JW>*)c.outs;
+    if (c.aux->outs) {
+        OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
         wp_for<1>(32, [&](int m) {
             for (int k = 0; k < MAX_OUT; k++) { o.mo_active[m * MAX_OUT + k] = 0; o.mo_a[m * MAX_OUT + k] = -1; o.mo_b[m * MAX_OUT + k] = -1; }
         });
-        wp_for<JW>(EnvS<JW>::MT, [&](int t) {
+        wp_for<JW>(EnvS<JW, ST>::MT, [&](int t) {
             for (int k = 0; k < MAX_OUT; k++) { o.to_active[t * MAX_OUT + k] = 0; o.to_a[t * MAX_OUT + k] = -1; o.to_b[t * MAX_OUT + k] = -1; }
         });
     }
-    s.seq_ctr = EnvS<JW>::MJ;
+    s.seq_ctr = EnvS<JW, ST>::MJ;
     s.draw_ctr = 0;
-    if (c.tcur) {
-        // .time of every time object as compiled; in Philox mode the non-op stochastic objects get their
-        // construction-time sample (stochasticy_models.py:15) from the env's own stream
-        // .time of every time object as compiled.  Free-running mode: each stochastic object gets a numpy
-        // start seed (recorded, or uniform 0..30 like np.random.randint(0, 31), stochasticy_models.py:12) and
-        // its construction-time sample table[row][seed] (:15).
-        const bool table_mode = c.tape == nullptr && I.sample_row != nullptr;
-        wp_for_dyn(I.n_tobj, [&](int i) {
-            int v = I.tobj_init[i];
-            if (table_mode) {
-                const int row = I.sample_row[i];
-                if (row >= 0) {
-                    int sd;
-                    if (c.start_seeds) sd = c.start_seeds[i];
-                    else sd = (int)(philox4(c.seed, c.env_id, (uint32_t)i, 2u << 16).x % 31u);
-                    if (sd < 0) sd = 0;
-                    if (sd >= I.sample_depth) sd = I.sample_depth - 1;
-                    c.tseed[i] = (uint16_t)sd;
-                    if (!c.start_seeds) v = I.sample_table[row * I.sample_depth + sd];
-                }
-            }
-            c.tcur[i] = v;
-        });
-    }
+    if (ST) stoch_init(c.I, c.aux->tcur, c.aux->tseed, c.aux->start_seeds, c.aux->tape, c.aux->seed, c.aux->env_id);
     JSL_SYNCWARP();
 }
 
 // ------------------------------------------------------------------------------------ reward / step
 // rewards.py:118-148 BinaryActionJsspReward.make, IEEE double without contraction
-template <int JW>
-JSL_D double make_reward(EnvS<JW>& s, const Ctx& c) {
+template <int JW, bool ST>
+JSL_D double make_reward(EnvS<JW, ST>& s, const Ctx& c) {
     double sr;
     if (s.truncated) sr = (c.C->truncation_bias * 1.0) / c.C->sparse_bias;
     else if (!s.terminated) sr = 0.0;
-    else sr = (double)(c.max_allowed_time - s.time) / (double)(c.max_allowed_time - c.lower_bound);
+    else sr = (double)(c.aux->max_allowed_time - s.time) / (double)(c.aux->max_allowed_time - c.aux->lower_bound);
     if (s.last_action_empty) s.reward_noop = s.reward_noop + 1;
     else s.reward_noop = 0;
-    const double dr = s.reward_noop >= c.I->J ? c.neg_inv_n : 0.0;  // -int(flag) / N
+    const double dr = s.reward_noop >= c.I->J ? c.aux->neg_inv_n : 0.0;  // -int(flag) / N
 #if defined(__CUDACC__) && !defined(JSL_HOST_SIM)
     return __dadd_rn(__dmul_rn(sr, c.C->sparse_bias), __dmul_rn(dr, c.C->dense_bias));
 #else
@@ -1214,8 +1239,8 @@ struct StepPlan {
 
 // everything before the state machine: argument checks, SubTimeStepper, what to run.
 // returns false when env.step raises before touching the state machine (status is set).
-template <int JW>
-JSL_D bool env_step_pre(EnvS<JW>& s, Ctx& c, int action, StepPlan& plan) {
+template <int JW, bool ST>
+JSL_D bool env_step_pre(EnvS<JW, ST>& s, Ctx& c, int action, StepPlan& plan) {
     plan.run_sm = false; plan.has_action = false; plan.time_machine = TM_JUMP;
     plan.act.kind = 0; plan.act.comp = 0; plan.act.new_state = 0; plan.act.job = 0;
     if (s.status > JSL_ST_TRUNCATED) return false;                                     // a raise already escaped
@@ -1236,8 +1261,8 @@ JSL_D bool env_step_pre(EnvS<JW>& s, Ctx& c, int action, StepPlan& plan) {
 }
 
 // everything after it: middleware bookkeeping, terminated/truncated, reward.
-template <int JW>
-JSL_D double env_step_post(EnvS<JW>& s, Ctx& c, int action, const StepPlan& plan, bool success) {
+template <int JW, bool ST>
+JSL_D double env_step_post(EnvS<JW, ST>& s, Ctx& c, int action, const StepPlan& plan, bool success) {
     if (c.raise) { s.status = c.raise; return 0.0; }
     const bool action_empty = action == 0;
     if (action == 0 && plan.run_sm) {
@@ -1269,12 +1294,12 @@ JSL_D double env_step_post(EnvS<JW>& s, Ctx& c, int action, const StepPlan& plan
 // One env operation: OP_RESET (env.reset: init + dummy step) or an env.step(action).  The only place
 // sm_step is instantiated.
 constexpr int OP_RESET = -1;
-template <int JW>
-JSL_D double run_env_op(EnvS<JW>& s, Ctx& c, int op) {
+template <int JW, bool ST>
+JSL_D double run_env_op(EnvS<JW, ST>& s, Ctx& c, int op) {
     StepPlan plan;
     if (op == OP_RESET) {
         env_init(s, c);
-        if (c.op_log) wp_for_dyn(2 * c.I->N, [&](int i) { c.op_log[i] = -1; });
+        if (c.aux->op_log) wp_for_dyn(2 * c.I->N, [&](int i) { c.aux->op_log[i] = -1; });
         plan.run_sm = true; plan.has_action = false; plan.time_machine = TM_JUMP;
         plan.act.kind = 0; plan.act.comp = 0; plan.act.new_state = 0; plan.act.job = 0;
     } else if (!env_step_pre(s, c, op, plan)) {
@@ -1307,8 +1332,8 @@ JSL_D uint32_t philox_bit(uint64_t seed, uint64_t env_idx, uint32_t step) {
 }
 
 // dipatching_benchmark.py:17-67 + dispatch_rules_uitls.py:57-111
-template <int JW>
-JSL_D int policy_action(const EnvS<JW>& s, const Ctx& c, int policy, uint64_t seed, uint64_t env_idx,
+template <int JW, bool ST>
+JSL_D int policy_action(const EnvS<JW, ST>& s, const Ctx& c, int policy, uint64_t seed, uint64_t env_idx,
                         const int32_t* job_work) {
     const InstDev& I = *c.I;
     if (policy == JSL_POLICY_RANDOM) return (int)philox_bit(seed, env_idx, (uint32_t)s.n_steps);
@@ -1317,10 +1342,10 @@ JSL_D int policy_action(const EnvS<JW>& s, const Ctx& c, int policy, uint64_t se
     if (cand.kind == 1) return 1;
     const int pre = 3 * cand.comp, cj = cand.job;
     auto key = [&](int j) {
-        if (policy == JSL_POLICY_SPT) return op_duration(c, I.job_op_start[j] + s.j_k[j]);
-        if (!c.tcur) return (int)job_work[j];
+        if (policy == JSL_POLICY_SPT) return op_duration<ST>(c, I.job_op_start[j] + s.j_k[j]);
+        if (!ST) return (int)job_work[j];
         int w = 0;
-        for (int o = I.job_op_start[j]; o < I.job_op_start[j + 1]; o++) w += c.tcur[o];
+        for (int o = I.job_op_start[j]; o < I.job_op_start[j + 1]; o++) w += c.aux->tcur[o];
         return w;
     };
     const int ck = key(cj);
@@ -1347,8 +1372,8 @@ JSL_D int policy_action(const EnvS<JW>& s, const Ctx& c, int policy, uint64_t se
 JSL_HD int obs_bytes_binary(int J, int M) { return (16 + 4 * J + 4 * M + 2 * J + M + J * M + 15) & ~15; }
 JSL_HD int obs_bytes_oparray(int J, int N) { return (16 + 4 * N + 4 * J + 15) & ~15; }
 
-template <int JW>
-JSL_D void cand_floats(const EnvS<JW>& s, const Ctx& c, float* tr) {
+template <int JW, bool ST>
+JSL_D void cand_floats(const EnvS<JW, ST>& s, const Ctx& c, float* tr) {
     const InstDev& I = *c.I;
     if (!s.obs_done && s.n_possible - s.skip > 0) {
         Trans cand = current_candidate(s, c);
@@ -1361,8 +1386,8 @@ JSL_D void cand_floats(const EnvS<JW>& s, const Ctx& c, float* tr) {
     }
 }
 
-template <int JW>
-JSL_D void write_obs_binary(const EnvS<JW>& s, const Ctx& c, uint8_t* out) {
+template <int JW, bool ST>
+JSL_D void write_obs_binary(const EnvS<JW, ST>& s, const Ctx& c, uint8_t* out) {
     const InstDev& I = *c.I;
     const int J = I.J, M = I.M;
     float tr[3];
@@ -1376,7 +1401,7 @@ JSL_D void write_obs_binary(const EnvS<JW>& s, const Ctx& c, uint8_t* out) {
     int8_t* exec = mrun + M;
     const int total = obs_bytes_binary(J, M);
     wp_for_dyn(1, [&](int) {
-        f[0] = (float)((double)s.time / (double)c.max_allowed_time);
+        f[0] = (float)((double)s.time / (double)c.aux->max_allowed_time);
         f[1] = tr[0]; f[2] = tr[1]; f[3] = tr[2];
         for (int i = 16 + 4 * J + 4 * M + 2 * J + M + J * M; i < total; i++) out[i] = 0;
     });
@@ -1401,8 +1426,8 @@ JSL_D void write_obs_binary(const EnvS<JW>& s, const Ctx& c, uint8_t* out) {
 
 // BinaryOperationArrayObservation.make (observations.py:631-693 over :588-618):
 //   f32 current_transition[3] | f32 0 | f32 operation_state[N] | f32 job_locations[J]
-template <int JW>
-JSL_D void write_obs_oparray(const EnvS<JW>& s, Ctx& c, uint8_t* out) {
+template <int JW, bool ST>
+JSL_D void write_obs_oparray(const EnvS<JW, ST>& s, Ctx& c, uint8_t* out) {
     const InstDev& I = *c.I;
     float tr[3];
     cand_floats(s, c, tr);
@@ -1437,8 +1462,8 @@ JSL_D void write_obs_oparray(const EnvS<JW>& s, Ctx& c, uint8_t* out) {
 // ------------------------------------------------------------------------------------ canonical digest
 // Layout documented in DESIGN.md / oracle/ref_harness.py.  Executed by one env's warp (diagnostics,
 // parity tests, render()).  Returns the number of int32 produced (writes at most cap).
-template <int JW>
-JSL_D int write_digest(const EnvS<JW>& s, const Ctx& c, int32_t* out, int cap) {
+template <int JW, bool ST>
+JSL_D int write_digest(const EnvS<JW, ST>& s, const Ctx& c, int32_t* out, int cap) {
     const InstDev& I = *c.I;
     int n = 0;
     // executed redundantly by every lane with identical values (uniform stores)
@@ -1448,7 +1473,7 @@ JSL_D int write_digest(const EnvS<JW>& s, const Ctx& c, int32_t* out, int cap) {
         int k = s.j_k[j], nops = job_nops(I, j), o0 = I.job_op_start[j];
         JSL_PUT(k); JSL_PUT(s.j_proc[j]); JSL_PUT(s.j_loc[j]);
         for (int i = 0; i < nops; i++) {
-            if (i < k) { JSL_PUT(2); JSL_PUT(c.op_log ? c.op_log[2 * (o0 + i)] : -1); JSL_PUT(c.op_log ? c.op_log[2 * (o0 + i) + 1] : -1); }
+            if (i < k) { JSL_PUT(2); JSL_PUT(c.aux->op_log ? c.aux->op_log[2 * (o0 + i)] : -1); JSL_PUT(c.aux->op_log ? c.aux->op_log[2 * (o0 + i) + 1] : -1); }
             else if (i == k && s.j_proc[j]) { JSL_PUT(1); JSL_PUT(s.j_start[j]); JSL_PUT(s.j_end[j]); }
             else { JSL_PUT(0); JSL_PUT(-1); JSL_PUT(-1); }
         }
@@ -1480,8 +1505,8 @@ JSL_D int write_digest(const EnvS<JW>& s, const Ctx& c, int32_t* out, int cap) {
         JSL_PUT(s.t_lockind[t] ? (int)s.t_loc1[t] : -1); JSL_PUT(s.t_lockind[t] ? (int)s.t_loc2[t] : -1);
     }
     for (int b = 3 * I.M + I.T; b < I.NB; b++) put_store(b);
-    if (c.outs) {
-        const OutS<JW>& ou = *(const OutS<JW>*)c.outs;
+    if (c.aux->outs) {
+        const OutS<JW>& ou = *(const OutS<JW>*)c.aux->outs;
         for (int m = 0; m < I.M; m++) {
             int nm = I.has_m_out ? I.m_out_start[m + 1] - I.m_out_start[m] : 0;
             for (int k = 0; k < nm; k++) {

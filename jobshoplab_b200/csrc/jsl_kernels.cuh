@@ -17,10 +17,10 @@ namespace jsl {
 
 constexpr int WARPS_PER_CTA = 4;
 #ifndef JSL_ROLLOUT_MIN_CTAS
-#define JSL_ROLLOUT_MIN_CTAS 10  // resident CTAs per SM the rollout kernel is register-budgeted for
+#define JSL_ROLLOUT_MIN_CTAS 12  // resident CTAs per SM the rollout kernel is register-budgeted for
 #endif
 #ifndef JSL_STEP_MIN_CTAS
-#define JSL_STEP_MIN_CTAS 12
+#define JSL_STEP_MIN_CTAS 10
 #endif
 
 struct BatchDev {
@@ -40,7 +40,6 @@ struct BatchDev {
     const int32_t* start_seeds;  // [B][n_tobj] or nullptr
 };
 
-template <int JW>
 __device__ __forceinline__ void copy_in(void* dst, const void* src, int bytes) {
     const int4* s = (const int4*)src;
     int4* d = (int4*)dst;
@@ -48,32 +47,38 @@ __device__ __forceinline__ void copy_in(void* dst, const void* src, int bytes) {
     __syncwarp();
 }
 
-template <int JW>
-__device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env, void* outs_sm) {
+// per-warp shared-memory slot: EnvS | OutS (optional) | EnvAux
+__device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env, uint8_t* slot) {
     const InstDev& I = bd.inst;
     int64_t v = env % I.n_inst;
+    EnvAux* aux = (EnvAux*)(slot + bd.state_stride + bd.outs_stride);
     c.I = &bd.inst;
     c.C = &bd.cfg;
     c.op_mt = I.op_mt + v * I.N;
     c.op_dur = I.op_dur + v * I.N;
-    c.op_log = bd.op_log ? bd.op_log + env * 2 * (int64_t)I.N : nullptr;
-    c.outs = outs_sm;
+    c.aux = aux;
     c.raise = 0;
     c.now = 0;
-    c.lower_bound = I.lb_mat[2 * v];
-    c.max_allowed_time = I.lb_mat[2 * v + 1];
-    c.neg_inv_n = -1.0 / (double)I.N;
-    c.tcur = bd.tcur ? bd.tcur + env * (int64_t)I.n_tobj : nullptr;
-    c.tape = bd.tape ? bd.tape + env * bd.tape_stride : nullptr;
-    c.tape_len = (int)bd.tape_stride;
-    c.tseed = bd.tseed ? bd.tseed + env * (int64_t)I.n_tobj : nullptr;
-    c.start_seeds = bd.start_seeds ? bd.start_seeds + env * (int64_t)I.n_tobj : nullptr;
-    c.seed = bd.seed;
-    c.env_id = (uint64_t)(bd.env_base + env);
+    __syncwarp();
+    if (JSL_LANE == 0) {
+        aux->op_log = bd.op_log ? bd.op_log + env * 2 * (int64_t)I.N : nullptr;
+        aux->outs = bd.outs ? (void*)(slot + bd.state_stride) : nullptr;
+        aux->tcur = bd.tcur ? bd.tcur + env * (int64_t)I.n_tobj : nullptr;
+        aux->tseed = bd.tseed ? bd.tseed + env * (int64_t)I.n_tobj : nullptr;
+        aux->start_seeds = bd.start_seeds ? bd.start_seeds + env * (int64_t)I.n_tobj : nullptr;
+        aux->tape = bd.tape ? bd.tape + env * bd.tape_stride : nullptr;
+        aux->tape_len = (int)bd.tape_stride;
+        aux->seed = bd.seed;
+        aux->env_id = (uint64_t)(bd.env_base + env);
+        aux->lower_bound = I.lb_mat[2 * v];
+        aux->max_allowed_time = I.lb_mat[2 * v + 1];
+        aux->neg_inv_n = -1.0 / (double)I.N;
+    }
+    __syncwarp();
 }
 
-template <int JW>
-__device__ __forceinline__ void write_step_out(const EnvS<JW>& s, Ctx& c, const jsl_step_out& out, int64_t env,
+template <int JW, bool ST>
+__device__ __forceinline__ void write_step_out(const EnvS<JW, ST>& s, Ctx& c, const jsl_step_out& out, int64_t env,
                                                double reward, int obs_bytes) {
     const InstDev& I = *c.I;
     if (out.obs && s.status <= JSL_ST_STEP_FAILED) {
@@ -105,7 +110,7 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW>& s, Ctx& c, const 
     (void)I;
 }
 
-template <int JW>
+template <int JW, bool ST>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -113,33 +118,35 @@ k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, j
     const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
     if (env >= bd.B) return;
     if (mask && !mask[env]) return;
-    EnvS<JW>& s = *(EnvS<JW>*)(smem + (size_t)warp * (bd.state_stride + bd.outs_stride));
+    uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
+    EnvS<JW, ST>& s = *(EnvS<JW, ST>*)slot;
     void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
     Ctx c;
-    make_ctx<JW>(c, bd, env, outs_sm);
+    make_ctx(c, bd, env, slot);
     run_env_op(s, c, OP_RESET);
     __syncwarp();
     write_step_out(s, c, out, env, 0.0, obs_bytes);
     __syncwarp();
-    copy_in<JW>(bd.state + env * (int64_t)bd.state_stride, &s, bd.state_stride);
-    if (bd.outs) copy_in<JW>(bd.outs + env * (int64_t)bd.outs_stride, outs_sm, bd.outs_stride);
+    copy_in(bd.state + env * (int64_t)bd.state_stride, &s, bd.state_stride);
+    if (bd.outs) copy_in(bd.outs + env * (int64_t)bd.outs_stride, outs_sm, bd.outs_stride);
 }
 
-template <int JW>
+template <int JW, bool ST>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_STEP_MIN_CTAS)
 k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
     const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
     if (env >= bd.B) return;
-    EnvS<JW>& s = *(EnvS<JW>*)(smem + (size_t)warp * (bd.state_stride + bd.outs_stride));
+    uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
+    EnvS<JW, ST>& s = *(EnvS<JW, ST>*)slot;
     void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
     uint8_t* g_state = bd.state + env * (int64_t)bd.state_stride;
     uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
-    copy_in<JW>(&s, g_state, bd.state_stride);
-    if (g_outs) copy_in<JW>(outs_sm, g_outs, bd.outs_stride);
+    copy_in(&s, g_state, bd.state_stride);
+    if (g_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
     Ctx c;
-    make_ctx<JW>(c, bd, env, outs_sm);
+    make_ctx(c, bd, env, slot);
     const int action = actions[env];
     double r = run_env_op(s, c, action);
     __syncwarp();
@@ -150,8 +157,8 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
             step_noop = s.step_noop;
         double ret = s.ret;
         __syncwarp();
-        copy_in<JW>(&s, g_state, bd.state_stride);
-        if (g_outs) copy_in<JW>(outs_sm, g_outs, bd.outs_stride);
+        copy_in(&s, g_state, bd.state_stride);
+        if (g_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
         s.status = status;
         if (status == JSL_ST_STEP_FAILED) {
             s.truncated = 1; s.terminated = 0; s.obs_done = 1;
@@ -162,28 +169,29 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     }
     write_step_out(s, c, out, env, r, obs_bytes);
     __syncwarp();
-    copy_in<JW>(g_state, &s, bd.state_stride);
-    if (g_outs) copy_in<JW>(g_outs, outs_sm, bd.outs_stride);
+    copy_in(g_state, &s, bd.state_stride);
+    if (g_outs) copy_in(g_outs, outs_sm, bd.outs_stride);
 }
 
-template <int JW>
+template <int JW, bool ST>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_ROLLOUT_MIN_CTAS)
 k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __restrict__ tape, int64_t tape_stride,
           int max_steps, int flags, jsl_rollout_out out) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
-    EnvS<JW>& s = *(EnvS<JW>*)(smem + (size_t)warp * (bd.state_stride + bd.outs_stride));
+    uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
+    EnvS<JW, ST>& s = *(EnvS<JW, ST>*)slot;
     void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
     const int64_t stride = (int64_t)gridDim.x * WARPS_PER_CTA;
     for (int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; env < bd.B; env += stride) {
         uint8_t* g_state = bd.state + env * (int64_t)bd.state_stride;
         uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
         Ctx c;
-        make_ctx<JW>(c, bd, env, outs_sm);
+        make_ctx(c, bd, env, slot);
         bool pending_reset = (flags & JSL_RO_RESET_FIRST) != 0;
         if (!pending_reset) {
-            copy_in<JW>(&s, g_state, bd.state_stride);
-            if (g_outs) copy_in<JW>(outs_sm, g_outs, bd.outs_stride);
+            copy_in(&s, g_state, bd.state_stride);
+            if (g_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
         }
         __syncwarp();
         const int32_t* job_work = bd.inst.job_work + (env % bd.inst.n_inst) * bd.inst.J;
@@ -217,23 +225,24 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
         }
         __syncwarp();
         if (!(flags & JSL_RO_NO_WRITEBACK)) {
-            copy_in<JW>(g_state, &s, bd.state_stride);
-            if (g_outs) copy_in<JW>(g_outs, outs_sm, bd.outs_stride);
+            copy_in(g_state, &s, bd.state_stride);
+            if (g_outs) copy_in(g_outs, outs_sm, bd.outs_stride);
         }
         __syncwarp();
     }
 }
 
-template <int JW>
+template <int JW, bool ST>
 __global__ void __launch_bounds__(32)
 k_digest(const __grid_constant__ BatchDev bd, int64_t env, int32_t* out, int cap, int32_t* n_out) {
     extern __shared__ __align__(16) uint8_t smem[];
-    EnvS<JW>& s = *(EnvS<JW>*)smem;
+    uint8_t* slot = smem;
+    EnvS<JW, ST>& s = *(EnvS<JW, ST>*)smem;
     void* outs_sm = bd.outs ? (void*)(smem + bd.state_stride) : nullptr;
-    copy_in<JW>(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
-    if (bd.outs) copy_in<JW>(outs_sm, bd.outs + env * (int64_t)bd.outs_stride, bd.outs_stride);
+    copy_in(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
+    if (bd.outs) copy_in(outs_sm, bd.outs + env * (int64_t)bd.outs_stride, bd.outs_stride);
     Ctx c;
-    make_ctx<JW>(c, bd, env, outs_sm);
+    make_ctx(c, bd, env, slot);
     int n = write_digest(s, c, out, cap);
     if (JSL_LANE == 0) *n_out = n;
 }
@@ -244,35 +253,35 @@ struct LaunchCfg {
     cudaStream_t stream;
 };
 
-template <int JW>
+template <int JW, bool ST>
 cudaError_t launch_reset(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* mask, jsl_step_out out, int obs_bytes) {
-    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_reset<JW>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
-    k_reset<JW><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, mask, out, obs_bytes);
+    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_reset<JW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+    k_reset<JW, ST><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, mask, out, obs_bytes);
     return cudaGetLastError();
 }
-template <int JW>
+template <int JW, bool ST>
 cudaError_t launch_step(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* actions, jsl_step_out out, int obs_bytes) {
-    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_step<JW>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
-    k_step<JW><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, actions, out, obs_bytes);
+    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_step<JW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+    k_step<JW, ST><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, actions, out, obs_bytes);
     return cudaGetLastError();
 }
-template <int JW>
+template <int JW, bool ST>
 cudaError_t launch_rollout(const BatchDev& bd, const LaunchCfg& lc, int policy, const uint8_t* tape, int64_t tape_stride,
                            int max_steps, int flags, jsl_rollout_out out) {
-    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
-    k_rollout<JW><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, policy, tape, tape_stride, max_steps, flags, out);
+    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+    k_rollout<JW, ST><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, policy, tape, tape_stride, max_steps, flags, out);
     return cudaGetLastError();
 }
-template <int JW>
+template <int JW, bool ST>
 cudaError_t launch_digest(const BatchDev& bd, const LaunchCfg& lc, int64_t env, int32_t* out, int cap, int32_t* n_out) {
-    k_digest<JW><<<1, 32, lc.smem, lc.stream>>>(bd, env, out, cap, n_out);
+    k_digest<JW, ST><<<1, 32, lc.smem, lc.stream>>>(bd, env, out, cap, n_out);
     return cudaGetLastError();
 }
-template <int JW>
+template <int JW, bool ST>
 int rollout_occupancy(int smem) {  // resident CTAs per SM for the persistent rollout grid
     int n = 0;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_rollout<JW>, WARPS_PER_CTA * 32, smem) != cudaSuccess) return 8;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_rollout<JW, ST>, WARPS_PER_CTA * 32, smem) != cudaSuccess) return 8;
     return n > 0 ? n : 1;
 }
 
@@ -292,20 +301,20 @@ JSL_DECLARE_JW(4)
 
 #define JSL_DEFINE_JW(N)                                                                                              \
     cudaError_t launch_reset_jw##N(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* m, jsl_step_out o, int ob) { \
-        return launch_reset<N>(bd, lc, m, o, ob);                                                                     \
+        return bd.tcur ? launch_reset<N, true>(bd, lc, m, o, ob) : launch_reset<N, false>(bd, lc, m, o, ob);                                                                     \
     }                                                                                                                 \
     cudaError_t launch_step_jw##N(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* a, jsl_step_out o, int ob) { \
-        return launch_step<N>(bd, lc, a, o, ob);                                                                      \
+        return bd.tcur ? launch_step<N, true>(bd, lc, a, o, ob) : launch_step<N, false>(bd, lc, a, o, ob);                                                                      \
     }                                                                                                                 \
     cudaError_t launch_rollout_jw##N(const BatchDev& bd, const LaunchCfg& lc, int p, const uint8_t* t, int64_t ts,    \
                                      int ms, int f, jsl_rollout_out o) {                                              \
-        return launch_rollout<N>(bd, lc, p, t, ts, ms, f, o);                                                         \
+        return bd.tcur ? launch_rollout<N, true>(bd, lc, p, t, ts, ms, f, o) : launch_rollout<N, false>(bd, lc, p, t, ts, ms, f, o);                                                         \
     }                                                                                                                 \
     cudaError_t launch_digest_jw##N(const BatchDev& bd, const LaunchCfg& lc, int64_t e, int32_t* o, int c, int32_t* n) { \
-        return launch_digest<N>(bd, lc, e, o, c, n);                                                                  \
+        return bd.tcur ? launch_digest<N, true>(bd, lc, e, o, c, n) : launch_digest<N, false>(bd, lc, e, o, c, n);                                                                  \
     }                                                                                                                 \
-    int rollout_occupancy_jw##N(int smem) { return rollout_occupancy<N>(smem); }                                      \
-    int state_bytes_jw##N() { return (int)sizeof(EnvS<N>); }                                                          \
+    int rollout_occupancy_jw##N(int smem) { return rollout_occupancy<N, false>(smem); }                                      \
+    int state_bytes_jw##N() { return (int)sizeof(EnvS<N, false>); }                                                          \
     int outs_bytes_jw##N() { return (int)sizeof(OutS<N>); }
 
 }  // namespace jsl

@@ -35,6 +35,7 @@ struct Sim {
     std::vector<int32_t> tcur, tape, start_seeds;
     std::vector<uint16_t> tseed;
     uint64_t env_id = 0;
+    EnvAux aux;
 };
 
 template <class T, class U>
@@ -58,56 +59,58 @@ void lex_order(const char* pfx, int n, std::vector<uint8_t>& out) {
     }
 }
 
-template <int JW> void make_ctx(Sim* s, Ctx& c) {
+void make_ctx(Sim* s, Ctx& c) {
+    EnvAux& a = s->aux;
     c.I = &s->I; c.C = &s->C; c.op_mt = s->op_mt.data(); c.op_dur = s->op_dur.data();
-    c.op_log = s->C.record_ops ? s->op_log.data() : nullptr;
-    c.outs = s->outs_bytes ? (void*)s->outs.data() : nullptr;
-    c.raise = 0; c.now = 0; c.lower_bound = s->lb_mat[0]; c.max_allowed_time = s->lb_mat[1]; c.neg_inv_n = -1.0 / (double)s->I.N;
-    c.tcur = s->tobj.stochastic ? s->tcur.data() : nullptr;
-    c.tape = s->tape.empty() ? nullptr : s->tape.data(); c.tape_len = (int)s->tape.size();
-    c.seed = s->seed; c.env_id = s->env_id;
-    c.tseed = s->tobj.stochastic ? s->tseed.data() : nullptr;
-    c.start_seeds = s->start_seeds.empty() ? nullptr : s->start_seeds.data();
+    c.aux = &a; c.raise = 0; c.now = 0;
+    a.op_log = s->C.record_ops ? s->op_log.data() : nullptr;
+    a.outs = s->outs_bytes ? (void*)s->outs.data() : nullptr;
+    a.tcur = s->tobj.stochastic ? s->tcur.data() : nullptr;
+    a.tseed = s->tobj.stochastic ? s->tseed.data() : nullptr;
+    a.start_seeds = s->start_seeds.empty() ? nullptr : s->start_seeds.data();
+    a.tape = s->tape.empty() ? nullptr : s->tape.data(); a.tape_len = (int)s->tape.size();
+    a.seed = s->seed; a.env_id = s->env_id;
+    a.lower_bound = s->lb_mat[0]; a.max_allowed_time = s->lb_mat[1]; a.neg_inv_n = -1.0 / (double)s->I.N;
 }
 
-template <int JW> int do_reset(Sim* s) {
-    EnvS<JW>& st = *(EnvS<JW>*)s->state.data();
-    Ctx c; make_ctx<JW>(s, c);
+template <int JW, bool ST> int do_reset(Sim* s) {
+    EnvS<JW, ST>& st = *(EnvS<JW, ST>*)s->state.data();
+    Ctx c; make_ctx(s, c);
     run_env_op(st, c, OP_RESET);
     s->last_reward = 0.0;
     return st.status;
 }
-template <int JW> int do_step(Sim* s, int action) {
-    EnvS<JW>& st = *(EnvS<JW>*)s->state.data();
+template <int JW, bool ST> int do_step(Sim* s, int action) {
+    EnvS<JW, ST>& st = *(EnvS<JW, ST>*)s->state.data();
     s->backup = s->state; s->outs_backup = s->outs;
-    Ctx c; make_ctx<JW>(s, c);
+    Ctx c; make_ctx(s, c);
     double r = run_env_op(st, c, action);
     if (st.status >= JSL_ST_STEP_FAILED) {  // same rollback as k_step
         int status = st.status, n_steps = st.n_steps, rn = st.reward_noop, sa = st.step_action, sn = st.step_noop;
         double ret = st.ret;
         s->state = s->backup; s->outs = s->outs_backup;
-        EnvS<JW>& o = *(EnvS<JW>*)s->state.data();
+        EnvS<JW, ST>& o = *(EnvS<JW, ST>*)s->state.data();
         o.status = status;
         if (status == JSL_ST_STEP_FAILED) { o.truncated = 1; o.terminated = 0; o.obs_done = 1; o.n_steps = n_steps; o.reward_noop = rn; o.step_action = sa; o.step_noop = sn; o.ret = ret; }
     }
     s->last_reward = r;
-    return ((EnvS<JW>*)s->state.data())->status;
+    return ((EnvS<JW, ST>*)s->state.data())->status;
 }
-template <int JW> int do_digest(Sim* s, int32_t* out, int cap) {
-    EnvS<JW>& st = *(EnvS<JW>*)s->state.data();
-    Ctx c; make_ctx<JW>(s, c);
+template <int JW, bool ST> int do_digest(Sim* s, int32_t* out, int cap) {
+    EnvS<JW, ST>& st = *(EnvS<JW, ST>*)s->state.data();
+    Ctx c; make_ctx(s, c);
     return write_digest(st, c, out, cap);
 }
-template <int JW> int do_obs(Sim* s, uint8_t* out) {
-    EnvS<JW>& st = *(EnvS<JW>*)s->state.data();
-    Ctx c; make_ctx<JW>(s, c);
+template <int JW, bool ST> int do_obs(Sim* s, uint8_t* out) {
+    EnvS<JW, ST>& st = *(EnvS<JW, ST>*)s->state.data();
+    Ctx c; make_ctx(s, c);
     if (s->C.obs_kind == JSL_OBS_OPERATION_ARRAY) { write_obs_oparray(st, c, out); return c.raise ? -c.raise : obs_bytes_oparray(s->I.J, s->I.N); }
     write_obs_binary(st, c, out);
     return obs_bytes_binary(s->I.J, s->I.M);
 }
-template <int JW> int do_rollout(Sim* s, int policy, const uint8_t* tape, int n_tape, int max_steps, uint64_t env_idx) {
-    EnvS<JW>& st = *(EnvS<JW>*)s->state.data();
-    Ctx c; make_ctx<JW>(s, c);
+template <int JW, bool ST> int do_rollout(Sim* s, int policy, const uint8_t* tape, int n_tape, int max_steps, uint64_t env_idx) {
+    EnvS<JW, ST>& st = *(EnvS<JW, ST>*)s->state.data();
+    Ctx c; make_ctx(s, c);
     int n = 0;
     while (n < max_steps && st.status == JSL_ST_OK) {
         int a;
@@ -118,16 +121,17 @@ template <int JW> int do_rollout(Sim* s, int policy, const uint8_t* tape, int n_
     }
     return n;
 }
-template <int JW> void get_scalars(Sim* s, int32_t* o) {
-    EnvS<JW>& st = *(EnvS<JW>*)s->state.data();
+template <int JW, bool ST> void get_scalars(Sim* s, int32_t* o) {
+    EnvS<JW, ST>& st = *(EnvS<JW, ST>*)s->state.data();
     o[0] = st.time; o[1] = st.terminated; o[2] = st.truncated; o[3] = st.status; o[4] = st.n_steps; o[5] = st.noop_count;
     o[6] = st.n_possible - st.skip;
 }
-template <int JW> double get_ret(Sim* s) { return ((EnvS<JW>*)s->state.data())->ret; }
+template <int JW, bool ST> double get_ret(Sim* s) { return ((EnvS<JW, ST>*)s->state.data())->ret; }
 
 }  // namespace
 
-#define DISPATCH(s, F, ...) ((s)->JW == 1 ? F<1>(__VA_ARGS__) : (s)->JW == 2 ? F<2>(__VA_ARGS__) : F<4>(__VA_ARGS__))
+#define DISPATCH1(s, F, N, ...) ((s)->tobj.stochastic ? F<N, true>(__VA_ARGS__) : F<N, false>(__VA_ARGS__))
+#define DISPATCH(s, F, ...) ((s)->JW == 1 ? DISPATCH1(s, F, 1, __VA_ARGS__) : (s)->JW == 2 ? DISPATCH1(s, F, 2, __VA_ARGS__) : DISPATCH1(s, F, 4, __VA_ARGS__))
 
 extern "C" {
 
@@ -182,7 +186,7 @@ void* jsh_create(const jsl_instance_desc* d, const jsl_env_cfg* cfg, uint64_t se
     C.allow_early_transport = cfg->allow_early_transport; C.truncation_joker = cfg->truncation_joker;
     C.truncation_active = cfg->truncation_active; C.obs_kind = cfg->obs_kind; C.record_ops = cfg->record_ops;
     C.sparse_bias = cfg->sparse_bias; C.dense_bias = cfg->dense_bias; C.truncation_bias = cfg->truncation_bias;
-    s->state_bytes = s->JW == 1 ? sizeof(EnvS<1>) : s->JW == 2 ? sizeof(EnvS<2>) : sizeof(EnvS<4>);
+    s->state_bytes = s->JW == 1 ? sizeof(EnvS<1, false>) : s->JW == 2 ? sizeof(EnvS<2, false>) : sizeof(EnvS<4, false>);
     s->outs_bytes = (I.has_m_out || I.has_t_out) ? (s->JW == 1 ? sizeof(OutS<1>) : s->JW == 2 ? sizeof(OutS<2>) : sizeof(OutS<4>)) : 0;
     s->state.assign(s->state_bytes + 16, 0); s->outs.assign(s->outs_bytes + 16, 0);
     s->op_log.assign((size_t)2 * I.N + 2, -1);
