@@ -84,6 +84,7 @@ extern "C" {
 #define JSL_OBS_NONE 0
 #define JSL_OBS_BINARY_ACTION 1 /* BinaryActionObservationFactory :488-551 (default) */
 #define JSL_OBS_OPERATION_ARRAY 2 /* BinaryOperationArrayObservation :631-693 */
+#define JSL_OBS_TASSEL 3          /* TasselJsspObservation :696-918 (implies record_ops) */
 
 /*
  * Lowered instance: what jobshoplab.compiler (compiler.py:84, mapper.py:1201,1387) produces,

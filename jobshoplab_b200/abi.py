@@ -16,7 +16,7 @@ STATUS_NAMES = ("OK", "DONE", "TRUNCATED", "STEP_FAILED", "BUFFER_FULL", "UNSUCC
 POLICY_FIFO, POLICY_SPT, POLICY_MWKR, POLICY_RANDOM, POLICY_TAPE = range(5)
 POLICIES = {"fifo": POLICY_FIFO, "spt": POLICY_SPT, "mwkr": POLICY_MWKR, "random": POLICY_RANDOM,
             "tape": POLICY_TAPE}
-OBS_NONE, OBS_BINARY_ACTION, OBS_OPERATION_ARRAY = 0, 1, 2
+OBS_NONE, OBS_BINARY_ACTION, OBS_OPERATION_ARRAY, OBS_TASSEL = 0, 1, 2, 3
 
 _i32p = C.POINTER(C.c_int32)
 _f32p = C.POINTER(C.c_float)

@@ -263,12 +263,14 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
         b->allocs.push_back(p); b->bd.tseed = (uint16_t*)p;
         cudaMemset(p, 0, (size_t)B * t->tobj.n * sizeof(uint16_t));
     }
-    if (cfg->record_ops) {
+    if (cfg->record_ops || cfg->obs_kind == JSL_OBS_TASSEL) {
+        C.record_ops = 1;
         if (cudaMalloc(&p, (size_t)B * N * 2 * sizeof(int32_t)) != cudaSuccess) { set_err("cudaMalloc(op_log) failed"); jsl_batch_destroy(b); return nullptr; }
         b->allocs.push_back(p); b->bd.op_log = (int32_t*)p;
     }
     b->obs_bytes = cfg->obs_kind == JSL_OBS_BINARY_ACTION ? obs_bytes_binary(t->J, t->M)
-                   : cfg->obs_kind == JSL_OBS_OPERATION_ARRAY ? obs_bytes_oparray(t->J, t->N) : 0;
+                   : cfg->obs_kind == JSL_OBS_OPERATION_ARRAY ? obs_bytes_oparray(t->J, t->N)
+                   : cfg->obs_kind == JSL_OBS_TASSEL ? obs_bytes_tassel(t->J) : 0;
     b->digest_cap = 64 + 3 * t->J + 3 * N + t->M * 6 + 2 * t->J + 11 * t->T + t->S +
                     3 * ((int)t->m_outage_freq.size() + t->T * I.n_t_out) + 4 * (t->J + t->T * t->J);
     if (cudaMalloc(&p, (size_t)(b->digest_cap + 4) * sizeof(int32_t)) != cudaSuccess) { set_err("cudaMalloc(digest) failed"); jsl_batch_destroy(b); return nullptr; }

@@ -1371,6 +1371,7 @@ JSL_D int policy_action(const EnvS<JW, ST>& s, const Ctx& c, int policy, uint64_
 #endif
 JSL_HD int obs_bytes_binary(int J, int M) { return (16 + 4 * J + 4 * M + 2 * J + M + J * M + 15) & ~15; }
 JSL_HD int obs_bytes_oparray(int J, int N) { return (16 + 4 * N + 4 * J + 15) & ~15; }
+JSL_HD int obs_bytes_tassel(int J) { return (7 * 4 * J + 15) & ~15; }
 
 template <int JW, bool ST>
 JSL_D void cand_floats(const EnvS<JW, ST>& s, const Ctx& c, float* tr) {
@@ -1457,6 +1458,52 @@ JSL_D void write_obs_oparray(const EnvS<JW, ST>& s, Ctx& c, uint8_t* out) {
     });
     JSL_SYNCWARP();
     if (bad.any() && !c.raise) c.raise = JSL_ST_OTHER_INVALID;  // ZeroDivisionError
+}
+
+// TasselJsspObservation.make (observations.py:738-918): f32 [7][J] = allocatable | left_over_time |
+// percent_finished | total_completion | time_until_next_machine_is_free | idle_since_last_op | cum_idle_time.
+// Needs the per-op (start, end) log (cfg.record_ops is forced on for this observation kind).
+template <int JW, bool ST>
+JSL_D void write_obs_tassel(const EnvS<JW, ST>& s, const Ctx& c, uint8_t* out) {
+    const InstDev& I = *c.I;
+    const int J = I.J;
+    float* f = (float*)out;
+    const double mat = (double)c.aux->max_allowed_time;
+    const int32_t* log = c.aux->op_log;
+    const int now = s.time;
+    const int total_bytes = obs_bytes_tassel(J);
+    wp_for_dyn(1, [&](int) { for (int i = 7 * 4 * J; i < total_bytes; i++) out[i] = 0; });
+    wp_for<JW>(J, [&](int j) {
+        const int o0 = I.job_op_start[j], n = job_nops(I, j), k = s.j_k[j];
+        const bool proc = s.j_proc[j] != 0;
+        const int kidle = k + (proc ? 1 : 0);  // index of the first IDLE op
+        f[0 * J + j] = (kidle < n && !proc) ? 1.f : 0.f;
+        const int left = proc ? s.j_end[j] - now : 0;
+        f[1 * J + j] = (float)left;
+        f[2 * J + j] = (float)(n > 0 ? (double)k / (double)n : 0.0);
+        long long remaining = left;
+        for (int i = kidle; i < n; i++) remaining += op_duration<ST>(c, o0 + i);
+        f[3 * J + j] = (float)((double)remaining / mat);
+        int wait = 0;
+        if (kidle < n) {
+            int m = c.op_mt[o0 + kidle] & 0xffff;
+            if (s.m_state[m] == JSL_M_WORKING) wait = s.m_occ[m] - now;
+        }
+        f[4 * J + j] = (float)wait;
+        const int last_end = k > 0 ? log[2 * (o0 + k - 1) + 1] : 0;
+        f[5 * J + j] = (k > 0 && !proc) ? (float)((double)(now - last_end) / mat) : 0.f;
+        long long total = 0;
+        if (n > 0) {
+            if (k > 0) total += log[2 * o0];                 // first op done: its logged start
+            else if (proc) total += s.j_start[j];            // first op processing
+        }
+        for (int i = 0; i + 1 < n && i < k; i++) {           // op i DONE and op i+1 not IDLE
+            if (i + 1 < k) total += log[2 * (o0 + i + 1)] - log[2 * (o0 + i) + 1];
+            else if (proc) total += s.j_start[j] - log[2 * (o0 + i) + 1];
+        }
+        if (n > 0 && k == n && !proc) total += now - log[2 * (o0 + n - 1) + 1];
+        f[6 * J + j] = (float)((double)total / mat);
+    });
 }
 
 // ------------------------------------------------------------------------------------ canonical digest

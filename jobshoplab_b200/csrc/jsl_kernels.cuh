@@ -85,6 +85,7 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW, ST>& s, Ctx& c, co
         uint8_t* o = out.obs + env * (int64_t)obs_bytes;
         if (c.C->obs_kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o);
         else if (c.C->obs_kind == JSL_OBS_OPERATION_ARRAY) write_obs_oparray(s, c, o);
+        else if (c.C->obs_kind == JSL_OBS_TASSEL) write_obs_tassel(s, c, o);
     }
     int status = s.status;
     if (c.raise && status <= JSL_ST_STEP_FAILED) status = c.raise;  // observation factory raised

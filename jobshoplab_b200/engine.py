@@ -269,6 +269,11 @@ class Batch:
         torch = self.torch
         obs = self.out.obs if obs is None else obs
         J, M, N = self.shape.n_jobs, self.shape.n_machines, self.shape.n_ops
+        if self.cfg.obs_kind == abi.OBS_TASSEL:
+            f = obs[:, : 28 * J].view(torch.float32).view(-1, 7, J)
+            keys = ("allocatable", "left_over_time", "percent_finished", "total_completion",
+                    "time_until_next_machine_is_free", "idle_since_last_op", "cum_idle_time")
+            return {k: f[:, i] for i, k in enumerate(keys)}
         if self.cfg.obs_kind == abi.OBS_OPERATION_ARRAY:
             f = obs[:, : 16 + 4 * N + 4 * J].view(torch.float32)
             return {"operation_state": f[:, 4: 4 + N].unsqueeze(1), "job_locations": f[:, 4 + N: 4 + N + J].unsqueeze(1),

@@ -24,7 +24,8 @@ from .lowered import LoweredInstance
 from .state_view import parse_digest
 
 _OBS_KINDS = {"BinaryActionObservationFactory": abi.OBS_BINARY_ACTION,
-              "BinaryOperationArrayObservation": abi.OBS_OPERATION_ARRAY}
+              "BinaryOperationArrayObservation": abi.OBS_OPERATION_ARRAY,
+              "TasselJsspObservation": abi.OBS_TASSEL}
 
 
 class Discrete:

@@ -94,8 +94,9 @@ def run_scenario(sc: dict) -> dict:
         env = rh.make_env("dslstr", text, **cfg)
     ix = rh.Indexer(env.instance)
     li = env.jsl_rc.lowered
-    oparray = cfg.get("observation_factory") == "BinaryOperationArrayObservation"
-    obs_fn = rh.obs_oparray_bytes if oparray else rh.obs_bytes
+    of = cfg.get("observation_factory")
+    obs_fn = {"BinaryOperationArrayObservation": rh.obs_oparray_bytes,
+              "TasselJsspObservation": rh.obs_tassel_bytes}.get(of, rh.obs_bytes)
     policy = sc["policy"]
     state_hash = [hash_i32(rh.digest(ix, env.state))]
     obs_hash = [hash_bytes(obs_fn(env.current_observation[0]))]
@@ -292,7 +293,23 @@ def g_oparray():
     return out
 
 
-GROUPS = {"classic": g_classic, "solutions": g_solutions, "transport": g_transport, "buffers": g_buffers,
+def g_tassel():
+    out = []
+    cfg = dict(observation_factory="TasselJsspObservation")
+    for name in ["ft06", "la16", "ta01"]:
+        for pol, seed in [("fifo", 0), ("spt", 0), ("random", 0), ("random", 1)]:
+            out.append(dict(name=f"{name}/tassel/{pol}{seed}", kind="spec", src=spec(name), policy=pol, seed=seed, cfg=cfg))
+    for name in ["ft10", "la01"]:
+        src = str(DATA / "transport" / f"{name}.yaml")
+        for pol, seed in [("fifo", 0), ("random", 0)]:
+            out.append(dict(name=f"{name}-t/tassel/{pol}{seed}", kind="dsl", src=src, policy=pol, seed=seed, cfg=cfg))
+    p = TDATA / "full_feature_3x3_instance.yaml"
+    for seed in range(3):
+        out.append(dict(name=f"{p.stem}/tassel/random{seed}", kind="dsl", src=str(p), policy="random", seed=seed, cfg=cfg))
+    return out
+
+
+GROUPS = {"tassel": g_tassel, "classic": g_classic, "solutions": g_solutions, "transport": g_transport, "buffers": g_buffers,
           "features": g_features, "truncation": g_truncation, "oparray": g_oparray}
 
 

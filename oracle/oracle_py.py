@@ -44,7 +44,7 @@ def lib():
         L.jslo_set_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         for name in ("jslo_reset", "jslo_time", "jslo_terminated", "jslo_truncated", "jslo_status",
                      "jslo_n_steps", "jslo_noop_count", "jslo_n_possible", "jslo_obs_bytes",
-                     "jslo_obs_oparray_bytes", "jslo_tape_pos"):
+                     "jslo_obs_oparray_bytes", "jslo_obs_tassel_bytes", "jslo_tape_pos"):
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = C.c_int
         L.jslo_step.argtypes = [C.c_void_p, C.c_int]
@@ -56,6 +56,7 @@ def lib():
         L.jslo_digest.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.jslo_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.jslo_obs_oparray.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.jslo_obs_tassel.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.jslo_random_action.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
         L.jslo_policy_action.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
         L.jslo_rollout.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
@@ -146,6 +147,12 @@ class OracleEnv:
         r = self.L.jslo_obs_oparray(self.h, out.ctypes.data, n)
         if r < 0:
             raise RuntimeError(f"oracle obs raised status {-r}")
+        return out.tobytes()
+
+    def obs_tassel(self) -> bytes:
+        n = self.L.jslo_obs_tassel_bytes(self.h)
+        out = np.zeros(n, dtype=np.uint8)
+        self.L.jslo_obs_tassel(self.h, out.ctypes.data, n)
         return out.tobytes()
 
     def policy_action(self, policy: int, seed: int = 0, env_idx: int = 0) -> int:

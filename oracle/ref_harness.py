@@ -304,6 +304,14 @@ def obs_oparray_bytes(obs: dict) -> bytes:
     return raw + b"\0" * (-len(raw) % 16)
 
 
+def obs_tassel_bytes(obs: dict) -> bytes:
+    """Packed TasselJsspObservation: f32 [7][J] in the reference's key order, padded to 16 bytes."""
+    keys = ("allocatable", "left_over_time", "percent_finished", "total_completion",
+            "time_until_next_machine_is_free", "idle_since_last_op", "cum_idle_time")
+    raw = b"".join(np.asarray(obs[k], dtype=np.float64).astype(np.float32).tobytes() for k in keys)
+    return raw + b"\0" * (-len(raw) % 16)
+
+
 # ---------------------------------------------------------------- policies
 def philox4x32_10(counter, key):
     """Philox4x32-10 (Salmon et al. 2011). counter: 4 u32, key: 2 u32 -> 4 u32."""

@@ -10,7 +10,7 @@ import numpy as np
 from jobshoplab_b200 import lowered as L
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-GROUPS = ("classic", "solutions", "transport", "buffers", "features", "truncation", "oparray")
+GROUPS = ("classic", "solutions", "transport", "buffers", "features", "truncation", "oparray", "tassel")
 
 _P = np.uint64(1099511628211)
 _H0 = np.uint64(1469598103934665603)
@@ -81,8 +81,11 @@ class Scenario:
     @property
     def cfg(self) -> dict:
         c = dict(self.meta.get("cfg", {}))
-        if c.pop("observation_factory", None) == "BinaryOperationArrayObservation":
+        of = c.pop("observation_factory", None)
+        if of == "BinaryOperationArrayObservation":
             c["obs_kind"] = 2
+        elif of == "TasselJsspObservation":
+            c["obs_kind"] = 3
         return c
 
     @property

@@ -105,6 +105,7 @@ template <int JW, bool ST> int do_obs(Sim* s, uint8_t* out) {
     EnvS<JW, ST>& st = *(EnvS<JW, ST>*)s->state.data();
     Ctx c; make_ctx(s, c);
     if (s->C.obs_kind == JSL_OBS_OPERATION_ARRAY) { write_obs_oparray(st, c, out); return c.raise ? -c.raise : obs_bytes_oparray(s->I.J, s->I.N); }
+    if (s->C.obs_kind == JSL_OBS_TASSEL) { write_obs_tassel(st, c, out); return obs_bytes_tassel(s->I.J); }
     write_obs_binary(st, c, out);
     return obs_bytes_binary(s->I.J, s->I.M);
 }

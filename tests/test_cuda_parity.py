@@ -77,7 +77,7 @@ SHORT = {"classic": ["2x2/fifo", "3x3/random0", "ft06/fifo", "ft06/spt", "ft06/r
          "solutions": ["3x3/solution", "ft06/solution", "ft10/solution", "la01/solution", "ta01/solution"]}
 
 
-@pytest.mark.parametrize("group", ["classic", "solutions", "transport", "buffers", "features", "truncation", "oparray"])
+@pytest.mark.parametrize("group", ["classic", "solutions", "transport", "buffers", "features", "truncation", "oparray", "tassel"])
 def test_step_mode_matches_reference_traces(group):
     if group in SHORT:
         names = SHORT[group]

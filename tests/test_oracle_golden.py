@@ -27,7 +27,7 @@ def replay(sc: G.Scenario):
     if len(sc.samples):
         env.set_tape(sc.samples)
         env.reset()
-    obs = env.obs_oparray if sc.cfg.get("obs_kind") == 2 else env.obs
+    obs = {2: env.obs_oparray, 3: env.obs_tassel}.get(sc.cfg.get("obs_kind"), env.obs)
     assert G.hash_i32(env.digest()) == int(sc.state_hash[0]), "reset state"
     assert G.hash_bytes(obs()) == int(sc.obs_hash[0]), "reset obs"
     n = sc.meta["n_steps"]
