@@ -64,3 +64,11 @@ def test_engine_policies():
         else:
             e.rollout(abi.POLICIES[pol])
         assert e.n_steps == sc.meta["n_steps"] and e.time == sc.meta["makespan"], name
+
+
+def test_engine_source_differential_fuzz():
+    """Random small instances (buffers, capacities, travel, setup, outages, truncation): engine source vs
+    oracle, step by step -- tests/fuzz_engine.py."""
+    import fuzz_engine
+
+    fuzz_engine.main(250, 3)
