@@ -52,6 +52,10 @@ static inline unsigned jsl_fns_host(unsigned x, int n) {
 
 namespace jsl {
 
+#ifdef JSL_HOST_SIM
+static long g_invariant_checks = 0, g_invariant_violations = 0;  // CPU debug build only
+#endif
+
 constexpr int NONE8 = 0xff;
 constexpr int OCC_NOTIME = 0, OCC_TIME = 1, OCC_TD = 2;
 constexpr int INT_BIG = 0x7fffffff;
@@ -978,7 +982,7 @@ JSL_D int force_jump_to_event(const EnvS<JW, ST>& s, Ctx& c) {
 // handler.py:55-153, :329-379: evaluate on the current snapshot into the x_* scratch arrays.
 // returns true when at least one transition was created.
 template <int JW, bool ST>
-JSL_D bool create_timed(EnvS<JW, ST>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm) {
+JSL_D bool create_timed(EnvS<JW, ST>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, bool& time_due) {
     const InstDev& I = *c.I;
     const int now = c.now;
     // machines: occupied_till reached -> next state
@@ -988,6 +992,7 @@ JSL_D bool create_timed(EnvS<JW, ST>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm) {
         if (due) { s.x_mkind[m] = (uint8_t)((st + 1) & 3); s.x_mjob[m] = s.m_job[m]; }
         return due;
     });
+    time_due = mm.any();
     JSL_SYNCWARP();
     if (!I.flex_pre) {  // handler.py:117-153: automatic start from FIFO/LIFO/DUMMY prebuffers
         Mask<1> cand = wp_ballot<1>(I.M, [&](int m) {
@@ -1023,6 +1028,7 @@ JSL_D bool create_timed(EnvS<JW, ST>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm) {
         s.x_tkind[t] = (uint8_t)kind; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = (uint8_t)job;
         return true;
     });
+    time_due = time_due || tm.any();
     JSL_SYNCWARP();
     if (!flex_post) {
         need_ready = wp_ballot<JW>(I.T, [&](int t) { return tm.test(t) && s.t_state[t] == JSL_T_WAITINGPICKUP && s.t_job[t] != NONE8; });
@@ -1074,6 +1080,7 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
     for (int w = 0; w < JW; w++) { tm.w[w] = 0; tele.w[w] = 0; p.p1.w[w] = 0; p.idle.w[w] = 0; p.lr.w[w] = 0; p.li.w[w] = 0; }
     bool action_stage = has_action;
     bool first = true;
+    bool evaluated = false;  // the time machine already ran for the current state
     int guard = 0;
 #pragma unroll 1
     for (;;) {
@@ -1087,13 +1094,38 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
                 tm.w[act.comp >> 5] = 1u << (act.comp & 31);
             }
         } else {
-            p = compute_poss(s, c);
-            // time machine: jump_to_event keeps `now` while something is possible (time_machines.py:61-130)
-            const bool anyp = p.p1.any() || (p.idle.any() && (p.lr.any() || p.li.any()));
-            if ((first && time_machine == TM_FORCE) || !anyp) c.now = force_jump_to_event(s, c);
+            bool time_due = false;
+            const bool have = create_timed(s, c, mm, tm, time_due);
             if (c.raise) return true;
-            const bool have = create_timed(s, c, mm, tm);
-            if (c.raise) return true;
+            // Time machine (time_machines.py:61-130): `now` stays while something is possible, else it jumps to
+            // min(processing-op ends, busy-AGV times).  When an occupied_till-driven transition is due at `now`
+            // that minimum IS `now` (nothing pending can lie in the past: every due component fires in the very
+            // next batch), so the candidate scan is only needed in quiet batches and in the first one.
+            if (!evaluated && (first || !time_due)) {
+                p = compute_poss(s, c);
+                const bool anyp = p.p1.any() || (p.idle.any() && (p.lr.any() || p.li.any()));
+                if ((first && time_machine == TM_FORCE) || !anyp) {
+                    const int t2 = force_jump_to_event(s, c);
+                    if (c.raise) return true;
+                    if (t2 != c.now) {  // re-evaluate the timed transitions at the new time
+                        c.now = t2;
+                        evaluated = true;
+                        if (++guard > 100000) { c.raise = JSL_ST_OTHER_INVALID; return true; }
+                        continue;
+                    }
+                }
+            }
+#ifdef JSL_HOST_SIM
+            if (!evaluated && !(first || !time_due)) {  // the skipped evaluation must have been a no-op
+                Poss<JW> q = compute_poss(s, c);
+                const bool anyq = q.p1.any() || (q.idle.any() && (q.lr.any() || q.li.any()));
+                int save = c.raise;
+                g_invariant_checks++;
+                if (!anyq && force_jump_to_event(s, c) != c.now) g_invariant_violations++;
+                c.raise = save;
+            }
+#endif
+            evaluated = false;
             if (first && p.idle.any() && (p.lr.any() || p.li.any())) {
                 // teleports (state.py:229-232, :414-467): i-th idle AGV <- i-th lonely job with zero travel time
                 auto zero_travel = [&](int j, bool& bad) {

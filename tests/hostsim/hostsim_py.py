@@ -54,6 +54,14 @@ def lib():
     return _lib
 
 
+def invariants():
+    """(checks, violations) of the event-loop shortcut 'an occupied_till-driven transition is due at now =>
+    the time machine would not move' (jsl_engine.cuh sm_step), accumulated by the CPU debug build."""
+    o = (C.c_long * 2)()
+    lib().jsh_invariants(o)
+    return int(o[0]), int(o[1])
+
+
 class HostSimEnv:
     def __init__(self, lowered, seed=0, **cfg):
         self.L = lib()

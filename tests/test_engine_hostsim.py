@@ -72,3 +72,6 @@ def test_engine_source_differential_fuzz():
     import fuzz_engine
 
     fuzz_engine.main(250, 3)
+    from hostsim.hostsim_py import invariants
+    checks, violations = invariants()
+    assert checks > 1000 and violations == 0
