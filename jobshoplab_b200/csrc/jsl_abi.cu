@@ -275,6 +275,8 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
                     3 * ((int)t->m_outage_freq.size() + t->T * I.n_t_out) + 4 * (t->J + t->T * t->J);
     if (cudaMalloc(&p, (size_t)(b->digest_cap + 4) * sizeof(int32_t)) != cudaSuccess) { set_err("cudaMalloc(digest) failed"); jsl_batch_destroy(b); return nullptr; }
     b->allocs.push_back(p); b->d_digest = (int32_t*)p; b->d_digest_n = b->d_digest + b->digest_cap;
+    if (cudaMalloc(&p, sizeof(unsigned long long)) != cudaSuccess) { set_err("cudaMalloc(counter) failed"); jsl_batch_destroy(b); return nullptr; }
+    b->allocs.push_back(p); b->bd.work_counter = (unsigned long long*)p;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) b->sm_count = prop.multiProcessorCount;
     return b;
@@ -461,6 +463,7 @@ int jsl_rollout(jsl_batch_t* b, int policy, const uint8_t* action_tape, int64_t 
     int64_t need = (b->bd.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     int64_t persistent = (int64_t)b->sm_count * b->rollout_ctas_per_sm;  // one full wave of resident CTAs
     LaunchCfg lc = {(int)(need < persistent ? need : persistent), smem, (cudaStream_t)stream};
+    CK(cudaMemsetAsync(b->bd.work_counter, 0, sizeof(unsigned long long), (cudaStream_t)stream));
     JSL_DISPATCH(b, rollout, lc, policy, action_tape, tape_stride, max_steps, flags, out);
     return JSL_OK;
 }

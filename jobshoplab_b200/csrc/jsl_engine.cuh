@@ -197,6 +197,7 @@ struct Ctx {
     int now;
 };
 
+#define JSL_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #define JSL_RAISE(c, code)          \
     do {                            \
         if (!(c).raise) (c).raise = (code); \
@@ -406,7 +407,7 @@ JSL_D bool ready_for_pickup_lane(const EnvS<JW, ST>& s, const InstDev& I, int j)
 template <int JW, bool ST>
 JSL_D void put_in_buffer(EnvS<JW, ST>& s, Ctx& c, int b, int j) {
     const InstDev& I = *c.I;
-    if (!I.caps_inf) {
+    if (JSL_UNLIKELY(!I.caps_inf)) {
         int cap = buf_cap(I, b);
         if (cap != JSL_CAP_INF && buf_count(s, I, b) >= cap) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
     }
@@ -708,7 +709,7 @@ JSL_D bool machine_valid(const EnvS<JW, ST>& s, Ctx& c, int m, int to, int job) 
               : from == JSL_M_SETUP ? to == JSL_M_WORKING
               : from == JSL_M_WORKING ? (to == JSL_M_OUTAGE)
                                       : to == JSL_M_IDLE;
-    if (!ok) return false;
+    if (JSL_UNLIKELY(!ok)) return false;
     if (from == JSL_M_OUTAGE || from == JSL_M_WORKING) return true;
     if (job != NONE8) {
         if (s.j_mach[job] == NONE8) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, false);
@@ -726,12 +727,12 @@ JSL_D void machine_idle_to_setup(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
     int o = I.job_op_start[j] + s.j_k[j];
     int tool = (c.op_mt[o] >> 16) & 0xffff;
     int setup = 0;
-    if (I.setup || ST) {
+    if (JSL_UNLIKELY(I.setup || ST)) {
         const int si = (m * I.NT + s.m_tool[m]) * I.NT + tool;
         setup = setup_time_cur<ST>(c, si);
         if (setup == JSL_NO_TIME && !(ST && I.tobj_kind[I.off_setup + si] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
         setup = tobj_update<ST>(c, s.draw_ctr, I.off_setup + si, setup);
-        if (c.raise) return;
+        if (JSL_UNLIKELY(c.raise)) return;
     }
     if (s.m_job[m] != NONE8) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
     s.j_proc[j] = 1; s.j_start[j] = c.now; s.j_end[j] = c.now + setup;
@@ -746,7 +747,7 @@ JSL_D void machine_setup_to_working(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
     if (j == NONE8 || s.j_loc[j] != 3 * m + 2) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     const int o = I.job_op_start[j] + s.j_k[j];
     int dur = tobj_update<ST>(c, s.draw_ctr, o, c.op_dur[o]);
-    if (c.raise) return;
+    if (JSL_UNLIKELY(c.raise)) return;
     s.j_proc[j] = 1; s.j_start[j] = c.now; s.j_end[j] = c.now + dur;
     s.m_state[m] = JSL_M_WORKING; s.m_occ[m] = c.now + dur;
 }
@@ -755,12 +756,12 @@ template <int JW, bool ST>
 JSL_D void machine_working_to_outage(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     int occupied_for = 0;
-    if (I.has_m_out) {
+    if (JSL_UNLIKELY(I.has_m_out)) {
         int b = I.m_out_start[m], n = I.m_out_start[m + 1] - b;
         OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
         occupied_for = sample_outages<ST>(c, s.draw_ctr, c.now, n, I.m_out_freq + b, I.m_out_dur + b, I.off_mof + b,
                                       I.off_mod + b, o.mo_active + m * MAX_OUT, o.mo_a + m * MAX_OUT, o.mo_b + m * MAX_OUT);
-        if (c.raise) return;
+        if (JSL_UNLIKELY(c.raise)) return;
     }
     s.m_state[m] = JSL_M_OUTAGE; s.m_occ[m] = c.now + occupied_for;
     if (j == NONE8 || !s.j_proc[j]) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -785,8 +786,8 @@ JSL_D void machine_outage_to_idle(EnvS<JW, ST>& s, Ctx& c, int m) {
     s.m_done[m] = (uint16_t)(s.m_done[m] + 1);
     s.m_job[m] = NONE8;
     put_in_buffer(s, c, 3 * m + 1, j);
-    if (c.raise) return;
-    if (I.has_m_out) {
+    if (JSL_UNLIKELY(c.raise)) return;
+    if (JSL_UNLIKELY(I.has_m_out)) {
         OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
         release_outages(I.m_out_start[m + 1] - I.m_out_start[m], o.mo_active + m * MAX_OUT, o.mo_a + m * MAX_OUT,
                         o.mo_b + m * MAX_OUT);
@@ -798,7 +799,7 @@ JSL_D void machine_outage_to_idle(EnvS<JW, ST>& s, Ctx& c, int m) {
 template <int JW, bool ST>
 JSL_D bool apply_machine(EnvS<JW, ST>& s, Ctx& c, int m, int to, int job) {
     if (!machine_valid(s, c, m, to, job)) return false;
-    if (c.raise) return true;
+    if (JSL_UNLIKELY(c.raise)) return true;
     int from = s.m_state[m];
     if (from == JSL_M_IDLE) machine_idle_to_setup(s, c, m, job);
     else if (from == JSL_M_SETUP) machine_setup_to_working(s, c, m, job);
@@ -835,7 +836,7 @@ JSL_D void agv_idle_to_working(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
     if (s.t_lockind[t] != 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     int target = next_idle_place(s, c, j);
     if (target < 0) target = output_place(c);
-    if (c.raise) return;
+    if (JSL_UNLIKELY(c.raise)) return;
     int loc = s.j_loc[j];
     int src = place_of_buf(I, loc);
     if (src < 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TransportConfigError
@@ -894,13 +895,13 @@ JSL_D void agv_to_transit(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
     int nip = next_idle_place(s, c, j);
     if (nip < 0) dst = output_place(c);
     else dst = s.j_mach[j];  // get_next_not_done_operation(job).machine_id
-    if (c.raise) return;
+    if (JSL_UNLIKELY(c.raise)) return;
     if (!(src < I.M || dst < I.M)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     int travel = travel_time_cur<ST>(c, src, dst);
     const int tobj = I.off_travel + src * I.NP + dst;
     if (travel == JSL_NO_TIME && !(ST && I.tobj_kind[tobj] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TravelTimeError
     travel = tobj_update<ST>(c, s.draw_ctr, tobj, travel);  // resampled (time_utils.py:15)
-    if (c.raise) return;
+    if (JSL_UNLIKELY(c.raise)) return;
     if (s.t_carry[t] != NONE8) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
     if (loc % 3 == 2 && loc < 3 * I.M) s.m_job[loc / 3] = NONE8;  // lifted out of a machine buffer
     s.j_loc[j] = (uint16_t)(3 * I.M + t);
@@ -920,13 +921,13 @@ JSL_D void agv_transit_to_outage(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
     int to_buf = dest < I.M ? 3 * dest : 3 * I.M + I.T + (dest - I.M);
     s.t_carry[t] = NONE8;
     put_in_buffer(s, c, to_buf, j);
-    if (c.raise) return;
+    if (JSL_UNLIKELY(c.raise)) return;
     int occupied_for = 0;
-    if (I.has_t_out) {
+    if (JSL_UNLIKELY(I.has_t_out)) {
         OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
         occupied_for = sample_outages<ST>(c, s.draw_ctr, c.now, I.n_t_out, I.t_out_freq, I.t_out_dur, I.off_tof, I.off_tod,
                                       o.to_active + t * MAX_OUT, o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
-        if (c.raise) return;
+        if (JSL_UNLIKELY(c.raise)) return;
     }
     s.t_state[t] = JSL_T_OUTAGE;
     s.t_occkind[t] = OCC_TIME; s.t_occ[t] = c.now + occupied_for;
@@ -994,7 +995,7 @@ JSL_D bool create_timed(EnvS<JW, ST>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, bool
     });
     time_due = mm.any();
     JSL_SYNCWARP();
-    if (!I.flex_pre) {  // handler.py:117-153: automatic start from FIFO/LIFO/DUMMY prebuffers
+    if (JSL_UNLIKELY(!I.flex_pre)) {  // handler.py:117-153: automatic start from FIFO/LIFO/DUMMY prebuffers
         Mask<1> cand = wp_ballot<1>(I.M, [&](int m) {
             return !mm.test(m) && s.m_state[m] == JSL_M_IDLE && I.pre_type[m] != JSL_BUF_FLEX;
         });
@@ -1030,14 +1031,14 @@ JSL_D bool create_timed(EnvS<JW, ST>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, bool
     });
     time_due = time_due || tm.any();
     JSL_SYNCWARP();
-    if (!flex_post) {
+    if (JSL_UNLIKELY(!flex_post)) {
         need_ready = wp_ballot<JW>(I.T, [&](int t) { return tm.test(t) && s.t_state[t] == JSL_T_WAITINGPICKUP && s.t_job[t] != NONE8; });
         while (need_ready.any()) {  // handler.py:191-252: WAITINGPICKUP & ready -> TRANSIT
             int t = need_ready.pop_first();
             if (ready_for_pickup(s, I, s.t_job[t])) s.x_tkind[t] = JSL_T_TRANSIT;
         }
     }
-    if (!I.flex_post) {  // handler.py:278-326,356-359 resolved TimeDependency -> stored transition
+    if (JSL_UNLIKELY(!I.flex_post)) {  // handler.py:278-326,356-359 resolved TimeDependency -> stored transition
         td = wp_ballot<JW>(I.T, [&](int t) { return s.t_occkind[t] == OCC_TD; });
         while (td.any()) {
             int t = td.pop_first();
@@ -1096,7 +1097,7 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
         } else {
             bool time_due = false;
             const bool have = create_timed(s, c, mm, tm, time_due);
-            if (c.raise) return true;
+            if (JSL_UNLIKELY(c.raise)) return true;
             // Time machine (time_machines.py:61-130): `now` stays while something is possible, else it jumps to
             // min(processing-op ends, busy-AGV times).  When an occupied_till-driven transition is due at `now`
             // that minimum IS `now` (nothing pending can lie in the past: every due component fires in the very
@@ -1106,7 +1107,7 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
                 const bool anyp = p.p1.any() || (p.idle.any() && (p.lr.any() || p.li.any()));
                 if ((first && time_machine == TM_FORCE) || !anyp) {
                     const int t2 = force_jump_to_event(s, c);
-                    if (c.raise) return true;
+                    if (JSL_UNLIKELY(c.raise)) return true;
                     if (t2 != c.now) {  // re-evaluate the timed transitions at the new time
                         c.now = t2;
                         evaluated = true;
@@ -1163,8 +1164,8 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
         while (mm.any()) {
             int m = mm.pop_first();
             bool ok = apply_machine(s, c, m, s.x_mkind[m], s.x_mjob[m]);
-            if (c.raise) return true;
-            if (!ok) return false;
+            if (JSL_UNLIKELY(c.raise)) return true;
+            if (JSL_UNLIKELY(!ok)) return false;
         }
 #pragma unroll 1
         for (int ph = 0; ph < 2; ph++) {
@@ -1172,8 +1173,8 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
             while (cur.any()) {
                 int t = cur.pop_first();
                 bool ok = apply_transport(s, c, s.x_tcomp[t], s.x_tkind[t], s.x_tjob[t]);
-                if (c.raise) return true;
-                if (!ok) return false;
+                if (JSL_UNLIKELY(c.raise)) return true;
+                if (JSL_UNLIKELY(!ok)) return false;
             }
         }
 #pragma unroll

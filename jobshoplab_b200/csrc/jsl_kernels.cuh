@@ -15,9 +15,12 @@
 
 namespace jsl {
 
-constexpr int WARPS_PER_CTA = 4;
+#ifndef JSL_WARPS_PER_CTA
+#define JSL_WARPS_PER_CTA 4
+#endif
+constexpr int WARPS_PER_CTA = JSL_WARPS_PER_CTA;
 #ifndef JSL_ROLLOUT_MIN_CTAS
-#define JSL_ROLLOUT_MIN_CTAS 12  // resident CTAs per SM the rollout kernel is register-budgeted for
+#define JSL_ROLLOUT_MIN_CTAS 16  // resident CTAs per SM the rollout kernel is register-budgeted for
 #endif
 #ifndef JSL_STEP_MIN_CTAS
 #define JSL_STEP_MIN_CTAS 10
@@ -36,6 +39,7 @@ struct BatchDev {
     int32_t* tcur;       // [B][n_tobj] current .time of every time object (stochastic instances) or nullptr
     const int32_t* tape; // [B][tape_stride] replayed update() results or nullptr
     int64_t tape_stride;
+    unsigned long long* work_counter;  // next env index of the persistent rollout grid (dynamic work queue)
     uint16_t* tseed;     // [B][n_tobj] numpy seed of every stochastic time object
     const int32_t* start_seeds;  // [B][n_tobj] or nullptr
 };
@@ -183,8 +187,13 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
     uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
     EnvS<JW, ST>& s = *(EnvS<JW, ST>*)slot;
     void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
-    const int64_t stride = (int64_t)gridDim.x * WARPS_PER_CTA;
-    for (int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; env < bd.B; env += stride) {
+    // persistent warps pull env indices from a global counter: episodes differ in length, a static
+    // grid-stride split leaves the tail of the launch half empty
+    for (;;) {
+        unsigned long long next = 0;
+        if (JSL_LANE == 0) next = atomicAdd(bd.work_counter, 1ull);
+        const int64_t env = (int64_t)__shfl_sync(0xffffffffu, next, 0);
+        if (env >= bd.B) break;
         uint8_t* g_state = bd.state + env * (int64_t)bd.state_stride;
         uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
         Ctx c;
