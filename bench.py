@@ -335,7 +335,7 @@ def main():
         }
         if not args.no_cpu:
             threads = os.cpu_count() or 1
-            n = max(threads * 4, 32)
+            n = max(threads * 128, 256)
             r, dt = cpu_run(n, threads, first=0)
             gpu_mk = batch.rout.makespan[:n].cpu().numpy() if first == 0 else None
             out["cpu_baseline"] = {

@@ -119,7 +119,7 @@ template <int JW, bool ST>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int warp = threadIdx.x >> 5;
+    const int warp = WARPS_PER_CTA == 1 ? 0 : (int)(threadIdx.x >> 5);
     const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
     if (env >= bd.B) return;
     if (mask && !mask[env]) return;
@@ -140,7 +140,7 @@ template <int JW, bool ST>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_STEP_MIN_CTAS)
 k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int warp = threadIdx.x >> 5;
+    const int warp = WARPS_PER_CTA == 1 ? 0 : (int)(threadIdx.x >> 5);
     const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
     if (env >= bd.B) return;
     uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_ROLLOUT_MIN_CTAS)
 k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __restrict__ tape, int64_t tape_stride,
           int max_steps, int flags, jsl_rollout_out out) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int warp = threadIdx.x >> 5;
+    const int warp = WARPS_PER_CTA == 1 ? 0 : (int)(threadIdx.x >> 5);
     uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
     EnvS<JW, ST>& s = *(EnvS<JW, ST>*)slot;
     void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
