@@ -173,6 +173,9 @@ struct alignas(16) OutS {
 
 // Rarely used per-env constants: kept in the env's shared-memory slot, not in registers.
 struct alignas(16) EnvAux {
+    const int32_t* op_mt;        // this env's variant of the op tables
+    const int32_t* op_dur;
+    const int32_t* job_work;     // [J] sum of each job's durations ("mwkr" key)
     int32_t* op_log;             // [N][2] or nullptr
     void* outs;                  // OutS<JW>* or nullptr
     int32_t* tcur;               // [n_tobj] current .time of every time object (stochastic instances) or nullptr
@@ -190,8 +193,6 @@ struct alignas(16) EnvAux {
 struct Ctx {
     const InstDev* I;
     const CfgDev* C;
-    const int32_t* op_mt;   // this env's variant
-    const int32_t* op_dur;
     EnvAux* aux;
     int raise;              // JSL_ST_* of an escaping exception, 0 = none
     int now;
@@ -433,7 +434,7 @@ JSL_D int next_idle_place(const EnvS<JW, ST>& s, const Ctx& c, int j) {  // -1 =
     const InstDev& I = *c.I;
     int k = s.j_k[j] + (s.j_proc[j] ? 1 : 0);
     if (k >= job_nops(I, j)) return -1;
-    return c.op_mt[I.job_op_start[j] + k] & 0xffff;
+    return c.aux->op_mt[I.job_op_start[j] + k] & 0xffff;
 }
 
 template <int JW, bool ST>
@@ -507,7 +508,7 @@ JSL_D Trans current_candidate(const EnvS<JW, ST>& s, const Ctx& c) {
 // ------------------------------------------------------------------------------------ time objects
 // .time of a time object (no resample)
 template <bool ST>
-JSL_D int op_duration(const Ctx& c, int o) { return ST ? c.aux->tcur[o] : c.op_dur[o]; }
+JSL_D int op_duration(const Ctx& c, int o) { return ST ? c.aux->tcur[o] : c.aux->op_dur[o]; }
 template <bool ST>
 JSL_D int setup_time_cur(const Ctx& c, int i) {
     if (ST) return c.aux->tcur[c.I->off_setup + i];
@@ -725,7 +726,7 @@ JSL_D void machine_idle_to_setup(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     if (s.j_loc[j] != 3 * m) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     int o = I.job_op_start[j] + s.j_k[j];
-    int tool = (c.op_mt[o] >> 16) & 0xffff;
+    int tool = (c.aux->op_mt[o] >> 16) & 0xffff;
     int setup = 0;
     if (JSL_UNLIKELY(I.setup || ST)) {
         const int si = (m * I.NT + s.m_tool[m]) * I.NT + tool;
@@ -746,7 +747,7 @@ JSL_D void machine_setup_to_working(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8 || s.j_loc[j] != 3 * m + 2) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     const int o = I.job_op_start[j] + s.j_k[j];
-    int dur = tobj_update<ST>(c, s.draw_ctr, o, c.op_dur[o]);
+    int dur = tobj_update<ST>(c, s.draw_ctr, o, c.aux->op_dur[o]);
     if (JSL_UNLIKELY(c.raise)) return;
     s.j_proc[j] = 1; s.j_start[j] = c.now; s.j_end[j] = c.now + dur;
     s.m_state[m] = JSL_M_WORKING; s.m_occ[m] = c.now + dur;
@@ -781,7 +782,7 @@ JSL_D void machine_outage_to_idle(EnvS<JW, ST>& s, Ctx& c, int m) {
     }
     s.j_k[j] = (uint8_t)(k + 1);
     s.j_proc[j] = 0;
-    s.j_mach[j] = (k + 1 < job_nops(I, j)) ? (uint8_t)(c.op_mt[I.job_op_start[j] + k + 1] & 0xffff) : (uint8_t)NONE8;
+    s.j_mach[j] = (k + 1 < job_nops(I, j)) ? (uint8_t)(c.aux->op_mt[I.job_op_start[j] + k + 1] & 0xffff) : (uint8_t)NONE8;
     if (c.now > s.max_done_end) s.max_done_end = c.now;
     s.m_done[m] = (uint16_t)(s.m_done[m] + 1);
     s.m_job[m] = NONE8;
@@ -1075,10 +1076,10 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
     c.now = s.time;
     Mask<1> mm;
     Mask<JW> tm, tele;
-    Poss<JW> p;
     mm.w[0] = 0;
 #pragma unroll
-    for (int w = 0; w < JW; w++) { tm.w[w] = 0; tele.w[w] = 0; p.p1.w[w] = 0; p.idle.w[w] = 0; p.lr.w[w] = 0; p.li.w[w] = 0; }
+    for (int w = 0; w < JW; w++) { tm.w[w] = 0; tele.w[w] = 0; }
+    // the candidate masks live in the state (c_p1 / c_idle / c_lr / c_li), not in registers
     bool action_stage = has_action;
     bool first = true;
     bool evaluated = false;  // the time machine already ran for the current state
@@ -1103,7 +1104,8 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
             // that minimum IS `now` (nothing pending can lie in the past: every due component fires in the very
             // next batch), so the candidate scan is only needed in quiet batches and in the first one.
             if (!evaluated && (first || !time_due)) {
-                p = compute_poss(s, c);
+                const Poss<JW> p = compute_poss(s, c);
+                store_poss(s, p, false);
                 const bool anyp = p.p1.any() || (p.idle.any() && (p.lr.any() || p.li.any()));
                 if ((first && time_machine == TM_FORCE) || !anyp) {
                     const int t2 = force_jump_to_event(s, c);
@@ -1127,6 +1129,7 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
             }
 #endif
             evaluated = false;
+            const Poss<JW> p = cached_poss(s);
             if (first && p.idle.any() && (p.lr.any() || p.li.any())) {
                 // teleports (state.py:229-232, :414-467): i-th idle AGV <- i-th lonely job with zero travel time
                 auto zero_travel = [&](int j, bool& bad) {
@@ -1192,10 +1195,10 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
         if (s.max_done_end >= 0) s.time = s.max_done_end;
         s.n_possible = 0;
     } else {
-        s.n_possible = p.total();
+        s.n_possible = cached_poss(s).total();
     }
     s.all_out = done ? 1 : 0;
-    store_poss(s, p, done);
+    if (done) store_poss(s, cached_poss(s), true);
     return true;
 }
 
@@ -1215,7 +1218,7 @@ JSL_D void env_init(EnvS<JW, ST>& s, Ctx& c) {
         s.j_seq[j] = (uint32_t)j;  // initial stores list jobs in job order (mapper.py:1296-1321)
         s.j_loc[j] = live ? I.job_init_buf[j] : (uint16_t)0xffff;
         s.j_k[j] = 0; s.j_proc[j] = 0; s.j_agv[j] = NONE8;
-        s.j_mach[j] = (live && job_nops(I, j) > 0) ? (uint8_t)(c.op_mt[I.job_op_start[j]] & 0xffff) : (uint8_t)NONE8;
+        s.j_mach[j] = (live && job_nops(I, j) > 0) ? (uint8_t)(c.aux->op_mt[I.job_op_start[j]] & 0xffff) : (uint8_t)NONE8;
     });
     wp_for<1>(32, [&](int m) {
         s.m_occ[m] = JSL_NO_TIME; s.m_done[m] = 0; s.m_state[m] = JSL_M_IDLE;
@@ -1366,17 +1369,16 @@ JSL_D uint32_t philox_bit(uint64_t seed, uint64_t env_idx, uint32_t step) {
 
 // dipatching_benchmark.py:17-67 + dispatch_rules_uitls.py:57-111
 template <int JW, bool ST>
-JSL_D int policy_action(const EnvS<JW, ST>& s, const Ctx& c, int policy, uint64_t seed, uint64_t env_idx,
-                        const int32_t* job_work) {
+JSL_D int policy_action(const EnvS<JW, ST>& s, const Ctx& c, int policy) {
     const InstDev& I = *c.I;
-    if (policy == JSL_POLICY_RANDOM) return (int)philox_bit(seed, env_idx, (uint32_t)s.n_steps);
+    if (policy == JSL_POLICY_RANDOM) return (int)philox_bit(c.aux->seed, c.aux->env_id, (uint32_t)s.n_steps);
     if (policy == JSL_POLICY_FIFO || s.n_possible - s.skip <= 0) return 1;
     Trans cand = current_candidate(s, c);
     if (cand.kind == 1) return 1;
     const int pre = 3 * cand.comp, cj = cand.job;
     auto key = [&](int j) {
         if (policy == JSL_POLICY_SPT) return op_duration<ST>(c, I.job_op_start[j] + s.j_k[j]);
-        if (!ST) return (int)job_work[j];
+        if (!ST) return (int)c.aux->job_work[j];
         int w = 0;
         for (int o = I.job_op_start[j]; o < I.job_op_start[j + 1]; o++) w += c.aux->tcur[o];
         return w;
@@ -1449,7 +1451,7 @@ JSL_D void write_obs_binary(const EnvS<JW, ST>& s, const Ctx& c, uint8_t* out) {
         int8_t* row = exec + r * M;
         for (int m = 0; m < M; m++) row[m] = 0;
         int o0 = I.job_op_start[j];
-        for (int k = 0; k < s.j_k[j]; k++) row[c.op_mt[o0 + k] & 0xffff] = 1;
+        for (int k = 0; k < s.j_k[j]; k++) row[c.aux->op_mt[o0 + k] & 0xffff] = 1;
     });
     wp_for<1>(M, [&](int r) {
         int m = I.mach_lex[r];
@@ -1519,7 +1521,7 @@ JSL_D void write_obs_tassel(const EnvS<JW, ST>& s, const Ctx& c, uint8_t* out) {
         f[3 * J + j] = (float)((double)remaining / mat);
         int wait = 0;
         if (kidle < n) {
-            int m = c.op_mt[o0 + kidle] & 0xffff;
+            int m = c.aux->op_mt[o0 + kidle] & 0xffff;
             if (s.m_state[m] == JSL_M_WORKING) wait = s.m_occ[m] - now;
         }
         f[4 * J + j] = (float)wait;

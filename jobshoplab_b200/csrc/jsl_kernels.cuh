@@ -58,13 +58,14 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
     EnvAux* aux = (EnvAux*)(slot + bd.state_stride + bd.outs_stride);
     c.I = &bd.inst;
     c.C = &bd.cfg;
-    c.op_mt = I.op_mt + v * I.N;
-    c.op_dur = I.op_dur + v * I.N;
     c.aux = aux;
     c.raise = 0;
     c.now = 0;
     __syncwarp();
     if (JSL_LANE == 0) {
+        aux->op_mt = I.op_mt + v * I.N;
+        aux->op_dur = I.op_dur + v * I.N;
+        aux->job_work = I.job_work + v * I.J;
         aux->op_log = bd.op_log ? bd.op_log + env * 2 * (int64_t)I.N : nullptr;
         aux->outs = bd.outs ? (void*)(slot + bd.state_stride) : nullptr;
         aux->tcur = bd.tcur ? bd.tcur + env * (int64_t)I.n_tobj : nullptr;
@@ -204,7 +205,6 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
             if (g_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
         }
         __syncwarp();
-        const int32_t* job_work = bd.inst.job_work + (env % bd.inst.n_inst) * bd.inst.J;
         const uint8_t* my_tape = tape ? tape + env * tape_stride : nullptr;
         int n = 0;
 #pragma unroll 1
@@ -218,7 +218,7 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
                     if (s.n_steps >= tape_stride) break;
                     op = my_tape[s.n_steps];
                 } else {
-                    op = policy_action(s, c, policy, bd.seed, (uint64_t)(bd.env_base + env), job_work);
+                    op = policy_action(s, c, policy);
                 }
                 n++;
             }

@@ -61,7 +61,7 @@ void lex_order(const char* pfx, int n, std::vector<uint8_t>& out) {
 
 void make_ctx(Sim* s, Ctx& c) {
     EnvAux& a = s->aux;
-    c.I = &s->I; c.C = &s->C; c.op_mt = s->op_mt.data(); c.op_dur = s->op_dur.data();
+    c.I = &s->I; c.C = &s->C; a.op_mt = s->op_mt.data(); a.op_dur = s->op_dur.data(); a.job_work = s->job_work.data();
     c.aux = &a; c.raise = 0; c.now = 0;
     a.op_log = s->C.record_ops ? s->op_log.data() : nullptr;
     a.outs = s->outs_bytes ? (void*)s->outs.data() : nullptr;
@@ -116,7 +116,7 @@ template <int JW, bool ST> int do_rollout(Sim* s, int policy, const uint8_t* tap
     while (n < max_steps && st.status == JSL_ST_OK) {
         int a;
         if (policy == JSL_POLICY_TAPE) { if (st.n_steps >= n_tape) break; a = tape[st.n_steps]; }
-        else a = policy_action(st, c, policy, s->seed, env_idx, s->job_work.data());
+        else { c.aux->env_id = env_idx; a = policy_action(st, c, policy); }
         run_env_op(st, c, a);
         n++;
     }
