@@ -182,6 +182,9 @@ struct alignas(16) EnvAux {
     uint16_t* tseed;             // [n_tobj] current numpy seed of every stochastic time object
     const int32_t* start_seeds;  // [n_tobj] recorded start seeds, or nullptr (drawn 0..30 from Philox)
     const int32_t* tape;         // replayed update() results, or nullptr (table mode)
+    const uint8_t* action_tape;  // TAPE policy: this env's actions
+    int64_t env;                 // index of the env inside its batch
+    int32_t step_limit;          // rollout: stop once n_steps reaches this
     uint64_t seed, env_id;       // Philox key / stream of this env
     double neg_inv_n;            // -1.0 / N: the dense reward of a penalised step (rewards.py:135-138)
     int32_t tape_len;

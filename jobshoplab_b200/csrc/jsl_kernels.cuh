@@ -195,48 +195,50 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
         if (JSL_LANE == 0) next = atomicAdd(bd.work_counter, 1ull);
         const int64_t env = (int64_t)__shfl_sync(0xffffffffu, next, 0);
         if (env >= bd.B) break;
-        uint8_t* g_state = bd.state + env * (int64_t)bd.state_stride;
-        uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
         Ctx c;
         make_ctx(c, bd, env, slot);
         bool pending_reset = (flags & JSL_RO_RESET_FIRST) != 0;
         if (!pending_reset) {
-            copy_in(&s, g_state, bd.state_stride);
-            if (g_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
+            copy_in(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
+            if (bd.outs) copy_in(outs_sm, bd.outs + env * (int64_t)bd.outs_stride, bd.outs_stride);
+        }
+        if (JSL_LANE == 0) {  // per-env loop constants live in the aux block, not in registers
+            c.aux->env = env;
+            c.aux->action_tape = tape ? tape + env * tape_stride : nullptr;
+            const int64_t lim = (int64_t)(pending_reset ? 0 : s.n_steps) + max_steps;
+            c.aux->step_limit = lim > 0x7fffffff ? 0x7fffffff : (int32_t)lim;
         }
         __syncwarp();
-        const uint8_t* my_tape = tape ? tape + env * tape_stride : nullptr;
-        int n = 0;
 #pragma unroll 1
         for (;;) {
             int op;
             if (pending_reset) {
                 op = OP_RESET;
             } else {
-                if (n >= max_steps || s.status != JSL_ST_OK) break;
+                if (s.n_steps >= c.aux->step_limit || s.status != JSL_ST_OK) break;
                 if (policy == JSL_POLICY_TAPE) {
                     if (s.n_steps >= tape_stride) break;
-                    op = my_tape[s.n_steps];
+                    op = c.aux->action_tape[s.n_steps];
                 } else {
                     op = policy_action(s, c, policy);
                 }
-                n++;
             }
             run_env_op(s, c, op);
             pending_reset = false;
             __syncwarp();
         }
+        const int64_t e = c.aux->env;
         if (JSL_LANE == 0) {
-            if (out.makespan) out.makespan[env] = s.time;
-            if (out.n_steps) out.n_steps[env] = s.n_steps;
-            if (out.ret) out.ret[env] = s.ret;
-            if (out.status) out.status[env] = (uint8_t)s.status;
-            if (out.no_op_count) out.no_op_count[env] = s.noop_count;
+            if (out.makespan) out.makespan[e] = s.time;
+            if (out.n_steps) out.n_steps[e] = s.n_steps;
+            if (out.ret) out.ret[e] = s.ret;
+            if (out.status) out.status[e] = (uint8_t)s.status;
+            if (out.no_op_count) out.no_op_count[e] = s.noop_count;
         }
         __syncwarp();
         if (!(flags & JSL_RO_NO_WRITEBACK)) {
-            copy_in(g_state, &s, bd.state_stride);
-            if (g_outs) copy_in(g_outs, outs_sm, bd.outs_stride);
+            copy_in(bd.state + e * (int64_t)bd.state_stride, &s, bd.state_stride);
+            if (bd.outs) copy_in(bd.outs + e * (int64_t)bd.outs_stride, outs_sm, bd.outs_stride);
         }
         __syncwarp();
     }
