@@ -238,6 +238,8 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     I.flex_pre = all_equal(t->pre_type, JSL_BUF_FLEX);
     I.flex_post = all_equal(t->post_type, JSL_BUF_FLEX) && all_equal(t->sbuf_type, JSL_BUF_FLEX);
     I.caps_inf = all_equal(t->pre_cap, JSL_CAP_INF) && all_equal(t->post_cap, JSL_CAP_INF) && all_equal(t->sbuf_cap, JSL_CAP_INF);
+    b->bd.classic = I.flex_pre && I.flex_post && I.caps_inf && !I.has_m_out && !I.has_t_out && !I.setup && !I.travel &&
+                    !t->stochastic && I.out_buf >= 0;
     CfgDev& C = b->bd.cfg;
     C.allow_early_transport = cfg->allow_early_transport; C.truncation_joker = cfg->truncation_joker;
     C.truncation_active = cfg->truncation_active; C.obs_kind = cfg->obs_kind; C.record_ops = cfg->record_ops;

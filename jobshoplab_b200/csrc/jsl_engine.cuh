@@ -121,7 +121,7 @@ struct CfgDev {
 // ------------------------------------------------------------------------------------ state
 // Mutable state of one env.  JW = ceil(max(J,T)/32) lane words; machines <= 32.
 // The same struct is the HBM image (step mode) and the shared-memory working copy.
-template <int JW, bool ST = false>
+template <int JW, bool ST = false, bool CL = false>
 struct alignas(16) EnvS {
     static constexpr int MJ = 32 * JW, MT = 32 * JW, MM = 32;
     // scalars (uniform)
@@ -357,14 +357,14 @@ JSL_D int job_nops(const InstDev& I, int j) { return I.job_op_start[j + 1] - I.j
 JSL_D int travel_time(const InstDev& I, int a, int b) { return I.travel ? I.travel[a * I.NP + b] : 0; }
 
 // ------------------------------------------------------------------------------------ buffers as (loc, seq)
-template <int JW, bool ST>
-JSL_DN int buf_count(const EnvS<JW, ST>& s, const InstDev& I, int b) {
+template <int JW, bool ST, bool CL>
+JSL_DN int buf_count(const EnvS<JW, ST, CL>& s, const InstDev& I, int b) {
     return wp_ballot<JW>(I.J, [&](int j) { return s.j_loc[j] == b; }).count();
 }
 
 // buffer_type_utils.py:236-262 get_next_job_from_buffer; -1 = None
-template <int JW, bool ST>
-JSL_DN int next_job_from_buffer(const EnvS<JW, ST>& s, const InstDev& I, int b) {
+template <int JW, bool ST, bool CL>
+JSL_DN int next_job_from_buffer(const EnvS<JW, ST, CL>& s, const InstDev& I, int b) {
     int ty = buf_type(I, b);
     if (ty == JSL_BUF_FLEX) return -1;
     // seq stamps are unique per env, so the stamp identifies the job
@@ -380,8 +380,8 @@ JSL_DN int next_job_from_buffer(const EnvS<JW, ST>& s, const InstDev& I, int b) 
 }
 
 // buffer_type_utils.py:328-353 is_job_ready_for_pickup_from_postbuffer (uniform j)
-template <int JW, bool ST>
-JSL_DN bool ready_for_pickup(const EnvS<JW, ST>& s, const InstDev& I, int j) {
+template <int JW, bool ST, bool CL>
+JSL_DN bool ready_for_pickup(const EnvS<JW, ST, CL>& s, const InstDev& I, int j) {
     int b = s.j_loc[j];
     bool right = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
     if (!right) return false;
@@ -393,8 +393,8 @@ JSL_DN bool ready_for_pickup(const EnvS<JW, ST>& s, const InstDev& I, int j) {
     return !wp_ballot<JW>(I.J, [&](int q) { return s.j_loc[q] == b && s.j_seq[q] < sq; }).any();
 }
 // same test evaluated by one lane for its own job (serial scan; only used when early transport is off)
-template <int JW, bool ST>
-JSL_D bool ready_for_pickup_lane(const EnvS<JW, ST>& s, const InstDev& I, int j) {
+template <int JW, bool ST, bool CL>
+JSL_D bool ready_for_pickup_lane(const EnvS<JW, ST, CL>& s, const InstDev& I, int j) {
     int b = s.j_loc[j];
     bool right = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
     if (!right) return false;
@@ -408,10 +408,10 @@ JSL_D bool ready_for_pickup_lane(const EnvS<JW, ST>& s, const InstDev& I, int j)
 }
 
 // buffer_type_utils.py:77-105 put_in_buffer (multi-slot buffers)
-template <int JW, bool ST>
-JSL_D void put_in_buffer(EnvS<JW, ST>& s, Ctx& c, int b, int j) {
+template <int JW, bool ST, bool CL>
+JSL_D void put_in_buffer(EnvS<JW, ST, CL>& s, Ctx& c, int b, int j) {
     const InstDev& I = *c.I;
-    if (JSL_UNLIKELY(!I.caps_inf)) {
+    if (JSL_UNLIKELY(!CL && !I.caps_inf)) {
         int cap = buf_cap(I, b);
         if (cap != JSL_CAP_INF && buf_count(s, I, b) >= cap) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
     }
@@ -432,16 +432,16 @@ struct Poss {
 };
 
 // machine of the next IDLE op of job j and whether it has one (lane-local)
-template <int JW, bool ST>
-JSL_D int next_idle_place(const EnvS<JW, ST>& s, const Ctx& c, int j) {  // -1 = none -> output buffer
+template <int JW, bool ST, bool CL>
+JSL_D int next_idle_place(const EnvS<JW, ST, CL>& s, const Ctx& c, int j) {  // -1 = none -> output buffer
     const InstDev& I = *c.I;
     int k = s.j_k[j] + (s.j_proc[j] ? 1 : 0);
     if (k >= job_nops(I, j)) return -1;
     return c.aux->op_mt[I.job_op_start[j] + k] & 0xffff;
 }
 
-template <int JW, bool ST>
-JSL_D Poss<JW> compute_poss(const EnvS<JW, ST>& s, const Ctx& c) {
+template <int JW, bool ST, bool CL>
+JSL_D Poss<JW> compute_poss(const EnvS<JW, ST, CL>& s, const Ctx& c) {
     const InstDev& I = *c.I;
     Poss<JW> p;
     // possible_transition_utils.py:68-118 is_action_possible
@@ -471,8 +471,8 @@ struct Trans {
 };
 
 // idx-th element of get_possible_transitions(state) (state.py:298-341 ordering)
-template <int JW, bool ST>
-JSL_D Trans nth_possible(const EnvS<JW, ST>& s, const Ctx& c, const Poss<JW>& p, int idx) {
+template <int JW, bool ST, bool CL>
+JSL_D Trans nth_possible(const EnvS<JW, ST, CL>& s, const Ctx& c, const Poss<JW>& p, int idx) {
     Trans t;
     int n1 = p.p1.count();
     if (idx < n1) {
@@ -487,15 +487,15 @@ JSL_D Trans nth_possible(const EnvS<JW, ST>& s, const Ctx& c, const Poss<JW>& p,
     return t;
 }
 
-template <int JW, bool ST>
-JSL_D Poss<JW> cached_poss(const EnvS<JW, ST>& s) {
+template <int JW, bool ST, bool CL>
+JSL_D Poss<JW> cached_poss(const EnvS<JW, ST, CL>& s) {
     Poss<JW> p;
 #pragma unroll
     for (int w = 0; w < JW; w++) { p.p1.w[w] = s.c_p1[w]; p.idle.w[w] = s.c_idle[w]; p.lr.w[w] = s.c_lr[w]; p.li.w[w] = s.c_li[w]; }
     return p;
 }
-template <int JW, bool ST>
-JSL_D void store_poss(EnvS<JW, ST>& s, const Poss<JW>& p, bool clear) {
+template <int JW, bool ST, bool CL>
+JSL_D void store_poss(EnvS<JW, ST, CL>& s, const Poss<JW>& p, bool clear) {
 #pragma unroll
     for (int w = 0; w < JW; w++) {
         s.c_p1[w] = clear ? 0u : p.p1.w[w]; s.c_idle[w] = clear ? 0u : p.idle.w[w];
@@ -503,8 +503,8 @@ JSL_D void store_poss(EnvS<JW, ST>& s, const Poss<JW>& p, bool clear) {
     }
 }
 // the candidate the agent is looking at: possible_transitions[0] after `skip` dropped ones
-template <int JW, bool ST>
-JSL_D Trans current_candidate(const EnvS<JW, ST>& s, const Ctx& c) {
+template <int JW, bool ST, bool CL>
+JSL_D Trans current_candidate(const EnvS<JW, ST, CL>& s, const Ctx& c) {
     return nth_possible(s, c, cached_poss(s), s.skip);
 }
 
@@ -512,15 +512,15 @@ JSL_D Trans current_candidate(const EnvS<JW, ST>& s, const Ctx& c) {
 // .time of a time object (no resample)
 template <bool ST>
 JSL_D int op_duration(const Ctx& c, int o) { return ST ? c.aux->tcur[o] : c.aux->op_dur[o]; }
-template <bool ST>
+template <bool ST, bool CL>
 JSL_D int setup_time_cur(const Ctx& c, int i) {
     if (ST) return c.aux->tcur[c.I->off_setup + i];
-    return c.I->setup ? c.I->setup[i] : 0;
+    return (!CL && c.I->setup) ? c.I->setup[i] : 0;
 }
-template <bool ST>
+template <bool ST, bool CL>
 JSL_D int travel_time_cur(const Ctx& c, int a, int b) {
     if (ST) return c.aux->tcur[c.I->off_travel + a * c.I->NP + b];
-    return c.I->travel ? c.I->travel[a * c.I->NP + b] : 0;
+    return (!CL && c.I->travel) ? c.I->travel[a * c.I->NP + b] : 0;
 }
 
 struct Rng4 { uint32_t x, y, z, w; };
@@ -705,8 +705,8 @@ JSL_D void release_outages(int n, uint8_t* active, int32_t* a, int32_t* b) {
 
 // ------------------------------------------------------------------------------------ machine handlers
 // validate.py:30-82.  returns false on a validation error (StateMachineResult.success = False)
-template <int JW, bool ST>
-JSL_D bool machine_valid(const EnvS<JW, ST>& s, Ctx& c, int m, int to, int job) {
+template <int JW, bool ST, bool CL>
+JSL_D bool machine_valid(const EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int job) {
     int from = s.m_state[m];
     if (from == to) return false;
     bool ok = from == JSL_M_IDLE ? to == JSL_M_SETUP
@@ -723,17 +723,17 @@ JSL_D bool machine_valid(const EnvS<JW, ST>& s, Ctx& c, int m, int to, int job) 
 }
 
 // handler.py:414-457 + manipulate.py:378-444
-template <int JW, bool ST>
-JSL_D void machine_idle_to_setup(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
+template <int JW, bool ST, bool CL>
+JSL_D void machine_idle_to_setup(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     if (s.j_loc[j] != 3 * m) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     int o = I.job_op_start[j] + s.j_k[j];
     int tool = (c.aux->op_mt[o] >> 16) & 0xffff;
     int setup = 0;
-    if (JSL_UNLIKELY(I.setup || ST)) {
+    if (JSL_UNLIKELY(!CL && (I.setup || ST))) {
         const int si = (m * I.NT + s.m_tool[m]) * I.NT + tool;
-        setup = setup_time_cur<ST>(c, si);
+        setup = setup_time_cur<ST, CL>(c, si);
         if (setup == JSL_NO_TIME && !(ST && I.tobj_kind[I.off_setup + si] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
         setup = tobj_update<ST>(c, s.draw_ctr, I.off_setup + si, setup);
         if (JSL_UNLIKELY(c.raise)) return;
@@ -745,8 +745,8 @@ JSL_D void machine_idle_to_setup(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
     s.m_state[m] = JSL_M_SETUP; s.m_occ[m] = c.now + setup; s.m_tool[m] = (uint8_t)tool;
 }
 // handler.py:460-503 + manipulate.py:225-276
-template <int JW, bool ST>
-JSL_D void machine_setup_to_working(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
+template <int JW, bool ST, bool CL>
+JSL_D void machine_setup_to_working(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8 || s.j_loc[j] != 3 * m + 2) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     const int o = I.job_op_start[j] + s.j_k[j];
@@ -756,11 +756,11 @@ JSL_D void machine_setup_to_working(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
     s.m_state[m] = JSL_M_WORKING; s.m_occ[m] = c.now + dur;
 }
 // handler.py:506-543 + manipulate.py:328-375
-template <int JW, bool ST>
-JSL_D void machine_working_to_outage(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
+template <int JW, bool ST, bool CL>
+JSL_D void machine_working_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     int occupied_for = 0;
-    if (JSL_UNLIKELY(I.has_m_out)) {
+    if (JSL_UNLIKELY(!CL && I.has_m_out)) {
         int b = I.m_out_start[m], n = I.m_out_start[m + 1] - b;
         OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
         occupied_for = sample_outages<ST>(c, s.draw_ctr, c.now, n, I.m_out_freq + b, I.m_out_dur + b, I.off_mof + b,
@@ -772,8 +772,8 @@ JSL_D void machine_working_to_outage(EnvS<JW, ST>& s, Ctx& c, int m, int j) {
     s.j_end[j] = c.now + occupied_for;
 }
 // handler.py:546-574 + manipulate.py:117-193
-template <int JW, bool ST>
-JSL_D void machine_outage_to_idle(EnvS<JW, ST>& s, Ctx& c, int m) {
+template <int JW, bool ST, bool CL>
+JSL_D void machine_outage_to_idle(EnvS<JW, ST, CL>& s, Ctx& c, int m) {
     const InstDev& I = *c.I;
     int j = s.m_job[m];
     if (j == NONE8 || !s.j_proc[j]) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -791,7 +791,7 @@ JSL_D void machine_outage_to_idle(EnvS<JW, ST>& s, Ctx& c, int m) {
     s.m_job[m] = NONE8;
     put_in_buffer(s, c, 3 * m + 1, j);
     if (JSL_UNLIKELY(c.raise)) return;
-    if (JSL_UNLIKELY(I.has_m_out)) {
+    if (JSL_UNLIKELY(!CL && I.has_m_out)) {
         OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
         release_outages(I.m_out_start[m + 1] - I.m_out_start[m], o.mo_active + m * MAX_OUT, o.mo_a + m * MAX_OUT,
                         o.mo_b + m * MAX_OUT);
@@ -800,8 +800,8 @@ JSL_D void machine_outage_to_idle(EnvS<JW, ST>& s, Ctx& c, int m) {
 }
 
 // process one machine transition (validate + handle); false = validation error
-template <int JW, bool ST>
-JSL_D bool apply_machine(EnvS<JW, ST>& s, Ctx& c, int m, int to, int job) {
+template <int JW, bool ST, bool CL>
+JSL_D bool apply_machine(EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int job) {
     if (!machine_valid(s, c, m, to, job)) return false;
     if (JSL_UNLIKELY(c.raise)) return true;
     int from = s.m_state[m];
@@ -815,8 +815,8 @@ JSL_D bool apply_machine(EnvS<JW, ST>& s, Ctx& c, int m, int to, int job) {
 // ------------------------------------------------------------------------------------ transport handlers
 JSL_D int t_general(int st) { return st == JSL_T_IDLE ? 0 : st == JSL_T_OUTAGE ? 2 : 1; }
 // validate.py:85-118 + transitions.py:82-107,161-186
-template <int JW, bool ST>
-JSL_D bool transport_valid(const EnvS<JW, ST>& s, int t, int to) {
+template <int JW, bool ST, bool CL>
+JSL_D bool transport_valid(const EnvS<JW, ST, CL>& s, int t, int to) {
     // bit (from*6 + to): idle->running, running->running|outage (same state only for WAITINGPICKUP), outage->idle
     constexpr uint64_t R = (1ull << JSL_T_WORKING) | (1ull << JSL_T_PICKUP) | (1ull << JSL_T_TRANSIT) | (1ull << JSL_T_WAITINGPICKUP);
     constexpr uint64_t RO = R | (1ull << JSL_T_OUTAGE);
@@ -833,8 +833,8 @@ JSL_D int output_place(Ctx& c) {
 }
 
 // handler.py:808-902 idle -> working (PICKUP)
-template <int JW, bool ST>
-JSL_D void agv_idle_to_working(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
+template <int JW, bool ST, bool CL>
+JSL_D void agv_idle_to_working(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     if (s.t_lockind[t] != 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -844,7 +844,7 @@ JSL_D void agv_idle_to_working(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
     int loc = s.j_loc[j];
     int src = place_of_buf(I, loc);
     if (src < 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TransportConfigError
-    int ttp = travel_time_cur<ST>(c, s.t_loc0[t], src);    // no resample (handler.py:876-885)
+    int ttp = travel_time_cur<ST, CL>(c, s.t_loc0[t], src);    // no resample (handler.py:876-885)
     if (ttp == JSL_NO_TIME) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     s.t_occkind[t] = OCC_TIME; s.t_occ[t] = c.now + ttp;
     s.t_lockind[t] = 1; s.t_loc1[t] = (uint16_t)loc; s.t_loc2[t] = (uint8_t)target;
@@ -854,8 +854,8 @@ JSL_D void agv_idle_to_working(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
 }
 
 // handler.py:577-639 _get_waiting_time, :642-702, :989-1030
-template <int JW, bool ST>
-JSL_D void agv_to_waitingpickup(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
+template <int JW, bool ST, bool CL>
+JSL_D void agv_to_waitingpickup(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     int loc = s.j_loc[j];
@@ -865,7 +865,7 @@ JSL_D void agv_to_waitingpickup(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
     } else if (is_agv_buf(I, loc)) {
         JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     } else if (loc % 3 == 1) {  // in the machine's postbuffer
-        if (!ready_for_pickup(s, I, j)) {
+        if (!CL && !ready_for_pickup(s, I, j)) {  // FLEX postbuffers: always ready
             int nxt = next_job_from_buffer(s, I, loc);
             if (nxt < 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
             int other = s.j_agv[nxt];
@@ -888,8 +888,8 @@ JSL_D void agv_to_waitingpickup(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
 }
 
 // handler.py:705-805 (waiting)pickup -> transit
-template <int JW, bool ST>
-JSL_D void agv_to_transit(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
+template <int JW, bool ST, bool CL>
+JSL_D void agv_to_transit(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     int loc = s.j_loc[j];
@@ -901,7 +901,7 @@ JSL_D void agv_to_transit(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
     else dst = s.j_mach[j];  // get_next_not_done_operation(job).machine_id
     if (JSL_UNLIKELY(c.raise)) return;
     if (!(src < I.M || dst < I.M)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
-    int travel = travel_time_cur<ST>(c, src, dst);
+    int travel = travel_time_cur<ST, CL>(c, src, dst);
     const int tobj = I.off_travel + src * I.NP + dst;
     if (travel == JSL_NO_TIME && !(ST && I.tobj_kind[tobj] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);  // TravelTimeError
     travel = tobj_update<ST>(c, s.draw_ctr, tobj, travel);  // resampled (time_utils.py:15)
@@ -915,8 +915,8 @@ JSL_D void agv_to_transit(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
 }
 
 // handler.py:905-958 + manipulate.py:45-114 transit -> outage (drop-off)
-template <int JW, bool ST>
-JSL_D void agv_transit_to_outage(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
+template <int JW, bool ST, bool CL>
+JSL_D void agv_transit_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     if (s.t_lockind[t] != 1) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -927,7 +927,7 @@ JSL_D void agv_transit_to_outage(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
     put_in_buffer(s, c, to_buf, j);
     if (JSL_UNLIKELY(c.raise)) return;
     int occupied_for = 0;
-    if (JSL_UNLIKELY(I.has_t_out)) {
+    if (JSL_UNLIKELY(!CL && I.has_t_out)) {
         OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
         occupied_for = sample_outages<ST>(c, s.draw_ctr, c.now, I.n_t_out, I.t_out_freq, I.t_out_dur, I.off_tof, I.off_tod,
                                       o.to_active + t * MAX_OUT, o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
@@ -941,8 +941,8 @@ JSL_D void agv_transit_to_outage(EnvS<JW, ST>& s, Ctx& c, int t, int j) {
 }
 
 // process one transport transition; false = validation error
-template <int JW, bool ST>
-JSL_D bool apply_transport(EnvS<JW, ST>& s, Ctx& c, int t, int to, int job) {
+template <int JW, bool ST, bool CL>
+JSL_D bool apply_transport(EnvS<JW, ST, CL>& s, Ctx& c, int t, int to, int job) {
     if (!transport_valid(s, t, to)) return false;
     int from = s.t_state[t];
     if (from == JSL_T_IDLE && to == JSL_T_WORKING) agv_idle_to_working(s, c, t, job);
@@ -950,7 +950,7 @@ JSL_D bool apply_transport(EnvS<JW, ST>& s, Ctx& c, int t, int to, int job) {
     else if ((from == JSL_T_WAITINGPICKUP || from == JSL_T_PICKUP) && to == JSL_T_TRANSIT) agv_to_transit(s, c, t, job);
     else if ((from == JSL_T_WORKING || from == JSL_T_TRANSIT) && to == JSL_T_OUTAGE) agv_transit_to_outage(s, c, t, job);
     else if (from == JSL_T_OUTAGE && to == JSL_T_IDLE) {  // handler.py:961-986
-        if (c.I->has_t_out) {
+        if (!CL && c.I->has_t_out) {
             OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
             release_outages(c.I->n_t_out, o.to_active + t * MAX_OUT, o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
         }
@@ -962,8 +962,8 @@ JSL_D bool apply_transport(EnvS<JW, ST>& s, Ctx& c, int t, int to, int job) {
 
 // ------------------------------------------------------------------------------------ time machines
 // time_machines.py:133-221
-template <int JW, bool ST>
-JSL_D int force_jump_to_event(const EnvS<JW, ST>& s, Ctx& c) {
+template <int JW, bool ST, bool CL>
+JSL_D int force_jump_to_event(const EnvS<JW, ST, CL>& s, Ctx& c) {
     const InstDev& I = *c.I;
     int bj = wp_min<JW>(I.J, [&](int j) { return s.j_proc[j] ? s.j_end[j] : INT_BIG; });
     bool bad = false;
@@ -986,8 +986,8 @@ JSL_D int force_jump_to_event(const EnvS<JW, ST>& s, Ctx& c) {
 // ------------------------------------------------------------------------------------ timed transitions
 // handler.py:55-153, :329-379: evaluate on the current snapshot into the x_* scratch arrays.
 // returns true when at least one transition was created.
-template <int JW, bool ST>
-JSL_D bool create_timed(EnvS<JW, ST>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, bool& time_due) {
+template <int JW, bool ST, bool CL>
+JSL_D bool create_timed(EnvS<JW, ST, CL>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, bool& time_due) {
     const InstDev& I = *c.I;
     const int now = c.now;
     // machines: occupied_till reached -> next state
@@ -999,7 +999,7 @@ JSL_D bool create_timed(EnvS<JW, ST>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, bool
     });
     time_due = mm.any();
     JSL_SYNCWARP();
-    if (JSL_UNLIKELY(!I.flex_pre)) {  // handler.py:117-153: automatic start from FIFO/LIFO/DUMMY prebuffers
+    if (JSL_UNLIKELY(!CL && !I.flex_pre)) {  // handler.py:117-153: automatic start from FIFO/LIFO/DUMMY prebuffers
         Mask<1> cand = wp_ballot<1>(I.M, [&](int m) {
             return !mm.test(m) && s.m_state[m] == JSL_M_IDLE && I.pre_type[m] != JSL_BUF_FLEX;
         });
@@ -1016,7 +1016,7 @@ JSL_D bool create_timed(EnvS<JW, ST>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, bool
     // transports (a PICKUP/WAITINGPICKUP transport without a job or a TRANSIT one without cargo -- raises in
     // the reference -- is caught by the handlers: job == NONE8)
     Mask<JW> need_ready, td;
-    const bool flex_post = I.flex_post != 0;
+    const bool flex_post = CL || I.flex_post != 0;
     tm = wp_ballot<JW>(I.T, [&](int t) {
         s.x_tkind[t] = NONE8;
         if (s.t_occkind[t] != OCC_TIME || s.t_occ[t] > now) return false;
@@ -1042,7 +1042,7 @@ JSL_D bool create_timed(EnvS<JW, ST>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, bool
             if (ready_for_pickup(s, I, s.t_job[t])) s.x_tkind[t] = JSL_T_TRANSIT;
         }
     }
-    if (JSL_UNLIKELY(!I.flex_post)) {  // handler.py:278-326,356-359 resolved TimeDependency -> stored transition
+    if (JSL_UNLIKELY(!CL && !I.flex_post)) {  // handler.py:278-326,356-359 resolved TimeDependency -> stored transition
         td = wp_ballot<JW>(I.T, [&](int t) { return s.t_occkind[t] == OCC_TD; });
         while (td.any()) {
             int t = td.pop_first();
@@ -1073,8 +1073,8 @@ constexpr int TM_JUMP = 0, TM_FORCE = 1;
 // was applied after them), so they double as the new possible_transitions.
 // Returns success (false = validation error -> StateMachineResult.success=False); escaping exceptions
 // are left in c.raise.
-template <int JW, bool ST>
-JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time_machine) {
+template <int JW, bool ST, bool CL>
+JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int time_machine) {
     const InstDev& I = *c.I;
     c.now = s.time;
     Mask<1> mm;
@@ -1142,13 +1142,13 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
                     if (nxt == -2) { bad = true; return false; }
                     if (cur == nxt) return true;
                     if (cur < 0) { bad = true; return false; }
-                    int tt = travel_time_cur<ST>(c, cur, nxt);
+                    int tt = travel_time_cur<ST, CL>(c, cur, nxt);
                     if (tt == JSL_NO_TIME) { bad = true; return false; }
                     return tt == 0;
                 };
                 Mask<JW> zr = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.lr.test(j) && zero_travel(j, bd); });
                 Mask<JW> zi = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.li.test(j) && zero_travel(j, bd); });
-                if (I.travel || ST || I.out_buf < 0) {
+                if (!CL && (I.travel || ST || I.out_buf < 0)) {
                     Mask<JW> badm = wp_ballot<JW>(I.J, [&](int j) {
                         bool bd = false;
                         if (p.lr.test(j) || p.li.test(j)) zero_travel(j, bd);
@@ -1206,8 +1206,8 @@ JSL_D bool sm_step(EnvS<JW, ST>& s, Ctx& c, bool has_action, Trans act, int time
 }
 
 // ------------------------------------------------------------------------------------ reset
-template <int JW, bool ST>
-JSL_D void env_init(EnvS<JW, ST>& s, Ctx& c) {
+template <int JW, bool ST, bool CL>
+JSL_D void env_init(EnvS<JW, ST, CL>& s, Ctx& c) {
     const InstDev& I = *c.I;
     s.time = I.start_time; s.seq_ctr = 0; s.n_possible = 0; s.skip = 0;
     s.joker = c.C->truncation_joker; s.step_noop = 0; s.step_action = 0; s.reward_noop = 0;
@@ -1215,7 +1215,7 @@ JSL_D void env_init(EnvS<JW, ST>& s, Ctx& c) {
     s.terminated = 0; s.truncated = 0; s.last_action_empty = 1; s.obs_done = 0;
     s.ret = 0.0;
     JSL_SYNCWARP();
-    wp_for<JW>(EnvS<JW, ST>::MJ, [&](int j) {
+    wp_for<JW>(EnvS<JW, ST, CL>::MJ, [&](int j) {
         bool live = j < I.J;
         s.j_start[j] = -1; s.j_end[j] = -1;
         s.j_seq[j] = (uint32_t)j;  // initial stores list jobs in job order (mapper.py:1296-1321)
@@ -1227,7 +1227,7 @@ JSL_D void env_init(EnvS<JW, ST>& s, Ctx& c) {
         s.m_occ[m] = JSL_NO_TIME; s.m_done[m] = 0; s.m_state[m] = JSL_M_IDLE;
         s.m_tool[m] = (uint8_t)I.default_tool; s.m_job[m] = NONE8; s.x_mkind[m] = 0; s.x_mjob[m] = NONE8;
     });
-    wp_for<JW>(EnvS<JW, ST>::MT, [&](int t) {
+    wp_for<JW>(EnvS<JW, ST, CL>::MT, [&](int t) {
         s.t_occ[t] = -1; s.t_loc1[t] = 0; s.t_tdbuf[t] = 0;
         s.t_state[t] = JSL_T_IDLE; s.t_job[t] = NONE8; s.t_carry[t] = NONE8; s.t_occkind[t] = OCC_NOTIME;
         s.t_lockind[t] = 0; s.t_loc0[t] = t < I.T ? I.agv_init_place[t] : 0; s.t_loc2[t] = 0;
@@ -1238,11 +1238,11 @@ JSL_D void env_init(EnvS<JW, ST>& s, Ctx& c) {
         wp_for<1>(32, [&](int m) {
             for (int k = 0; k < MAX_OUT; k++) { o.mo_active[m * MAX_OUT + k] = 0; o.mo_a[m * MAX_OUT + k] = -1; o.mo_b[m * MAX_OUT + k] = -1; }
         });
-        wp_for<JW>(EnvS<JW, ST>::MT, [&](int t) {
+        wp_for<JW>(EnvS<JW, ST, CL>::MT, [&](int t) {
             for (int k = 0; k < MAX_OUT; k++) { o.to_active[t * MAX_OUT + k] = 0; o.to_a[t * MAX_OUT + k] = -1; o.to_b[t * MAX_OUT + k] = -1; }
         });
     }
-    s.seq_ctr = EnvS<JW, ST>::MJ;
+    s.seq_ctr = EnvS<JW, ST, CL>::MJ;
     s.draw_ctr = 0;
     if (ST) stoch_init(c.I, c.aux->tcur, c.aux->tseed, c.aux->start_seeds, c.aux->tape, c.aux->seed, c.aux->env_id);
     JSL_SYNCWARP();
@@ -1250,8 +1250,8 @@ JSL_D void env_init(EnvS<JW, ST>& s, Ctx& c) {
 
 // ------------------------------------------------------------------------------------ reward / step
 // rewards.py:118-148 BinaryActionJsspReward.make, IEEE double without contraction
-template <int JW, bool ST>
-JSL_D double make_reward(EnvS<JW, ST>& s, const Ctx& c) {
+template <int JW, bool ST, bool CL>
+JSL_D double make_reward(EnvS<JW, ST, CL>& s, const Ctx& c) {
     double sr;
     if (s.truncated) sr = (c.C->truncation_bias * 1.0) / c.C->sparse_bias;
     else if (!s.terminated) sr = 0.0;
@@ -1278,8 +1278,8 @@ struct StepPlan {
 
 // everything before the state machine: argument checks, SubTimeStepper, what to run.
 // returns false when env.step raises before touching the state machine (status is set).
-template <int JW, bool ST>
-JSL_D bool env_step_pre(EnvS<JW, ST>& s, Ctx& c, int action, StepPlan& plan) {
+template <int JW, bool ST, bool CL>
+JSL_D bool env_step_pre(EnvS<JW, ST, CL>& s, Ctx& c, int action, StepPlan& plan) {
     plan.run_sm = false; plan.has_action = false; plan.time_machine = TM_JUMP;
     plan.act.kind = 0; plan.act.comp = 0; plan.act.new_state = 0; plan.act.job = 0;
     if (s.status > JSL_ST_TRUNCATED) return false;                                     // a raise already escaped
@@ -1300,8 +1300,8 @@ JSL_D bool env_step_pre(EnvS<JW, ST>& s, Ctx& c, int action, StepPlan& plan) {
 }
 
 // everything after it: middleware bookkeeping, terminated/truncated, reward.
-template <int JW, bool ST>
-JSL_D double env_step_post(EnvS<JW, ST>& s, Ctx& c, int action, const StepPlan& plan, bool success) {
+template <int JW, bool ST, bool CL>
+JSL_D double env_step_post(EnvS<JW, ST, CL>& s, Ctx& c, int action, const StepPlan& plan, bool success) {
     if (c.raise) { s.status = c.raise; return 0.0; }
     const bool action_empty = action == 0;
     if (action == 0 && plan.run_sm) {
@@ -1333,8 +1333,8 @@ JSL_D double env_step_post(EnvS<JW, ST>& s, Ctx& c, int action, const StepPlan& 
 // One env operation: OP_RESET (env.reset: init + dummy step) or an env.step(action).  The only place
 // sm_step is instantiated.
 constexpr int OP_RESET = -1;
-template <int JW, bool ST>
-JSL_D double run_env_op(EnvS<JW, ST>& s, Ctx& c, int op) {
+template <int JW, bool ST, bool CL>
+JSL_D double run_env_op(EnvS<JW, ST, CL>& s, Ctx& c, int op) {
     StepPlan plan;
     if (op == OP_RESET) {
         env_init(s, c);
@@ -1371,8 +1371,8 @@ JSL_D uint32_t philox_bit(uint64_t seed, uint64_t env_idx, uint32_t step) {
 }
 
 // dipatching_benchmark.py:17-67 + dispatch_rules_uitls.py:57-111
-template <int JW, bool ST>
-JSL_D int policy_action(const EnvS<JW, ST>& s, const Ctx& c, int policy) {
+template <int JW, bool ST, bool CL>
+JSL_D int policy_action(const EnvS<JW, ST, CL>& s, const Ctx& c, int policy) {
     const InstDev& I = *c.I;
     if (policy == JSL_POLICY_RANDOM) return (int)philox_bit(c.aux->seed, c.aux->env_id, (uint32_t)s.n_steps);
     if (policy == JSL_POLICY_FIFO || s.n_possible - s.skip <= 0) return 1;
@@ -1411,8 +1411,8 @@ JSL_HD int obs_bytes_binary(int J, int M) { return (16 + 4 * J + 4 * M + 2 * J +
 JSL_HD int obs_bytes_oparray(int J, int N) { return (16 + 4 * N + 4 * J + 15) & ~15; }
 JSL_HD int obs_bytes_tassel(int J) { return (7 * 4 * J + 15) & ~15; }
 
-template <int JW, bool ST>
-JSL_D void cand_floats(const EnvS<JW, ST>& s, const Ctx& c, float* tr) {
+template <int JW, bool ST, bool CL>
+JSL_D void cand_floats(const EnvS<JW, ST, CL>& s, const Ctx& c, float* tr) {
     const InstDev& I = *c.I;
     if (!s.obs_done && s.n_possible - s.skip > 0) {
         Trans cand = current_candidate(s, c);
@@ -1425,8 +1425,8 @@ JSL_D void cand_floats(const EnvS<JW, ST>& s, const Ctx& c, float* tr) {
     }
 }
 
-template <int JW, bool ST>
-JSL_D void write_obs_binary(const EnvS<JW, ST>& s, const Ctx& c, uint8_t* out) {
+template <int JW, bool ST, bool CL>
+JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* out) {
     const InstDev& I = *c.I;
     const int J = I.J, M = I.M;
     float tr[3];
@@ -1465,8 +1465,8 @@ JSL_D void write_obs_binary(const EnvS<JW, ST>& s, const Ctx& c, uint8_t* out) {
 
 // BinaryOperationArrayObservation.make (observations.py:631-693 over :588-618):
 //   f32 current_transition[3] | f32 0 | f32 operation_state[N] | f32 job_locations[J]
-template <int JW, bool ST>
-JSL_D void write_obs_oparray(const EnvS<JW, ST>& s, Ctx& c, uint8_t* out) {
+template <int JW, bool ST, bool CL>
+JSL_D void write_obs_oparray(const EnvS<JW, ST, CL>& s, Ctx& c, uint8_t* out) {
     const InstDev& I = *c.I;
     float tr[3];
     cand_floats(s, c, tr);
@@ -1501,8 +1501,8 @@ JSL_D void write_obs_oparray(const EnvS<JW, ST>& s, Ctx& c, uint8_t* out) {
 // TasselJsspObservation.make (observations.py:738-918): f32 [7][J] = allocatable | left_over_time |
 // percent_finished | total_completion | time_until_next_machine_is_free | idle_since_last_op | cum_idle_time.
 // Needs the per-op (start, end) log (cfg.record_ops is forced on for this observation kind).
-template <int JW, bool ST>
-JSL_D void write_obs_tassel(const EnvS<JW, ST>& s, const Ctx& c, uint8_t* out) {
+template <int JW, bool ST, bool CL>
+JSL_D void write_obs_tassel(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* out) {
     const InstDev& I = *c.I;
     const int J = I.J;
     float* f = (float*)out;
@@ -1547,8 +1547,8 @@ JSL_D void write_obs_tassel(const EnvS<JW, ST>& s, const Ctx& c, uint8_t* out) {
 // ------------------------------------------------------------------------------------ canonical digest
 // Layout documented in DESIGN.md / oracle/ref_harness.py.  Executed by one env's warp (diagnostics,
 // parity tests, render()).  Returns the number of int32 produced (writes at most cap).
-template <int JW, bool ST>
-JSL_D int write_digest(const EnvS<JW, ST>& s, const Ctx& c, int32_t* out, int cap) {
+template <int JW, bool ST, bool CL>
+JSL_D int write_digest(const EnvS<JW, ST, CL>& s, const Ctx& c, int32_t* out, int cap) {
     const InstDev& I = *c.I;
     int n = 0;
     // executed redundantly by every lane with identical values (uniform stores)

@@ -39,6 +39,7 @@ struct BatchDev {
     int32_t* tcur;       // [B][n_tobj] current .time of every time object (stochastic instances) or nullptr
     const int32_t* tape; // [B][tape_stride] replayed update() results or nullptr
     int64_t tape_stride;
+    int classic;         // all-FLEX unbounded buffers, zero travel/setup, no outages: the CL specialisation applies
     unsigned long long* work_counter;  // next env index of the persistent rollout grid (dynamic work queue)
     uint16_t* tseed;     // [B][n_tobj] numpy seed of every stochastic time object
     const int32_t* start_seeds;  // [B][n_tobj] or nullptr
@@ -82,8 +83,8 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
     __syncwarp();
 }
 
-template <int JW, bool ST>
-__device__ __forceinline__ void write_step_out(const EnvS<JW, ST>& s, Ctx& c, const jsl_step_out& out, int64_t env,
+template <int JW, bool ST, bool CL>
+__device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c, const jsl_step_out& out, int64_t env,
                                                double reward, int obs_bytes) {
     const InstDev& I = *c.I;
     if (out.obs && s.status <= JSL_ST_STEP_FAILED) {
@@ -116,7 +117,7 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW, ST>& s, Ctx& c, co
     (void)I;
 }
 
-template <int JW, bool ST>
+template <int JW, bool ST, bool CL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -125,7 +126,7 @@ k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, j
     if (env >= bd.B) return;
     if (mask && !mask[env]) return;
     uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
-    EnvS<JW, ST>& s = *(EnvS<JW, ST>*)slot;
+    EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
     void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
     Ctx c;
     make_ctx(c, bd, env, slot);
@@ -137,7 +138,7 @@ k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, j
     if (bd.outs) copy_in(bd.outs + env * (int64_t)bd.outs_stride, outs_sm, bd.outs_stride);
 }
 
-template <int JW, bool ST>
+template <int JW, bool ST, bool CL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_STEP_MIN_CTAS)
 k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -145,7 +146,7 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
     if (env >= bd.B) return;
     uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
-    EnvS<JW, ST>& s = *(EnvS<JW, ST>*)slot;
+    EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
     void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
     uint8_t* g_state = bd.state + env * (int64_t)bd.state_stride;
     uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
@@ -179,14 +180,14 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     if (g_outs) copy_in(g_outs, outs_sm, bd.outs_stride);
 }
 
-template <int JW, bool ST>
+template <int JW, bool ST, bool CL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_ROLLOUT_MIN_CTAS)
 k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __restrict__ tape, int64_t tape_stride,
           int max_steps, int flags, jsl_rollout_out out) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = WARPS_PER_CTA == 1 ? 0 : (int)(threadIdx.x >> 5);
     uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
-    EnvS<JW, ST>& s = *(EnvS<JW, ST>*)slot;
+    EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
     void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
     // persistent warps pull env indices from a global counter: episodes differ in length, a static
     // grid-stride split leaves the tail of the launch half empty
@@ -244,12 +245,12 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
     }
 }
 
-template <int JW, bool ST>
+template <int JW, bool ST, bool CL>
 __global__ void __launch_bounds__(32)
 k_digest(const __grid_constant__ BatchDev bd, int64_t env, int32_t* out, int cap, int32_t* n_out) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* slot = smem;
-    EnvS<JW, ST>& s = *(EnvS<JW, ST>*)smem;
+    EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)smem;
     void* outs_sm = bd.outs ? (void*)(smem + bd.state_stride) : nullptr;
     copy_in(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
     if (bd.outs) copy_in(outs_sm, bd.outs + env * (int64_t)bd.outs_stride, bd.outs_stride);
@@ -265,35 +266,35 @@ struct LaunchCfg {
     cudaStream_t stream;
 };
 
-template <int JW, bool ST>
+template <int JW, bool ST, bool CL>
 cudaError_t launch_reset(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* mask, jsl_step_out out, int obs_bytes) {
-    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_reset<JW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
-    k_reset<JW, ST><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, mask, out, obs_bytes);
+    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_reset<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+    k_reset<JW, ST, CL><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, mask, out, obs_bytes);
     return cudaGetLastError();
 }
-template <int JW, bool ST>
+template <int JW, bool ST, bool CL>
 cudaError_t launch_step(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* actions, jsl_step_out out, int obs_bytes) {
-    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_step<JW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
-    k_step<JW, ST><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, actions, out, obs_bytes);
+    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_step<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+    k_step<JW, ST, CL><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, actions, out, obs_bytes);
     return cudaGetLastError();
 }
-template <int JW, bool ST>
+template <int JW, bool ST, bool CL>
 cudaError_t launch_rollout(const BatchDev& bd, const LaunchCfg& lc, int policy, const uint8_t* tape, int64_t tape_stride,
                            int max_steps, int flags, jsl_rollout_out out) {
-    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
-    k_rollout<JW, ST><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, policy, tape, tape_stride, max_steps, flags, out);
+    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+    k_rollout<JW, ST, CL><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, policy, tape, tape_stride, max_steps, flags, out);
     return cudaGetLastError();
 }
-template <int JW, bool ST>
+template <int JW, bool ST, bool CL>
 cudaError_t launch_digest(const BatchDev& bd, const LaunchCfg& lc, int64_t env, int32_t* out, int cap, int32_t* n_out) {
-    k_digest<JW, ST><<<1, 32, lc.smem, lc.stream>>>(bd, env, out, cap, n_out);
+    k_digest<JW, ST, CL><<<1, 32, lc.smem, lc.stream>>>(bd, env, out, cap, n_out);
     return cudaGetLastError();
 }
-template <int JW, bool ST>
+template <int JW, bool ST, bool CL>
 int rollout_occupancy(int smem) {  // resident CTAs per SM for the persistent rollout grid
     int n = 0;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_rollout<JW, ST>, WARPS_PER_CTA * 32, smem) != cudaSuccess) return 8;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_rollout<JW, ST, CL>, WARPS_PER_CTA * 32, smem) != cudaSuccess) return 8;
     return n > 0 ? n : 1;
 }
 
@@ -313,20 +314,28 @@ JSL_DECLARE_JW(4)
 
 #define JSL_DEFINE_JW(N)                                                                                              \
     cudaError_t launch_reset_jw##N(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* m, jsl_step_out o, int ob) { \
-        return bd.tcur ? launch_reset<N, true>(bd, lc, m, o, ob) : launch_reset<N, false>(bd, lc, m, o, ob);                                                                     \
+        return bd.tcur ? launch_reset<N, true, false>(bd, lc, m, o, ob)                                           \
+               : bd.classic ? launch_reset<N, false, true>(bd, lc, m, o, ob)                                     \
+                            : launch_reset<N, false, false>(bd, lc, m, o, ob);                                                                     \
     }                                                                                                                 \
     cudaError_t launch_step_jw##N(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* a, jsl_step_out o, int ob) { \
-        return bd.tcur ? launch_step<N, true>(bd, lc, a, o, ob) : launch_step<N, false>(bd, lc, a, o, ob);                                                                      \
+        return bd.tcur ? launch_step<N, true, false>(bd, lc, a, o, ob)                                            \
+               : bd.classic ? launch_step<N, false, true>(bd, lc, a, o, ob)                                      \
+                            : launch_step<N, false, false>(bd, lc, a, o, ob);                                                                      \
     }                                                                                                                 \
     cudaError_t launch_rollout_jw##N(const BatchDev& bd, const LaunchCfg& lc, int p, const uint8_t* t, int64_t ts,    \
                                      int ms, int f, jsl_rollout_out o) {                                              \
-        return bd.tcur ? launch_rollout<N, true>(bd, lc, p, t, ts, ms, f, o) : launch_rollout<N, false>(bd, lc, p, t, ts, ms, f, o);                                                         \
+        return bd.tcur ? launch_rollout<N, true, false>(bd, lc, p, t, ts, ms, f, o)                               \
+               : bd.classic ? launch_rollout<N, false, true>(bd, lc, p, t, ts, ms, f, o)                         \
+                            : launch_rollout<N, false, false>(bd, lc, p, t, ts, ms, f, o);                                                         \
     }                                                                                                                 \
     cudaError_t launch_digest_jw##N(const BatchDev& bd, const LaunchCfg& lc, int64_t e, int32_t* o, int c, int32_t* n) { \
-        return bd.tcur ? launch_digest<N, true>(bd, lc, e, o, c, n) : launch_digest<N, false>(bd, lc, e, o, c, n);                                                                  \
+        return bd.tcur ? launch_digest<N, true, false>(bd, lc, e, o, c, n)                                        \
+               : bd.classic ? launch_digest<N, false, true>(bd, lc, e, o, c, n)                                  \
+                            : launch_digest<N, false, false>(bd, lc, e, o, c, n);                                                                  \
     }                                                                                                                 \
-    int rollout_occupancy_jw##N(int smem) { return rollout_occupancy<N, false>(smem); }                                      \
-    int state_bytes_jw##N() { return (int)sizeof(EnvS<N, false>); }                                                          \
+    int rollout_occupancy_jw##N(int smem) { return rollout_occupancy<N, false, false>(smem); }                                      \
+    int state_bytes_jw##N() { return (int)sizeof(EnvS<N, false, false>); }                                                          \
     int outs_bytes_jw##N() { return (int)sizeof(OutS<N>); }
 
 }  // namespace jsl
