@@ -802,7 +802,9 @@ JSL_D void machine_outage_to_idle(EnvS<JW, ST, CL>& s, Ctx& c, int m) {
 // process one machine transition (validate + handle); false = validation error
 template <int JW, bool ST, bool CL>
 JSL_D bool apply_machine(EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int job) {
-    if (!machine_valid(s, c, m, to, job)) return false;
+    // classic specialisation: every transition is created from the component's own current state (no
+    // TimeDependency hand-me-downs), so the state-graph check cannot fail
+    if (!CL && !machine_valid(s, c, m, to, job)) return false;
     if (JSL_UNLIKELY(c.raise)) return true;
     int from = s.m_state[m];
     if (from == JSL_M_IDLE) machine_idle_to_setup(s, c, m, job);
@@ -943,7 +945,7 @@ JSL_D void agv_transit_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
 // process one transport transition; false = validation error
 template <int JW, bool ST, bool CL>
 JSL_D bool apply_transport(EnvS<JW, ST, CL>& s, Ctx& c, int t, int to, int job) {
-    if (!transport_valid(s, t, to)) return false;
+    if (!CL && !transport_valid(s, t, to)) return false;
     int from = s.t_state[t];
     if (from == JSL_T_IDLE && to == JSL_T_WORKING) agv_idle_to_working(s, c, t, job);
     else if (from == JSL_T_PICKUP && to == JSL_T_WAITINGPICKUP) agv_to_waitingpickup(s, c, t, job);
@@ -1030,7 +1032,8 @@ JSL_D bool create_timed(EnvS<JW, ST, CL>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, 
             }
         } else if (st == JSL_T_TRANSIT) { kind = JSL_T_OUTAGE; job = s.t_carry[t]; }
         else if (st == JSL_T_OUTAGE) { kind = JSL_T_IDLE; job = NONE8; }
-        s.x_tkind[t] = (uint8_t)kind; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = (uint8_t)job;
+        s.x_tkind[t] = (uint8_t)kind; s.x_tjob[t] = (uint8_t)job;
+        if (!CL) s.x_tcomp[t] = (uint8_t)t;
         return true;
     });
     time_due = time_due || tm.any();
@@ -1094,7 +1097,8 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                 s.x_mkind[act.comp] = (uint8_t)act.new_state; s.x_mjob[act.comp] = (uint8_t)act.job;
                 mm.w[0] = 1u << act.comp;
             } else {
-                s.x_tkind[act.comp] = (uint8_t)act.new_state; s.x_tcomp[act.comp] = (uint8_t)act.comp;
+                s.x_tkind[act.comp] = (uint8_t)act.new_state;
+                if (!CL) s.x_tcomp[act.comp] = (uint8_t)act.comp;
                 s.x_tjob[act.comp] = (uint8_t)act.job;
                 tm.w[act.comp >> 5] = 1u << (act.comp & 31);
             }
@@ -1160,7 +1164,8 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                 while (idle.any() && (zr.any() || zi.any())) {
                     int t = idle.pop_first();
                     int j = zr.any() ? zr.pop_first() : zi.pop_first();
-                    s.x_tkind[t] = JSL_T_WORKING; s.x_tcomp[t] = (uint8_t)t; s.x_tjob[t] = (uint8_t)j;
+                    s.x_tkind[t] = JSL_T_WORKING; s.x_tjob[t] = (uint8_t)j;
+                    if (!CL) s.x_tcomp[t] = (uint8_t)t;
                     tele.w[t >> 5] |= 1u << (t & 31);
                 }
             }
@@ -1178,7 +1183,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
             Mask<JW> cur = ph == 0 ? tm : tele;
             while (cur.any()) {
                 int t = cur.pop_first();
-                bool ok = apply_transport(s, c, s.x_tcomp[t], s.x_tkind[t], s.x_tjob[t]);
+                bool ok = apply_transport(s, c, CL ? t : (int)s.x_tcomp[t], s.x_tkind[t], s.x_tjob[t]);
                 if (JSL_UNLIKELY(c.raise)) return true;
                 if (JSL_UNLIKELY(!ok)) return false;
             }

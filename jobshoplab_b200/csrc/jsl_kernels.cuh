@@ -16,14 +16,14 @@
 namespace jsl {
 
 #ifndef JSL_WARPS_PER_CTA
-#define JSL_WARPS_PER_CTA 4
+#define JSL_WARPS_PER_CTA 2
 #endif
 constexpr int WARPS_PER_CTA = JSL_WARPS_PER_CTA;
 #ifndef JSL_ROLLOUT_MIN_CTAS
-#define JSL_ROLLOUT_MIN_CTAS 16  // resident CTAs per SM the rollout kernel is register-budgeted for
+#define JSL_ROLLOUT_MIN_CTAS 32  // resident CTAs per SM the rollout kernel is register-budgeted for
 #endif
 #ifndef JSL_STEP_MIN_CTAS
-#define JSL_STEP_MIN_CTAS 10
+#define JSL_STEP_MIN_CTAS 24
 #endif
 
 struct BatchDev {
