@@ -1150,15 +1150,20 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                     if (tt == JSL_NO_TIME) { bad = true; return false; }
                     return tt == 0;
                 };
-                Mask<JW> zr = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.lr.test(j) && zero_travel(j, bd); });
-                Mask<JW> zi = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.li.test(j) && zero_travel(j, bd); });
-                if (!CL && (I.travel || ST || I.out_buf < 0)) {
-                    Mask<JW> badm = wp_ballot<JW>(I.J, [&](int j) {
-                        bool bd = false;
-                        if (p.lr.test(j) || p.li.test(j)) zero_travel(j, bd);
-                        return bd;
-                    });
-                    if (badm.any()) { c.raise = JSL_ST_OTHER_INVALID; return true; }
+                Mask<JW> zr, zi;
+                if (CL) {  // every travel time is zero: all lonely jobs qualify
+                    zr = p.lr; zi = p.li;
+                } else {
+                    zr = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.lr.test(j) && zero_travel(j, bd); });
+                    zi = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.li.test(j) && zero_travel(j, bd); });
+                    if (I.travel || ST || I.out_buf < 0) {
+                        Mask<JW> badm = wp_ballot<JW>(I.J, [&](int j) {
+                            bool bd = false;
+                            if (p.lr.test(j) || p.li.test(j)) zero_travel(j, bd);
+                            return bd;
+                        });
+                        if (badm.any()) { c.raise = JSL_ST_OTHER_INVALID; return true; }
+                    }
                 }
                 Mask<JW> idle = p.idle;
                 while (idle.any() && (zr.any() || zi.any())) {
