@@ -802,9 +802,11 @@ JSL_D void machine_outage_to_idle(EnvS<JW, ST, CL>& s, Ctx& c, int m) {
 // process one machine transition (validate + handle); false = validation error
 template <int JW, bool ST, bool CL>
 JSL_D bool apply_machine(EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int job) {
-    // classic specialisation: every transition is created from the component's own current state (no
-    // TimeDependency hand-me-downs), so the state-graph check cannot fail
-    if (!CL && !machine_valid(s, c, m, to, job)) return false;
+    // every machine transition is created from that machine's own current state (timed) or from the candidate
+    // masks of the unchanged state (action); only the TimeDependency hand-me-downs of non-FLEX postbuffers
+    // (handler.py:632) can put two transitions of one component into a batch, so the state-graph check
+    // (validate.py:30-82) can only fail there
+    if (!CL && !c.I->flex_post && !machine_valid(s, c, m, to, job)) return false;
     if (JSL_UNLIKELY(c.raise)) return true;
     int from = s.m_state[m];
     if (from == JSL_M_IDLE) machine_idle_to_setup(s, c, m, job);
@@ -945,7 +947,7 @@ JSL_D void agv_transit_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
 // process one transport transition; false = validation error
 template <int JW, bool ST, bool CL>
 JSL_D bool apply_transport(EnvS<JW, ST, CL>& s, Ctx& c, int t, int to, int job) {
-    if (!CL && !transport_valid(s, t, to)) return false;
+    if (!CL && !c.I->flex_post && !transport_valid(s, t, to)) return false;
     int from = s.t_state[t];
     if (from == JSL_T_IDLE && to == JSL_T_WORKING) agv_idle_to_working(s, c, t, job);
     else if (from == JSL_T_PICKUP && to == JSL_T_WAITINGPICKUP) agv_to_waitingpickup(s, c, t, job);
