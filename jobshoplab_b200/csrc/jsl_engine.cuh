@@ -1456,6 +1456,8 @@ JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* ou
         f[1] = tr[0]; f[2] = tr[1]; f[3] = tr[2];
         for (int i = 16 + 4 * J + 4 * M + 2 * J + M + J * M; i < total; i++) out[i] = 0;
     });
+    // rows of job_executed_on_machine are written as 32-bit words when they are word aligned
+    const bool word_rows = (M & 3) == 0 && (((16 + 4 * J + 4 * M + 2 * J + M) & 3) == 0) && M <= 32;
     wp_for<JW>(J, [&](int r) {
         int j = I.job_lex[r];
         jrun[r] = (int8_t)s.j_proc[j];
@@ -1463,10 +1465,18 @@ JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* ou
         // numeric index into the lexicographically ordered tuple (observations.py:437-441)
         avail[r] = (int8_t)(any_idle && !s.j_proc[I.job_lex[j]]);
         jprog[r] = s.j_k[r];
-        int8_t* row = exec + r * M;
-        for (int m = 0; m < M; m++) row[m] = 0;
         int o0 = I.job_op_start[j];
-        for (int k = 0; k < s.j_k[j]; k++) row[c.aux->op_mt[o0 + k] & 0xffff] = 1;
+        uint32_t mask = 0;
+        const int kd = s.j_k[j];
+        for (int k = 0; k < kd; k++) mask |= 1u << (c.aux->op_mt[o0 + k] & 31);
+        int8_t* row = exec + r * M;
+        if (word_rows) {
+            uint32_t* rw = (uint32_t*)row;
+            for (int q = 0; q < M / 4; q++) rw[q] = (((mask >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
+        } else {
+            for (int m = 0; m < M; m++) row[m] = 0;
+            for (int k = 0; k < kd; k++) row[c.aux->op_mt[o0 + k] & 0xffff] = 1;
+        }
     });
     wp_for<1>(M, [&](int r) {
         int m = I.mach_lex[r];

@@ -45,6 +45,23 @@ struct BatchDev {
     const int32_t* start_seeds;  // [B][n_tobj] or nullptr
 };
 
+// fixed-size variant: all 128-bit loads of a lane are issued before the first store (latency overlap)
+template <int BYTES>
+__device__ __forceinline__ void copy_fixed(void* dst, const void* src) {
+    constexpr int N = BYTES / 16, K = (N + 31) / 32;
+    const int4* s = (const int4*)src;
+    int4* d = (int4*)dst;
+    int4 v[K];
+    const int lane = JSL_LANE;
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        if (lane + 32 * k < N) v[k] = s[lane + 32 * k];
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        if (lane + 32 * k < N) d[lane + 32 * k] = v[k];
+    __syncwarp();
+}
+
 __device__ __forceinline__ void copy_in(void* dst, const void* src, int bytes) {
     const int4* s = (const int4*)src;
     int4* d = (int4*)dst;
@@ -150,7 +167,7 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
     uint8_t* g_state = bd.state + env * (int64_t)bd.state_stride;
     uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
-    copy_in(&s, g_state, bd.state_stride);
+    copy_fixed<(int)sizeof(EnvS<JW, ST, CL>)>(&s, g_state);
     if (g_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
     Ctx c;
     make_ctx(c, bd, env, slot);
@@ -176,7 +193,7 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     }
     write_step_out(s, c, out, env, r, obs_bytes);
     __syncwarp();
-    copy_in(g_state, &s, bd.state_stride);
+    copy_fixed<(int)sizeof(EnvS<JW, ST, CL>)>(g_state, &s);
     if (g_outs) copy_in(g_outs, outs_sm, bd.outs_stride);
 }
 
