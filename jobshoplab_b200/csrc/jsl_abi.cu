@@ -217,6 +217,13 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
             I.sample_depth = t->tobj.sample_depth;
         }
     }
+    {
+        std::vector<float> tc(t->M + t->T), tj(t->J + 1);
+        for (int i = 0; i < t->M + t->T; i++) tc[i] = (float)((double)i / (double)(t->M + t->T));
+        for (int i = 0; i <= t->J; i++) tj[i] = (float)((double)i / (double)t->J);
+        rc |= upload(b, tc, &I.tr_comp);
+        rc |= upload(b, tj, &I.tr_job);
+    }
     rc |= upload(b, jl, &I.job_lex);
     rc |= upload(b, ml, &I.mach_lex);
     if (rc) { jsl_batch_destroy(b); return nullptr; }

@@ -88,6 +88,8 @@ struct InstDev {
     const int32_t* m_out_dur;       // [n]
     const int32_t* t_out_freq;      // [n_t_out]
     const int32_t* t_out_dur;       // [n_t_out]
+    const float* tr_comp;           // [M+T] float32(comp_idx / (M+T))  (observations.py:541)
+    const float* tr_job;            // [J+1] float32(job / J), [J] = "no job"  (:536-539)
     const uint8_t* job_lex;         // [J] r-th job in string-id order
     const uint8_t* mach_lex;        // [M]
     int n_t_out;
@@ -1429,8 +1431,8 @@ JSL_D void cand_floats(const EnvS<JW, ST, CL>& s, const Ctx& c, float* tr) {
     if (!s.obs_done && s.n_possible - s.skip > 0) {
         Trans cand = current_candidate(s, c);
         int comp_idx = cand.kind == 0 ? cand.comp : I.M + cand.comp;
-        tr[0] = (float)((double)comp_idx / (double)(I.M + I.T));
-        tr[1] = (float)((double)cand.job / (double)I.J);
+        tr[0] = I.tr_comp[comp_idx];  // float32 of the float64 quotient, tabulated on the host
+        tr[1] = I.tr_job[cand.job];
         tr[2] = cand.kind == 0 ? 0.0f : (float)0.33;
     } else {
         tr[0] = tr[1] = tr[2] = 1.0f;

@@ -72,7 +72,7 @@ __device__ __forceinline__ void copy_in(void* dst, const void* src, int bytes) {
 // per-warp shared-memory slot: EnvS | OutS (optional) | EnvAux
 __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env, uint8_t* slot) {
     const InstDev& I = bd.inst;
-    int64_t v = env % I.n_inst;
+    const int64_t v = I.n_inst == 1 ? 0 : (env < I.n_inst ? env : env % I.n_inst);
     EnvAux* aux = (EnvAux*)(slot + bd.state_stride + bd.outs_stride);
     c.I = &bd.inst;
     c.C = &bd.cfg;

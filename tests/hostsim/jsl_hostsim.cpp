@@ -26,6 +26,7 @@ struct Sim {
         travel, m_out_start, m_out_freq, m_out_dur, t_out_freq, t_out_dur;
     std::vector<uint8_t> pre_type, post_type, sbuf_type, sbuf_role, agv_init_place, job_lex, mach_lex;
     std::vector<uint16_t> job_init_buf;
+    std::vector<float> tr_comp, tr_job;
     std::vector<int32_t> op_log;
     std::vector<uint8_t> state, backup, outs, outs_backup;
     int state_bytes, outs_bytes;
@@ -174,6 +175,10 @@ void* jsh_create(const jsl_instance_desc* d, const jsl_env_cfg* cfg, uint64_t se
     I.agv_init_place = s->agv_init_place.data(); I.job_init_buf = s->job_init_buf.data();
     I.m_out_start = s->m_out_start.data(); I.m_out_freq = s->m_out_freq.data(); I.m_out_dur = s->m_out_dur.data();
     I.t_out_freq = s->t_out_freq.data(); I.t_out_dur = s->t_out_dur.data();
+    s->tr_comp.resize(I.M + I.T); s->tr_job.resize(I.J + 1);
+    for (int i = 0; i < I.M + I.T; i++) s->tr_comp[i] = (float)((double)i / (double)(I.M + I.T));
+    for (int i = 0; i <= I.J; i++) s->tr_job[i] = (float)((double)i / (double)I.J);
+    I.tr_comp = s->tr_comp.data(); I.tr_job = s->tr_job.data();
     I.job_lex = s->job_lex.data(); I.mach_lex = s->mach_lex.data();
     I.n_t_out = d->n_t_outages; I.has_m_out = n_mo > 0; I.has_t_out = I.n_t_out > 0;
     I.out_buf = -1;
