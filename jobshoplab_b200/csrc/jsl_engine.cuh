@@ -8,7 +8,14 @@
 //     wp_for     -- independent per-element work + __syncwarp()
 // Ordered buffers (FIFO/LIFO stores of the reference) are not stored as lists: every job carries the
 // buffer it is in and a monotone sequence stamp; queue head/tail, fill level and position tests are
-// ballots / min-reductions over (loc, seq).
+// ballots / min-reductions over (loc, seq).  possible_transitions is four bit masks (cached in the state),
+// element k is recovered arithmetically in the reference's order.
+//
+// Template parameters of everything below: JW = lane words (ceil(max(J,T)/32)), ST = the instance has
+// stochastic time objects, CL = "classic" specialisation (all buffers FLEX and unbounded, zero travel and
+// setup times, no outages): capacity / position / TimeDependency / outage / lookup code is compiled out.
+// The hot loop has to stay inside the instruction cache: one call site per phase (sm_step, run_env_op),
+// rare paths out of line (JSL_DN), rarely used per-env constants in EnvAux (shared memory).
 //
 // The header also compiles as plain C++ (JSL_HOST_SIM) with the primitives written as loops.  That
 // build exists only for CPU-side debugging of this very source (tests/hostsim) -- the product never
@@ -19,7 +26,7 @@
 //   validate.py:30-161, core/transitions.py:82-186, state_machine/time_machines.py:61-221,
 //   utils/state_machine_utils/{possible_transition_utils,buffer_type_utils,outage_utils}.py,
 //   state_machine/middleware/middleware.py:264-443, env/factories/{actions,observations,rewards}.py,
-//   env/env.py:427-454, utils/dipatching_benchmark.py:17-67.
+//   env/env.py:427-454, utils/dipatching_benchmark.py:17-67, types/stochasticy_models.py:6-121.
 #pragma once
 #include <stdint.h>
 
@@ -356,7 +363,6 @@ JSL_D int place_of_buf(const InstDev& I, int b) {
     return -1;
 }
 JSL_D int job_nops(const InstDev& I, int j) { return I.job_op_start[j + 1] - I.job_op_start[j]; }
-JSL_D int travel_time(const InstDev& I, int a, int b) { return I.travel ? I.travel[a * I.NP + b] : 0; }
 
 // ------------------------------------------------------------------------------------ buffers as (loc, seq)
 template <int JW, bool ST, bool CL>
@@ -666,7 +672,7 @@ JSL_DN void stoch_init(const InstDev* I, int32_t* tcur, uint16_t* tseed, const i
 }
 
 // ------------------------------------------------------------------------------------ outages
-// outage_utils.py:20-131: sample, occupied time; static frequencies/durations (stochastic: TODO tape)
+// outage_utils.py:20-131: sample the outages of one component, return the occupied time
 template <bool ST>
 JSL_D int sample_outages(Ctx& c, int32_t& draw_ctr, int now, int n, const int32_t* freq, const int32_t* dur,
                          int freq_obj, int dur_obj, uint8_t* active, int32_t* a, int32_t* b) {
@@ -819,7 +825,6 @@ JSL_D bool apply_machine(EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int job) {
 }
 
 // ------------------------------------------------------------------------------------ transport handlers
-JSL_D int t_general(int st) { return st == JSL_T_IDLE ? 0 : st == JSL_T_OUTAGE ? 2 : 1; }
 // validate.py:85-118 + transitions.py:82-107,161-186
 template <int JW, bool ST, bool CL>
 JSL_D bool transport_valid(const EnvS<JW, ST, CL>& s, int t, int to) {

@@ -102,6 +102,19 @@ class BatchedJobShopLabEnv:
                 out.truncated.copy_(final["truncated"]); out.makespan.copy_(final["makespan"])
         return self.batch.unpack_obs(out.obs), out.reward, out.terminated, out.truncated, out
 
+    # gymnasium.vector / SB3 VecEnv style split step: the launch is asynchronous on the
+    # current CUDA stream anyway, step_wait only hands out the views
+    def step_async(self, actions):
+        self._pending = self.step(actions)
+
+    def step_wait(self):
+        out, self._pending = self._pending, None
+        return out
+
+    @property
+    def single_action_space(self):
+        return self.action_space
+
     def rollout(self, policy="random", **kw):
         return self.batch.rollout(policy, **kw)
 

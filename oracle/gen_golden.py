@@ -309,7 +309,13 @@ def g_tassel():
     return out
 
 
-GROUPS = {"tassel": g_tassel, "classic": g_classic, "solutions": g_solutions, "transport": g_transport, "buffers": g_buffers,
+def g_big():
+    """100 jobs x 20 machines (ta71): exercises the 4-lane-word kernels (JW = 4)."""
+    return [dict(name="ta71/fifo", kind="spec", src=spec("ta71"), policy="fifo"),
+            dict(name="ta71/random0", kind="spec", src=spec("ta71"), policy="random", seed=0, env_idx=5, max_steps=700)]
+
+
+GROUPS = {"big": g_big, "tassel": g_tassel, "classic": g_classic, "solutions": g_solutions, "transport": g_transport, "buffers": g_buffers,
           "features": g_features, "truncation": g_truncation, "oparray": g_oparray}
 
 

@@ -10,7 +10,7 @@ import numpy as np
 from jobshoplab_b200 import lowered as L
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-GROUPS = ("classic", "solutions", "transport", "buffers", "features", "truncation", "oparray", "tassel")
+GROUPS = ("classic", "solutions", "transport", "buffers", "features", "truncation", "oparray", "tassel", "big")
 
 _P = np.uint64(1099511628211)
 _H0 = np.uint64(1469598103934665603)
@@ -87,6 +87,11 @@ class Scenario:
         elif of == "TasselJsspObservation":
             c["obs_kind"] = 3
         return c
+
+    @property
+    def cut(self) -> bool:
+        """the harness stopped the episode at max_steps before it was done"""
+        return self.meta.get("max_steps") is not None and self.meta["n_steps"] >= self.meta["max_steps"]
 
     @property
     def kind(self):

@@ -40,7 +40,7 @@ def replay(sc):
         assert e.noop_count == sc.meta["no_op_count"]
 
 
-@pytest.mark.parametrize("group", ["classic", "solutions", "transport", "buffers", "features", "truncation", "oparray", "tassel"])
+@pytest.mark.parametrize("group", ["classic", "solutions", "transport", "buffers", "features", "truncation", "oparray", "tassel", "big"])
 def test_engine_source_matches_reference_traces(group):
     names = PICK.get(group)
     if names is None:

@@ -93,6 +93,9 @@ def test_batched_env_auto_reset_and_views():
         assert (mk == 68).all()  # ft06 always-accept makespan, BASELINE.md 2a
     assert finished == 3 * B
     assert int(out.status.max()) <= 1
+    env.step_async(acts)
+    obs2, rew2, term2, trunc2, _ = env.step_wait()
+    assert obs2["job_progression"].shape == (B, 6) and env.single_action_space.n == 2
     r = env.rollout("mwkr", reset_first=True)
     assert (r.makespan == 83).all() and (r.n_steps == 46).all()
     assert env.state(5).state.time.time == 83

@@ -79,8 +79,6 @@ def test_no_cpu_fallback():
     sc = G.Scenario("classic", "ft06/fifo")
     with pytest.raises(EngineUnavailable):
         engine.Batch(sc.lowered, 4)
-    src = "".join(p.read_text() for p in (ROOT / "jobshoplab_b200").glob("*.py"))
-    assert "oracle" not in src.replace("oracle/", "").lower() or True
     for p in (ROOT / "jobshoplab_b200").glob("*.py"):
         text = p.read_text()
         assert "import oracle" not in text and "from oracle" not in text and "hostsim" not in text, p
