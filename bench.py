@@ -201,6 +201,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: library chatter (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -344,7 +348,10 @@ def main():
                           f"threads, {dt:.1f} s",
                 "makespans_equal_gpu": bool(gpu_mk is not None and np.array_equal(gpu_mk, r["makespan"])),
             }
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
