@@ -61,6 +61,7 @@ namespace jsl {
 
 #ifdef JSL_HOST_SIM
 static long g_invariant_checks = 0, g_invariant_violations = 0;  // CPU debug build only
+static long g_fast_start = 0, g_fast_complete = 0, g_general_batches = 0;
 #endif
 
 constexpr int NONE8 = 0xff;
@@ -1074,6 +1075,125 @@ JSL_D bool create_timed(EnvS<JW, ST, CL>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, 
     return mm.any() || tm.any();
 }
 
+// ------------------------------------------------------------------------------------ classic fast paths
+// In classic instances (CL: FLEX unbounded buffers, zero setup / travel / outage times) an operation's start
+// and its completion each unroll into a fixed chain of same-time transitions, one per loop iteration of
+// state.py:154-295.  The two functions below apply such a chain in one go when -- and only when -- the batch
+// has exactly the chain's shape; every other situation takes the general loop.  Each is the composition of the
+// handlers named in its comment, so the state after it equals the state after the iterations it replaces.
+
+// Start of an operation by the agent: machine IDLE->SETUP (stage 0), SETUP->WORKING plus the teleport
+// IDLE->PICKUP of the first idle AGV for the now running job (first batch), PICKUP->WAITINGPICKUP (second
+// batch).  Preconditions: no lonely job in the quiet state the step starts from (so the started job is the only
+// teleport candidate) and a positive duration (else WORKING->OUTAGE is due in the second batch).  Leaves the
+// candidate masks of the resulting state in s.c_*.
+template <int JW, bool ST, bool CL>
+JSL_D bool classic_start(EnvS<JW, ST, CL>& s, Ctx& c, const Trans& act) {
+    const InstDev& I = *c.I;
+    Poss<JW> p = cached_poss(s);
+    if (p.lr.any() || p.li.any()) return false;
+    const int m = act.comp, j = act.job;
+    const int k = s.j_k[j];
+    const int o = I.job_op_start[j] + k;
+    const int dur = c.aux->op_dur[o];
+    if (dur <= 0 || I.out_buf < 0) return false;
+    if (s.j_loc[j] != 3 * m || s.m_job[m] != NONE8 || s.m_state[m] != JSL_M_IDLE) return false;
+    const int now = c.now, end = now + dur;
+    // machine_idle_to_setup + machine_setup_to_working
+    s.j_proc[j] = 1; s.j_start[j] = now; s.j_end[j] = end;
+    s.j_loc[j] = (uint16_t)(3 * m + 2);
+    s.m_job[m] = (uint8_t)j;
+    s.m_state[m] = JSL_M_WORKING; s.m_occ[m] = end; s.m_tool[m] = (uint8_t)((c.aux->op_mt[o] >> 16) & 0xffff);
+    if (c.C->allow_early_transport != 0) {
+        const int a = p.idle.first();
+        if (a >= 0) {  // agv_idle_to_working + agv_to_waitingpickup (waits for the processing op's end)
+            int target = (k + 1 < job_nops(I, j)) ? (c.aux->op_mt[o + 1] & 0xffff) : I.M + (I.out_buf - 3 * I.M - I.T);
+            s.t_occkind[a] = OCC_TIME; s.t_occ[a] = end;
+            s.t_lockind[a] = 1; s.t_loc1[a] = (uint16_t)(3 * m + 2); s.t_loc2[a] = (uint8_t)target;
+            s.t_state[a] = JSL_T_WAITINGPICKUP;
+            s.t_job[a] = (uint8_t)j;
+            s.j_agv[j] = (uint8_t)a;
+            p.idle.w[a >> 5] &= ~(1u << (a & 31));
+        } else {
+            p.lr.w[j >> 5] |= 1u << (j & 31);
+        }
+    }
+    // machine m is busy now: nobody waiting in front of it can start
+    const Mask<JW> at_m = wp_ballot<JW>(I.J, [&](int q) { return s.j_mach[q] == m; });
+#pragma unroll
+    for (int w = 0; w < JW; w++) p.p1.w[w] &= ~at_m.w[w];
+    store_poss(s, p, false);
+    JSL_SYNCWARP();
+    return true;
+}
+
+// Completion of operations: the batch holds only WORKING->OUTAGE of machines and WAITINGPICKUP->WAITINGPICKUP
+// of the AGVs waiting for exactly those jobs.  The chain is OUTAGE->IDLE (job into the postbuffer) |
+// WAITINGPICKUP->TRANSIT | TRANSIT->OUTAGE (job into the next prebuffer / output buffer) | OUTAGE->IDLE, all at
+// `now`; buffer stamps keep the reference's order (machines by index, then AGVs by index).
+template <int JW, bool ST, bool CL>
+JSL_D bool classic_complete(EnvS<JW, ST, CL>& s, Ctx& c, const Mask<1>& mm, const Mask<JW>& tm) {
+    const InstDev& I = *c.I;
+    const bool bad_m = wp_ballot<1>(I.M, [&](int m) {
+        if (!mm.test(m)) return false;
+        const int j = s.m_job[m];
+        return s.x_mkind[m] != JSL_M_OUTAGE || j == NONE8 || !s.j_proc[j];
+    }).any();
+    if (bad_m) return false;
+    const bool bad_t = wp_ballot<JW>(I.T, [&](int t) {
+        if (!tm.test(t)) return false;
+        const int j = s.t_job[t];
+        if (s.x_tkind[t] != JSL_T_WAITINGPICKUP || s.t_state[t] != JSL_T_WAITINGPICKUP || j == NONE8 ||
+            s.t_lockind[t] != 1 || s.t_carry[t] != NONE8)
+            return true;
+        const int b = s.j_loc[j];
+        if (b >= 3 * I.M || (b % 3) != 2) return true;
+        return !mm.test(b / 3) || s.m_job[b / 3] != j;
+    }).any();
+    if (bad_t) return false;
+    const int now = c.now;
+    const int seq0 = s.seq_ctr, nm = mm.count();
+    JSL_SYNCWARP();
+    // machine_working_to_outage + machine_outage_to_idle
+    wp_for<1>(I.M, [&](int m) {
+        if (!mm.test(m)) return;
+        const int j = s.m_job[m];
+        const int k = s.j_k[j];
+        const int o = I.job_op_start[j] + k;
+        if (c.aux->op_log) { c.aux->op_log[2 * o] = s.j_start[j]; c.aux->op_log[2 * o + 1] = now; }
+        s.j_end[j] = now;
+        s.j_k[j] = (uint8_t)(k + 1);
+        s.j_proc[j] = 0;
+        s.j_mach[j] = (k + 1 < job_nops(I, j)) ? (uint8_t)(c.aux->op_mt[o + 1] & 0xffff) : (uint8_t)NONE8;
+        s.m_done[m] = (uint16_t)(s.m_done[m] + 1);
+        s.m_job[m] = NONE8;
+        s.j_loc[j] = (uint16_t)(3 * m + 1);
+        s.j_seq[j] = (uint32_t)(seq0 + JSL_POPC(mm.w[0] & ((1u << m) - 1u)));
+        s.m_state[m] = JSL_M_IDLE; s.m_occ[m] = now;
+    });
+    if (now > s.max_done_end) s.max_done_end = now;
+    // agv_to_waitingpickup (x2) + agv_to_transit + agv_transit_to_outage + OUTAGE->IDLE
+    wp_for<JW>(I.T, [&](int t) {
+        if (!tm.test(t)) return;
+        int rank = JSL_POPC(tm.w[t >> 5] & ((1u << (t & 31)) - 1u));
+#pragma unroll
+        for (int w = 0; w < JW; w++)
+            if (w < (t >> 5)) rank += JSL_POPC(tm.w[w]);
+        const int j = s.t_job[t];
+        const int dest = s.t_loc2[t];
+        s.j_loc[j] = (uint16_t)(dest < I.M ? 3 * dest : 3 * I.M + I.T + (dest - I.M));
+        s.j_seq[j] = (uint32_t)(seq0 + nm + rank);
+        s.j_agv[j] = NONE8;
+        s.t_state[t] = JSL_T_IDLE;
+        s.t_occkind[t] = OCC_TIME; s.t_occ[t] = now;
+        s.t_lockind[t] = 0; s.t_loc0[t] = (uint8_t)dest;
+        s.t_job[t] = NONE8;
+    });
+    s.seq_ctr = seq0 + nm + tm.count();
+    JSL_SYNCWARP();
+    return true;
+}
+
 // ------------------------------------------------------------------------------------ state.step
 constexpr int TM_JUMP = 0, TM_FORCE = 1;
 
@@ -1098,7 +1218,17 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
     bool action_stage = has_action;
     bool first = true;
     bool evaluated = false;  // the time machine already ran for the current state
+    // a step starts from the quiet state the previous call ended in (its loop only exits when nothing is due at
+    // `now`), and the classic fast paths end in one: no timed transition can exist in the next batch
+    bool known_quiet = !has_action && time_machine == TM_FORCE;  // (a reset starts from the initial state instead)
+    bool poss_fresh = false;  // s.c_* already describe the current state
     int guard = 0;
+    if (CL && has_action && act.kind == 0 && classic_start(s, c, act)) {
+        action_stage = false; first = false; known_quiet = true; poss_fresh = true;
+#ifdef JSL_HOST_SIM
+        g_fast_start++;
+#endif
+    }
 #pragma unroll 1
     for (;;) {
         if (action_stage) {
@@ -1113,15 +1243,29 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
             }
         } else {
             bool time_due = false;
-            const bool have = create_timed(s, c, mm, tm, time_due);
-            if (JSL_UNLIKELY(c.raise)) return true;
+            bool have = false;
+            if (!known_quiet) {
+                have = create_timed(s, c, mm, tm, time_due);
+                if (JSL_UNLIKELY(c.raise)) return true;
+            }
+#ifdef JSL_HOST_SIM
+            else {  // the skipped scan must have found nothing
+                Mask<1> qm; Mask<JW> qt; bool qd = false;
+                int save = c.raise;
+                g_invariant_checks++;
+                if (create_timed(s, c, qm, qt, qd) || c.raise != save) g_invariant_violations++;
+                c.raise = save;
+            }
+#endif
+            known_quiet = false;
             // Time machine (time_machines.py:61-130): `now` stays while something is possible, else it jumps to
             // min(processing-op ends, busy-AGV times).  When an occupied_till-driven transition is due at `now`
             // that minimum IS `now` (nothing pending can lie in the past: every due component fires in the very
             // next batch), so the candidate scan is only needed in quiet batches and in the first one.
             if (!evaluated && (first || !time_due)) {
-                const Poss<JW> p = compute_poss(s, c);
-                store_poss(s, p, false);
+                if (!poss_fresh) store_poss(s, compute_poss(s, c), false);
+                poss_fresh = false;
+                const Poss<JW> p = cached_poss(s);
                 const bool anyp = p.p1.any() || (p.idle.any() && (p.lr.any() || p.li.any()));
                 if ((first && time_machine == TM_FORCE) || !anyp) {
                     const int t2 = force_jump_to_event(s, c);
@@ -1184,7 +1328,21 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                 }
             }
             if (!have && !tele.any()) break;
+            if (CL && !tele.any() && classic_complete(s, c, mm, tm)) {
+                mm.w[0] = 0;
+#pragma unroll
+                for (int w = 0; w < JW; w++) tm.w[w] = 0;
+                first = false; known_quiet = true;
+#ifdef JSL_HOST_SIM
+                g_fast_complete++;
+#endif
+                if (++guard > 100000) { c.raise = JSL_ST_OTHER_INVALID; return true; }
+                continue;
+            }
         }
+#ifdef JSL_HOST_SIM
+        if (CL) g_general_batches++;
+#endif
         // apply: machines, then timed transports, then teleports -- in creation order
         while (mm.any()) {
             int m = mm.pop_first();

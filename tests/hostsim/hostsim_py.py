@@ -62,6 +62,13 @@ def invariants():
     return int(o[0]), int(o[1])
 
 
+def fast_paths():
+    """(classic_start hits, classic_complete hits, batches of classic instances that took the general loop)."""
+    o = (C.c_long * 3)()
+    lib().jsh_fast_paths(o)
+    return int(o[0]), int(o[1]), int(o[2])
+
+
 class HostSimEnv:
     def __init__(self, lowered, seed=0, **cfg):
         self.L = lib()

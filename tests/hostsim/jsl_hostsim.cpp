@@ -214,6 +214,7 @@ void* jsh_create(const jsl_instance_desc* d, const jsl_env_cfg* cfg, uint64_t se
 void jsh_destroy(void* h) { delete (Sim*)h; }
 void jsh_set_tape(void* h, const int32_t* t, int n) { Sim* s = (Sim*)h; s->tape.assign(t, t + n); }
 void jsh_invariants(long* o) { o[0] = g_invariant_checks; o[1] = g_invariant_violations; }
+void jsh_fast_paths(long* o) { o[0] = g_fast_start; o[1] = g_fast_complete; o[2] = g_general_batches; }
 void jsh_set_env_id(void* h, uint64_t id) { ((Sim*)h)->env_id = id; }
 void jsh_set_start_seeds(void* h, const int32_t* t, int n) { Sim* s = (Sim*)h; s->start_seeds.assign(t, t + n); }
 int jsh_draw(uint64_t seed, uint64_t env, uint32_t n, int kind, int base, float param) { return draw_time(seed, env, n, kind, base, param); }
