@@ -256,7 +256,7 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     int os = b->JW == 1 ? outs_bytes_jw1() : b->JW == 2 ? outs_bytes_jw2() : outs_bytes_jw4();
     b->bd.state_stride = ss;
     b->bd.outs_stride = (I.has_m_out || I.has_t_out) ? os : 0;
-    b->smem_per_warp = b->bd.state_stride + b->bd.outs_stride + (int)sizeof(EnvAux);
+    b->smem_per_warp = slot_bytes(b->JW, b->bd.classic != 0);
     void* p = nullptr;
     if (cudaMalloc(&p, (size_t)B * ss) != cudaSuccess) { set_err("cudaMalloc(state) failed"); jsl_batch_destroy(b); return nullptr; }
     b->allocs.push_back(p); b->bd.state = (uint8_t*)p;

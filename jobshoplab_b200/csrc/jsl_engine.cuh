@@ -199,7 +199,9 @@ struct alignas(16) EnvAux {
     double neg_inv_n;            // -1.0 / N: the dense reward of a penalised step (rewards.py:135-138)
     int32_t tape_len;
     int32_t lower_bound, max_allowed_time;
-    int32_t pad;
+    uint32_t act_block;          // RANDOM policy: 1 + index of the 32-step block whose actions are in act_bits (0 = none)
+    uint32_t act_bits;
+    int32_t pad[3];
 };
 
 // per-call context: the few uniform values the hot loop keeps in registers
@@ -1551,7 +1553,20 @@ JSL_D uint32_t philox_bit(uint64_t seed, uint64_t env_idx, uint32_t step) {
 template <int JW, bool ST, bool CL>
 JSL_D int policy_action(const EnvS<JW, ST, CL>& s, const Ctx& c, int policy) {
     const InstDev& I = *c.I;
-    if (policy == JSL_POLICY_RANDOM) return (int)philox_bit(c.aux->seed, c.aux->env_id, (uint32_t)s.n_steps);
+    if (policy == JSL_POLICY_RANDOM) {
+        // the action of step n is philox_bit(seed, env, n): lane l draws the one of step 32*block + l, so the
+        // ten Philox rounds run once per 32 steps
+        const uint32_t step = (uint32_t)s.n_steps, block = (step >> 5) + 1u;
+        if (c.aux->act_block != block) {
+            const uint64_t seed = c.aux->seed, env_id = c.aux->env_id;
+            const Mask<1> bits = wp_ballot<1>(32, [&](int l) { return philox_bit(seed, env_id, (step & ~31u) + (uint32_t)l) != 0u; });
+            JSL_SYNCWARP();
+            c.aux->act_bits = bits.w[0];
+            c.aux->act_block = block;
+            JSL_SYNCWARP();
+        }
+        return (int)((c.aux->act_bits >> (step & 31u)) & 1u);
+    }
     if (policy == JSL_POLICY_FIFO || s.n_possible - s.skip <= 0) return 1;
     Trans cand = current_candidate(s, c);
     if (cand.kind == 1) return 1;

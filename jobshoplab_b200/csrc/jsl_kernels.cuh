@@ -45,6 +45,10 @@ struct BatchDev {
     const int32_t* start_seeds;  // [B][n_tobj] or nullptr
 };
 
+// index of the warp inside its CTA, obtained through a warp reduction so that the compiler knows it (and
+// every shared-memory address derived from it) to be warp-uniform
+__device__ __forceinline__ int warp_index() { return (int)__reduce_min_sync(0xffffffffu, threadIdx.x >> 5); }
+
 // fixed-size variant: all 128-bit loads of a lane are issued before the first store (latency overlap)
 template <int BYTES>
 __device__ __forceinline__ void copy_fixed(void* dst, const void* src) {
@@ -69,11 +73,25 @@ __device__ __forceinline__ void copy_in(void* dst, const void* src, int bytes) {
     __syncwarp();
 }
 
-// per-warp shared-memory slot: EnvS | OutS (optional) | EnvAux
+// per-warp shared-memory slot: EnvS | OutS (not in the classic kernels) | EnvAux -- compile-time offsets, so
+// that every address inside the slot is "slot base + immediate"
+template <int JW, bool CL>
+struct Slot {
+    static constexpr int OUTS = (int)sizeof(EnvS<JW, false, false>);
+    static constexpr int AUX = OUTS + (CL ? 0 : (int)sizeof(OutS<JW>));
+    static constexpr int BYTES = AUX + (int)sizeof(EnvAux);
+};
+inline int slot_bytes(int JW, bool classic) {
+    return JW == 1 ? (classic ? Slot<1, true>::BYTES : Slot<1, false>::BYTES)
+         : JW == 2 ? (classic ? Slot<2, true>::BYTES : Slot<2, false>::BYTES)
+                   : (classic ? Slot<4, true>::BYTES : Slot<4, false>::BYTES);
+}
+
+template <int JW, bool CL>
 __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env, uint8_t* slot) {
     const InstDev& I = bd.inst;
     const int64_t v = I.n_inst == 1 ? 0 : (env < I.n_inst ? env : env % I.n_inst);
-    EnvAux* aux = (EnvAux*)(slot + bd.state_stride + bd.outs_stride);
+    EnvAux* aux = (EnvAux*)(slot + Slot<JW, CL>::AUX);
     c.I = &bd.inst;
     c.C = &bd.cfg;
     c.aux = aux;
@@ -85,7 +103,7 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
         aux->op_dur = I.op_dur + v * I.N;
         aux->job_work = I.job_work + v * I.J;
         aux->op_log = bd.op_log ? bd.op_log + env * 2 * (int64_t)I.N : nullptr;
-        aux->outs = bd.outs ? (void*)(slot + bd.state_stride) : nullptr;
+        aux->outs = bd.outs ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
         aux->tcur = bd.tcur ? bd.tcur + env * (int64_t)I.n_tobj : nullptr;
         aux->tseed = bd.tseed ? bd.tseed + env * (int64_t)I.n_tobj : nullptr;
         aux->start_seeds = bd.start_seeds ? bd.start_seeds + env * (int64_t)I.n_tobj : nullptr;
@@ -96,6 +114,7 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
         aux->lower_bound = I.lb_mat[2 * v];
         aux->max_allowed_time = I.lb_mat[2 * v + 1];
         aux->neg_inv_n = -1.0 / (double)I.N;
+        aux->act_block = 0;
     }
     __syncwarp();
 }
@@ -138,15 +157,15 @@ template <int JW, bool ST, bool CL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int warp = WARPS_PER_CTA == 1 ? 0 : (int)(threadIdx.x >> 5);
+    const int warp = WARPS_PER_CTA == 1 ? 0 : warp_index();
     const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
     if (env >= bd.B) return;
     if (mask && !mask[env]) return;
-    uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
+    uint8_t* slot = smem + warp * Slot<JW, CL>::BYTES;
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
-    void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
+    void* outs_sm = bd.outs ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
     Ctx c;
-    make_ctx(c, bd, env, slot);
+    make_ctx<JW, CL>(c, bd, env, slot);
     run_env_op(s, c, OP_RESET);
     __syncwarp();
     write_step_out(s, c, out, env, 0.0, obs_bytes);
@@ -159,18 +178,18 @@ template <int JW, bool ST, bool CL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_STEP_MIN_CTAS)
 k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int warp = WARPS_PER_CTA == 1 ? 0 : (int)(threadIdx.x >> 5);
+    const int warp = WARPS_PER_CTA == 1 ? 0 : warp_index();
     const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
     if (env >= bd.B) return;
-    uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
+    uint8_t* slot = smem + warp * Slot<JW, CL>::BYTES;
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
-    void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
+    void* outs_sm = bd.outs ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
     uint8_t* g_state = bd.state + env * (int64_t)bd.state_stride;
     uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
     copy_fixed<(int)sizeof(EnvS<JW, ST, CL>)>(&s, g_state);
     if (g_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
     Ctx c;
-    make_ctx(c, bd, env, slot);
+    make_ctx<JW, CL>(c, bd, env, slot);
     const int action = actions[env];
     double r = run_env_op(s, c, action);
     __syncwarp();
@@ -202,10 +221,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_ROLLOUT_MIN_CTAS)
 k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __restrict__ tape, int64_t tape_stride,
           int max_steps, int flags, jsl_rollout_out out) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int warp = WARPS_PER_CTA == 1 ? 0 : (int)(threadIdx.x >> 5);
-    uint8_t* slot = smem + (size_t)warp * (bd.state_stride + bd.outs_stride + (int)sizeof(EnvAux));
+    const int warp = WARPS_PER_CTA == 1 ? 0 : warp_index();
+    uint8_t* slot = smem + warp * Slot<JW, CL>::BYTES;
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
-    void* outs_sm = bd.outs ? (void*)((uint8_t*)&s + bd.state_stride) : nullptr;
+    void* outs_sm = bd.outs ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
     // persistent warps pull env indices from a global counter: episodes differ in length, a static
     // grid-stride split leaves the tail of the launch half empty
     for (;;) {
@@ -214,7 +233,7 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
         const int64_t env = (int64_t)__shfl_sync(0xffffffffu, next, 0);
         if (env >= bd.B) break;
         Ctx c;
-        make_ctx(c, bd, env, slot);
+        make_ctx<JW, CL>(c, bd, env, slot);
         bool pending_reset = (flags & JSL_RO_RESET_FIRST) != 0;
         if (!pending_reset) {
             copy_in(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
@@ -268,11 +287,11 @@ k_digest(const __grid_constant__ BatchDev bd, int64_t env, int32_t* out, int cap
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* slot = smem;
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)smem;
-    void* outs_sm = bd.outs ? (void*)(smem + bd.state_stride) : nullptr;
+    void* outs_sm = bd.outs ? (void*)(smem + Slot<JW, CL>::OUTS) : nullptr;
     copy_in(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
     if (bd.outs) copy_in(outs_sm, bd.outs + env * (int64_t)bd.outs_stride, bd.outs_stride);
     Ctx c;
-    make_ctx(c, bd, env, slot);
+    make_ctx<JW, CL>(c, bd, env, slot);
     int n = write_digest(s, c, out, cap);
     if (JSL_LANE == 0) *n_out = n;
 }

@@ -71,7 +71,7 @@ void make_ctx(Sim* s, Ctx& c) {
     a.tseed = s->tobj.stochastic ? s->tseed.data() : nullptr;
     a.start_seeds = s->start_seeds.empty() ? nullptr : s->start_seeds.data();
     a.tape = s->tape.empty() ? nullptr : s->tape.data(); a.tape_len = (int)s->tape.size();
-    a.seed = s->seed; a.env_id = s->env_id;
+    a.seed = s->seed; a.env_id = s->env_id; a.act_block = 0;
     a.lower_bound = s->lb_mat[0]; a.max_allowed_time = s->lb_mat[1]; a.neg_inv_n = -1.0 / (double)s->I.N;
 }
 
