@@ -187,7 +187,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--envs-per-gpu", type=int, default=262144)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--step-mode-steps", type=int, default=200)
+    ap.add_argument("--step-mode-steps", type=int, default=1000)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup

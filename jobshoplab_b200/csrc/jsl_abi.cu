@@ -239,6 +239,7 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     I.default_tool = t->default_tool;
     I.start_time = t->start_time;
     I.sb0 = 3 * t->M + t->T;
+    I.neg_inv_n = -1.0 / (double)I.N;
     I.out_mask = 0;
     for (int sb = 0; sb < t->S; sb++)
         if (t->sbuf_role[sb] == JSL_ROLE_OUTPUT) I.out_mask |= 1u << sb;

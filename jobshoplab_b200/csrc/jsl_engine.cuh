@@ -120,6 +120,7 @@ struct InstDev {
     int sample_depth;
     int n_tobj, off_setup, off_travel, off_mof, off_mod, off_tof, off_tod;
     int sb0;           // 3M+T: index of the first standalone buffer
+    double neg_inv_n;  // -1.0 / N (rewards.py:135-138)
     uint32_t out_mask; // bit s set: standalone buffer s has the OUTPUT role (S <= 32)
 };
 
@@ -159,6 +160,7 @@ struct alignas(16) EnvS {
     uint8_t j_proc[MJ];              // op j_k is PROCESSING
     uint8_t j_agv[MJ];               // transport whose transport_job is this job, or NONE8
     uint8_t j_mach[MJ];              // machine of op j_k (NONE8 when all ops are done)
+    uint32_t j_exec[MJ];             // bit m: the job has a DONE op on machine m (observation row)
     // machines
     int32_t m_occ[MM];
     uint16_t m_done[MM];             // DONE ops on this machine (observation)
@@ -226,6 +228,21 @@ struct Ctx {
     } while (0)
 
 // ------------------------------------------------------------------------------------ primitives
+// position of the k-th (0-based) set bit of x, k < popc(x).  (__fns is emulated by a long software sequence.)
+JSL_M int nth_bit(uint32_t x, int k) {
+    if (k < 4) {  // the usual case: the agent looks at one of the first candidates
+        for (; k > 0; k--) x &= x - 1;
+        return JSL_FFS(x) - 1;
+    }
+    int pos = 0, c;
+    c = JSL_POPC(x & 0xffffu); if (k >= c) { k -= c; pos += 16; x >>= 16; }
+    c = JSL_POPC(x & 0xffu);   if (k >= c) { k -= c; pos += 8;  x >>= 8; }
+    c = JSL_POPC(x & 0xfu);    if (k >= c) { k -= c; pos += 4;  x >>= 4; }
+    c = JSL_POPC(x & 0x3u);    if (k >= c) { k -= c; pos += 2;  x >>= 2; }
+    c = (int)(x & 1u);         if (k >= c) pos += 1;
+    return pos;
+}
+
 template <int W>
 struct Mask {
     uint32_t w[W];
@@ -262,7 +279,7 @@ struct Mask {
 #pragma unroll
         for (int i = 0; i < W; i++) {
             int c = JSL_POPC(w[i]);
-            if (k < c) return i * 32 + (int)JSL_FNS(w[i], k + 1);
+            if (k < c) return i * 32 + nth_bit(w[i], k);
             k -= c;
         }
         return -1;
@@ -796,6 +813,7 @@ JSL_D void machine_outage_to_idle(EnvS<JW, ST, CL>& s, Ctx& c, int m) {
     }
     s.j_k[j] = (uint8_t)(k + 1);
     s.j_proc[j] = 0;
+    s.j_exec[j] |= 1u << (c.aux->op_mt[I.job_op_start[j] + k] & 31);
     s.j_mach[j] = (k + 1 < job_nops(I, j)) ? (uint8_t)(c.aux->op_mt[I.job_op_start[j] + k + 1] & 0xffff) : (uint8_t)NONE8;
     if (c.now > s.max_done_end) s.max_done_end = c.now;
     s.m_done[m] = (uint16_t)(s.m_done[m] + 1);
@@ -1166,6 +1184,7 @@ JSL_D bool classic_complete(EnvS<JW, ST, CL>& s, Ctx& c, const Mask<1>& mm, cons
         s.j_end[j] = now;
         s.j_k[j] = (uint8_t)(k + 1);
         s.j_proc[j] = 0;
+        s.j_exec[j] |= 1u << m;
         s.j_mach[j] = (k + 1 < job_nops(I, j)) ? (uint8_t)(c.aux->op_mt[o + 1] & 0xffff) : (uint8_t)NONE8;
         s.m_done[m] = (uint16_t)(s.m_done[m] + 1);
         s.m_job[m] = NONE8;
@@ -1399,7 +1418,7 @@ JSL_D void env_init(EnvS<JW, ST, CL>& s, Ctx& c) {
         s.j_start[j] = -1; s.j_end[j] = -1;
         s.j_seq[j] = (uint32_t)j;  // initial stores list jobs in job order (mapper.py:1296-1321)
         s.j_loc[j] = live ? I.job_init_buf[j] : (uint16_t)0xffff;
-        s.j_k[j] = 0; s.j_proc[j] = 0; s.j_agv[j] = NONE8;
+        s.j_k[j] = 0; s.j_proc[j] = 0; s.j_agv[j] = NONE8; s.j_exec[j] = 0;
         s.j_mach[j] = (live && job_nops(I, j) > 0) ? (uint8_t)(c.aux->op_mt[I.job_op_start[j]] & 0xffff) : (uint8_t)NONE8;
     });
     wp_for<1>(32, [&](int m) {
@@ -1604,10 +1623,10 @@ JSL_HD int obs_bytes_oparray(int J, int N) { return (16 + 4 * N + 4 * J + 15) & 
 JSL_HD int obs_bytes_tassel(int J) { return (7 * 4 * J + 15) & ~15; }
 
 template <int JW, bool ST, bool CL>
-JSL_D void cand_floats(const EnvS<JW, ST, CL>& s, const Ctx& c, float* tr) {
+JSL_D void cand_floats(const EnvS<JW, ST, CL>& s, const Ctx& c, float* tr, const Trans* known = nullptr) {
     const InstDev& I = *c.I;
     if (!s.obs_done && s.n_possible - s.skip > 0) {
-        Trans cand = current_candidate(s, c);
+        Trans cand = known ? *known : current_candidate(s, c);
         int comp_idx = cand.kind == 0 ? cand.comp : I.M + cand.comp;
         tr[0] = I.tr_comp[comp_idx];  // float32 of the float64 quotient, tabulated on the host
         tr[1] = I.tr_job[cand.job];
@@ -1618,11 +1637,11 @@ JSL_D void cand_floats(const EnvS<JW, ST, CL>& s, const Ctx& c, float* tr) {
 }
 
 template <int JW, bool ST, bool CL>
-JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* out) {
+JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* out, const Trans* cand = nullptr) {
     const InstDev& I = *c.I;
     const int J = I.J, M = I.M;
     float tr[3];
-    cand_floats(s, c, tr);
+    cand_floats(s, c, tr, cand);
     float* f = (float*)out;
     int32_t* jprog = (int32_t*)(out + 16);
     int32_t* mprog = jprog + J;
@@ -1645,17 +1664,13 @@ JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* ou
         // numeric index into the lexicographically ordered tuple (observations.py:437-441)
         avail[r] = (int8_t)(any_idle && !s.j_proc[I.job_lex[j]]);
         jprog[r] = s.j_k[r];
-        int o0 = I.job_op_start[j];
-        uint32_t mask = 0;
-        const int kd = s.j_k[j];
-        for (int k = 0; k < kd; k++) mask |= 1u << (c.aux->op_mt[o0 + k] & 31);
+        const uint32_t mask = s.j_exec[j];
         int8_t* row = exec + r * M;
         if (word_rows) {
             uint32_t* rw = (uint32_t*)row;
             for (int q = 0; q < M / 4; q++) rw[q] = (((mask >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
         } else {
-            for (int m = 0; m < M; m++) row[m] = 0;
-            for (int k = 0; k < kd; k++) row[c.aux->op_mt[o0 + k] & 0xffff] = 1;
+            for (int m = 0; m < M; m++) row[m] = (int8_t)((mask >> m) & 1u);
         }
     });
     wp_for<1>(M, [&](int r) {
@@ -1668,10 +1683,10 @@ JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* ou
 // BinaryOperationArrayObservation.make (observations.py:631-693 over :588-618):
 //   f32 current_transition[3] | f32 0 | f32 operation_state[N] | f32 job_locations[J]
 template <int JW, bool ST, bool CL>
-JSL_D void write_obs_oparray(const EnvS<JW, ST, CL>& s, Ctx& c, uint8_t* out) {
+JSL_D void write_obs_oparray(const EnvS<JW, ST, CL>& s, Ctx& c, uint8_t* out, const Trans* cand = nullptr) {
     const InstDev& I = *c.I;
     float tr[3];
-    cand_floats(s, c, tr);
+    cand_floats(s, c, tr, cand);
     float* f = (float*)out;
     float* ops = f + 4;
     float* loc = ops + I.N;

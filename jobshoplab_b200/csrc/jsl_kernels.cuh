@@ -87,10 +87,10 @@ inline int slot_bytes(int JW, bool classic) {
                    : (classic ? Slot<4, true>::BYTES : Slot<4, false>::BYTES);
 }
 
-template <int JW, bool CL>
+template <int JW, bool ST, bool CL>
 __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env, uint8_t* slot) {
     const InstDev& I = bd.inst;
-    const int64_t v = I.n_inst == 1 ? 0 : (env < I.n_inst ? env : env % I.n_inst);
+    const int64_t v = I.n_inst == 1 ? 0 : (env < I.n_inst ? env : (int64_t)((uint64_t)env % (uint32_t)I.n_inst));
     EnvAux* aux = (EnvAux*)(slot + Slot<JW, CL>::AUX);
     c.I = &bd.inst;
     c.C = &bd.cfg;
@@ -98,44 +98,50 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
     c.raise = 0;
     c.now = 0;
     __syncwarp();
-    if (JSL_LANE == 0) {
-        aux->op_mt = I.op_mt + v * I.N;
-        aux->op_dur = I.op_dur + v * I.N;
-        aux->job_work = I.job_work + v * I.J;
-        aux->op_log = bd.op_log ? bd.op_log + env * 2 * (int64_t)I.N : nullptr;
-        aux->outs = bd.outs ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
-        aux->tcur = bd.tcur ? bd.tcur + env * (int64_t)I.n_tobj : nullptr;
+    // every lane stores the same (warp-uniform) values: no divergent single-lane section
+    aux->op_mt = I.op_mt + v * I.N;
+    aux->op_dur = I.op_dur + v * I.N;
+    aux->job_work = I.job_work + v * I.J;
+    aux->op_log = bd.op_log ? bd.op_log + env * 2 * (int64_t)I.N : nullptr;
+    aux->outs = (!CL && bd.outs) ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
+    if (ST) {
+        aux->tcur = bd.tcur + env * (int64_t)I.n_tobj;
         aux->tseed = bd.tseed ? bd.tseed + env * (int64_t)I.n_tobj : nullptr;
         aux->start_seeds = bd.start_seeds ? bd.start_seeds + env * (int64_t)I.n_tobj : nullptr;
         aux->tape = bd.tape ? bd.tape + env * bd.tape_stride : nullptr;
         aux->tape_len = (int)bd.tape_stride;
-        aux->seed = bd.seed;
-        aux->env_id = (uint64_t)(bd.env_base + env);
-        aux->lower_bound = I.lb_mat[2 * v];
-        aux->max_allowed_time = I.lb_mat[2 * v + 1];
-        aux->neg_inv_n = -1.0 / (double)I.N;
-        aux->act_block = 0;
+    } else {
+        aux->tcur = nullptr; aux->tseed = nullptr; aux->start_seeds = nullptr; aux->tape = nullptr; aux->tape_len = 0;
     }
+    aux->seed = bd.seed;
+    aux->env_id = (uint64_t)(bd.env_base + env);
+    aux->lower_bound = I.lb_mat[2 * v];
+    aux->max_allowed_time = I.lb_mat[2 * v + 1];
+    aux->neg_inv_n = I.neg_inv_n;
+    aux->act_block = 0;
     __syncwarp();
 }
 
 template <int JW, bool ST, bool CL>
 __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c, const jsl_step_out& out, int64_t env,
                                                double reward, int obs_bytes) {
-    const InstDev& I = *c.I;
+    const int remaining = s.n_possible - s.skip;
+    // the candidate the agent sees next: needed by the observation (current_transition) and by out.cand
+    Trans cand;
+    cand.kind = -1; cand.comp = -1; cand.new_state = 0; cand.job = -1;
+    const bool have_cand = remaining > 0 && s.status <= JSL_ST_STEP_FAILED;
+    if (have_cand) cand = current_candidate(s, c);
     if (out.obs && s.status <= JSL_ST_STEP_FAILED) {
         uint8_t* o = out.obs + env * (int64_t)obs_bytes;
-        if (c.C->obs_kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o);
-        else if (c.C->obs_kind == JSL_OBS_OPERATION_ARRAY) write_obs_oparray(s, c, o);
+        if (c.C->obs_kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o, have_cand ? &cand : nullptr);
+        else if (c.C->obs_kind == JSL_OBS_OPERATION_ARRAY) write_obs_oparray(s, c, o, have_cand ? &cand : nullptr);
         else if (c.C->obs_kind == JSL_OBS_TASSEL) write_obs_tassel(s, c, o);
     }
     int status = s.status;
     if (c.raise && status <= JSL_ST_STEP_FAILED) status = c.raise;  // observation factory raised
     int16_t cd[4] = {-1, -1, -1, 0};
-    int remaining = s.n_possible - s.skip;
     if (out.cand && remaining > 0 && status <= JSL_ST_TRUNCATED) {
-        Trans t = current_candidate(s, c);
-        cd[0] = (int16_t)t.kind; cd[1] = (int16_t)t.comp; cd[2] = (int16_t)t.job;
+        cd[0] = (int16_t)cand.kind; cd[1] = (int16_t)cand.comp; cd[2] = (int16_t)cand.job;
         cd[3] = (int16_t)(remaining > 32767 ? 32767 : remaining);
     }
     if (JSL_LANE == 0) {
@@ -150,7 +156,6 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c
             q[0] = cd[0]; q[1] = cd[1]; q[2] = cd[2]; q[3] = cd[3];
         }
     }
-    (void)I;
 }
 
 template <int JW, bool ST, bool CL>
@@ -165,7 +170,7 @@ k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, j
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
     void* outs_sm = bd.outs ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
     Ctx c;
-    make_ctx<JW, CL>(c, bd, env, slot);
+    make_ctx<JW, ST, CL>(c, bd, env, slot);
     run_env_op(s, c, OP_RESET);
     __syncwarp();
     write_step_out(s, c, out, env, 0.0, obs_bytes);
@@ -189,7 +194,7 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     copy_fixed<(int)sizeof(EnvS<JW, ST, CL>)>(&s, g_state);
     if (g_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
     Ctx c;
-    make_ctx<JW, CL>(c, bd, env, slot);
+    make_ctx<JW, ST, CL>(c, bd, env, slot);
     const int action = actions[env];
     double r = run_env_op(s, c, action);
     __syncwarp();
@@ -233,7 +238,7 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
         const int64_t env = (int64_t)__shfl_sync(0xffffffffu, next, 0);
         if (env >= bd.B) break;
         Ctx c;
-        make_ctx<JW, CL>(c, bd, env, slot);
+        make_ctx<JW, ST, CL>(c, bd, env, slot);
         bool pending_reset = (flags & JSL_RO_RESET_FIRST) != 0;
         if (!pending_reset) {
             copy_in(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
@@ -291,7 +296,7 @@ k_digest(const __grid_constant__ BatchDev bd, int64_t env, int32_t* out, int cap
     copy_in(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
     if (bd.outs) copy_in(outs_sm, bd.outs + env * (int64_t)bd.outs_stride, bd.outs_stride);
     Ctx c;
-    make_ctx<JW, CL>(c, bd, env, slot);
+    make_ctx<JW, ST, CL>(c, bd, env, slot);
     int n = write_digest(s, c, out, cap);
     if (JSL_LANE == 0) *n_out = n;
 }
