@@ -285,18 +285,37 @@ def main():
     s1.record()
     barrier()
     step_ms = s0.elapsed_time(s1)
+    # ---- instances generated on the device (InstanceRandomizer) instead of uploaded ---------
+    def gen_pass(k):
+        sb.randomize(seed=SEED + 1 + k, min_duration=1, max_duration=100)
+        r = sb.rollout("random", reset_first=True, writeback=False)
+        for h, d in zip(host_out, (r.makespan, r.n_steps, r.ret, r.status)):
+            h.copy_(d, non_blocking=True)
+
+    gen_pass(0)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    gen_steps = 0
+    for k in range(args.steps):
+        gen_pass(1 + k)
+        torch.cuda.current_stream().synchronize()
+        gen_steps += int(host_out[1].sum().item())
+    g1.record()
+    barrier()
+    gen_ms = g0.elapsed_time(g1)
     step_bytes = 2 * sb.shape.state_bytes + 1 + 8 + 2 + sb.shape.obs_bytes + 4 + 4 + 8 + 1
     shape_state_bytes, shape_obs_bytes = sb.shape.state_bytes, sb.shape.obs_bytes
     sb.close()
 
     # ---- reduce over ranks: max time, summed units ---------------------------------------------------
-    vec = torch.tensor([ms, e2e_ms, step_ms], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([steps_per_pass * args.steps, e2e_steps * args.steps, ok], dtype=torch.float64, device=dev)
+    vec = torch.tensor([ms, e2e_ms, step_ms, gen_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([steps_per_pass * args.steps, e2e_steps * args.steps, ok, gen_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms, e2e_ms, step_ms = vec.tolist()
-    total_steps, total_e2e_steps, ok = cnt.tolist()
+    ms, e2e_ms, step_ms, gen_ms = vec.tolist()
+    total_steps, total_e2e_steps, ok, total_gen_steps = cnt.tolist()
 
     if rank == 0:
         peaks = {}
@@ -337,6 +356,10 @@ def main():
                           "what": "jsl_step on the same batch with device-resident random actions: state image "
                                   "read+written and the default observation written every env.step"},
         }
+        out["device_instances"] = {
+            "value": total_gen_steps / (gen_ms / 1e3), "unit": "env-steps/s",
+            "what": "jsl_batch_randomize (InstanceRandomizer on the device: a fresh 30x20 instance per env) + "
+                    "jsl_rollout + D2H of the results, per pass; no host tables"}
         if not args.no_cpu:
             threads = os.cpu_count() or 1
             n = max(threads * 128, 256)

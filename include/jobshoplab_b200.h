@@ -213,6 +213,21 @@ jsl_batch_t* jsl_batch_create_variants(const jsl_instance_t* tmpl, int64_t n_ins
  * jsl_batch_create_variants; packed on the device by a small kernel on `stream`. */
 int jsl_batch_load_variants(jsl_batch_t*, const int32_t* op_machine, const int32_t* op_duration,
                             const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream);
+/* compiler/manipulators.py:99-150 InstanceRandomizer.manipulate for every variant of the batch, on the device:
+ * per job a uniformly random permutation of its operations (machine and tool travel together) and durations
+ * uniform in [min_duration, max_duration) (random.randrange); per-job work, the lower bound and
+ * max_allowed_time are recomputed (utils/utils.py:310-352).  Counter-based generator keyed by `seed` and the
+ * global variant index (env_base + v), see jsl_randomize.cuh; the reference draws from Python's global RNGs,
+ * so the distribution -- not sample values -- is the contract.  `mask` (dev u8 [n_inst], nullable) selects the
+ * variants to redraw (the reference recompiles, hence re-randomises, on every env.reset).  Takes effect at the
+ * next jsl_reset of the envs concerned.
+ * JSL_E_INVALID for an empty range (the reference raises ValueError), JSL_E_UNSUPPORTED for stochastic batches. */
+int jsl_batch_randomize(jsl_batch_t*, uint64_t seed, int min_duration, int max_duration, const uint8_t* mask,
+                        void* stream);
+/* Operation tables of variants [first, first+count) copied to HOST arrays ([count][n_ops] machine, tool,
+ * duration; [count] lower bound, max_allowed_time; any pointer may be NULL).  Synchronises. */
+int jsl_batch_get_variants(jsl_batch_t*, int64_t first, int64_t count, int32_t* op_machine, int32_t* op_tool,
+                           int32_t* op_duration, int32_t* lower_bound, int32_t* max_allowed_time);
 void jsl_batch_destroy(jsl_batch_t*);
 int jsl_batch_shape(const jsl_batch_t*, jsl_shape* out);
 /* Stochastic instances (stochasticy_models.py): by default every StochasticTimeConfig.update() draws from

@@ -20,7 +20,7 @@ LIB = Path(os.environ.get("JSL_LIB_OUT", CSRC / "libjsl_b200.so"))
 EXTRA = os.environ.get("JSL_NVCC_EXTRA", "").split()
 OBJ_TAG = os.environ.get("JSL_OBJ_TAG", "")
 UNITS = ["jsl_abi.cu", "jsl_kernels_jw1.cu", "jsl_kernels_jw2.cu", "jsl_kernels_jw4.cu"]
-HEADERS = [CSRC / "jsl_engine.cuh", CSRC / "jsl_kernels.cuh", CSRC / "jsl_tobj.hpp", INCLUDE / "jobshoplab_b200.h"]
+HEADERS = [CSRC / "jsl_engine.cuh", CSRC / "jsl_kernels.cuh", CSRC / "jsl_randomize.cuh", CSRC / "jsl_tobj.hpp", INCLUDE / "jobshoplab_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

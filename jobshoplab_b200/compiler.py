@@ -455,6 +455,34 @@ def _outage(o: dict, sampler):
     return (_get_time(None, o["frequency"], sampler), _get_time(None, o["duration"], sampler))
 
 
+# --------------------------------------------------------------------------- manipulators
+def randomize_instance(li: L.LoweredInstance) -> L.LoweredInstance:
+    """compiler/manipulators.py:99-150 InstanceRandomizer.manipulate on the lowered tables: per job
+    ``np.random.permutation`` of its operations, every duration ``random.randrange(min, max)`` over the
+    instance's current durations.  Same calls on the same global generators in the same order as the
+    reference, so equal ``np.random.seed`` / ``random.seed`` give the reference's instance.  The derived
+    figures (lower bound, max_allowed_time: utils.py:310-352) follow the new tables.  The batched, on-device
+    form is ``engine.Batch.randomize``."""
+    import dataclasses
+    import random
+
+    d = np.asarray(li.op_duration)
+    lo, hi = int(d.min()), int(d.max())
+    om, ot, od = li.op_machine.copy(), li.op_tool.copy(), li.op_duration.copy()
+    for j in range(li.n_jobs):
+        a, b = int(li.job_op_start[j]), int(li.job_op_start[j + 1])
+        perm = np.random.permutation(b - a)
+        om[a:b], ot[a:b] = li.op_machine[a:b][perm], li.op_tool[a:b][perm]
+        for k in range(a, b):
+            od[k] = random.randrange(lo, hi)  # ValueError for an empty range, like the reference
+    return dataclasses.replace(li, op_machine=om, op_tool=ot, op_duration=od, op_spec=L.TimeSpec(),
+                               lower_bound=_taillard_lower_bound(np.asarray(li.job_op_start), om, od),
+                               max_allowed_time=int(np.sum(od)))
+
+
+MANIPULATORS = {"DummyManipulator": lambda li: li, "InstanceRandomizer": randomize_instance}
+
+
 # --------------------------------------------------------------------------- Compiler facade
 class Compiler:
     """Same call shape as jobshoplab.compiler.Compiler (compiler.py:16-106); `compile()` returns a
@@ -474,9 +502,17 @@ class Compiler:
             else:
                 raise InvalidValue("compiler.repo", name)
         self.repo = repo
+        names = [m for m in (config.compiler.manipulators if config is not None else []) if m is not None]
+        for m in names:
+            if m not in MANIPULATORS:
+                raise InvalidValue("compiler.manipulators", m)  # the reference: AttributeError from getattr
+        self.manipulators = tuple(MANIPULATORS[m] for m in names)
 
     def compile(self) -> L.LoweredInstance:
-        return lower_dict(self.repo.load_as_dict())
+        li = lower_dict(self.repo.load_as_dict())
+        for manipulate in self.manipulators:  # compiler.py:98-99
+            li = manipulate(li)
+        return li
 
 
 def compile_spec_text(text: str) -> L.LoweredInstance:

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "jsl_kernels.cuh"
+#include "jsl_randomize.cuh"
 #include "jsl_tobj.hpp"
 
 using namespace jsl;
@@ -93,6 +94,17 @@ __global__ void k_pack_variants(int64_t n_inst, int N, int J, const int32_t* __r
         lb_mat[2 * i] = st_lb[i];
         lb_mat[2 * i + 1] = st_mat[i];
     }
+}
+
+// InstanceRandomizer for all variants: one thread per variant runs the sequential routine of jsl_randomize.cuh
+__global__ void k_randomize(int64_t n_inst, int N, int J, const int32_t* __restrict__ job_op_start, uint64_t seed,
+                            int64_t base, int min_d, int max_d, const uint8_t* __restrict__ mask, int32_t* op_mt,
+                            int32_t* op_dur, int32_t* job_work, int32_t* lb_mat) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_inst; v += stride)
+        if (!mask || mask[v])
+            randomize_variant(seed, (uint64_t)(base + v), J, job_op_start, min_d, max_d, op_mt + v * N, op_dur + v * N,
+                          job_work + v * J, lb_mat + 2 * v);
 }
 
 bool spec_is_static(const jsl_time_spec& sp, int n) {
@@ -392,6 +404,52 @@ int jsl_batch_load_variants(jsl_batch_t* b, const int32_t* op_machine, const int
                                                      (int32_t*)I.lb_mat);
     b->launches++;
     CK(cudaGetLastError());
+    return JSL_OK;
+}
+
+int jsl_batch_randomize(jsl_batch_t* b, uint64_t seed, int min_duration, int max_duration, const uint8_t* mask,
+                        void* stream) {
+    if (!b) return JSL_E_INVALID;
+    if (max_duration <= min_duration || min_duration < 0) { set_err("empty range for randrange()"); return JSL_E_INVALID; }
+    if (b->bd.tcur) { set_err("stochastic batches cannot be randomised"); return JSL_E_UNSUPPORTED; }
+    CK(cudaSetDevice(b->device));
+    const InstDev& I = b->bd.inst;
+    const int threads = 128;
+    int64_t blocks = (I.n_inst + threads - 1) / threads;
+    if (blocks > (int64_t)b->sm_count * 64) blocks = (int64_t)b->sm_count * 64;
+    k_randomize<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(I.n_inst, I.N, I.J, I.job_op_start, seed, b->bd.env_base,
+                                                                   min_duration, max_duration, mask, (int32_t*)I.op_mt,
+                                                                   (int32_t*)I.op_dur, (int32_t*)I.job_work, (int32_t*)I.lb_mat);
+    b->launches++;
+    CK(cudaGetLastError());
+    return JSL_OK;
+}
+
+int jsl_batch_get_variants(jsl_batch_t* b, int64_t first, int64_t count, int32_t* op_machine, int32_t* op_tool,
+                           int32_t* op_duration, int32_t* lower_bound, int32_t* max_allowed_time) {
+    if (!b) return JSL_E_INVALID;
+    const InstDev& I = b->bd.inst;
+    if (first < 0 || count < 0 || first + count > I.n_inst) return JSL_E_INVALID;
+    CK(cudaSetDevice(b->device));
+    CK(cudaDeviceSynchronize());
+    const size_t n = (size_t)count * I.N;
+    if (op_machine || op_tool) {
+        std::vector<int32_t> mt(n);
+        CK(cudaMemcpy(mt.data(), I.op_mt + first * I.N, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) {
+            if (op_machine) op_machine[i] = mt[i] & 0xffff;
+            if (op_tool) op_tool[i] = (mt[i] >> 16) & 0xffff;
+        }
+    }
+    if (op_duration) CK(cudaMemcpy(op_duration, I.op_dur + first * I.N, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (lower_bound || max_allowed_time) {
+        std::vector<int32_t> lm(2 * (size_t)count);
+        CK(cudaMemcpy(lm.data(), I.lb_mat + 2 * first, lm.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < count; i++) {
+            if (lower_bound) lower_bound[i] = lm[2 * i];
+            if (max_allowed_time) max_allowed_time[i] = lm[2 * i + 1];
+        }
+    }
     return JSL_OK;
 }
 

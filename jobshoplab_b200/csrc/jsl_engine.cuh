@@ -1242,7 +1242,8 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
     // a step starts from the quiet state the previous call ended in (its loop only exits when nothing is due at
     // `now`), and the classic fast paths end in one: no timed transition can exist in the next batch
     bool known_quiet = !has_action && time_machine == TM_FORCE;  // (a reset starts from the initial state instead)
-    bool poss_fresh = false;  // s.c_* already describe the current state
+    bool poss_fresh = known_quiet;  // s.c_* already describe the current state
+    bool moved = !CL || (!has_action && time_machine == TM_JUMP);  // a job may have reached an output buffer (reset: unknown)
     int guard = 0;
     if (CL && has_action && act.kind == 0 && classic_start(s, c, act)) {
         action_stage = false; first = false; known_quiet = true; poss_fresh = true;
@@ -1353,18 +1354,18 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                 mm.w[0] = 0;
 #pragma unroll
                 for (int w = 0; w < JW; w++) tm.w[w] = 0;
-                first = false; known_quiet = true;
+                first = false; known_quiet = true; moved = true;
 #ifdef JSL_HOST_SIM
                 g_fast_complete++;
 #endif
-                if (++guard > 100000) { c.raise = JSL_ST_OTHER_INVALID; return true; }
-                continue;
+                continue;  // (ends in a quiet state: the loop only comes back here after a guarded time jump)
             }
         }
 #ifdef JSL_HOST_SIM
         if (CL) g_general_batches++;
 #endif
         // apply: machines, then timed transports, then teleports -- in creation order
+        moved = true;
         while (mm.any()) {
             int m = mm.pop_first();
             bool ok = apply_machine(s, c, m, s.x_mkind[m], s.x_mjob[m]);
@@ -1391,7 +1392,8 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
     s.time = c.now;
     s.skip = 0;
     // core_utils.py:44-68 is_done, state.py:270-283
-    bool done = !wp_ballot<JW>(I.J, [&](int j) { return !is_output(I, s.j_loc[j]); }).any();
+    bool done = s.all_out != 0;
+    if (moved) done = !wp_ballot<JW>(I.J, [&](int j) { return !is_output(I, s.j_loc[j]); }).any();
     if (done) {
         if (s.max_done_end >= 0) s.time = s.max_done_end;
         s.n_possible = 0;

@@ -22,7 +22,7 @@ LIB_PATH = Path(os.environ.get("JSL_LIB", Path(__file__).resolve().parent / "csr
 _lib = None
 
 ABI_SYMBOLS = ("jsl_last_error", "jsl_abi_version", "jsl_instance_create", "jsl_instance_destroy", "jsl_batch_create",
-               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
+               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_randomize", "jsl_batch_get_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
                "jsl_reset", "jsl_step", "jsl_rollout", "jsl_get_state", "jsl_get_op_log", "jsl_launch_count")
 
 RO_RESET_FIRST, RO_NO_WRITEBACK = 1, 2
@@ -49,6 +49,8 @@ def load_library():
     L.jsl_batch_create_variants.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int64, C.c_int, C.c_uint64, C.POINTER(abi.EnvCfg)]
     L.jsl_batch_load_variants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.jsl_batch_randomize.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.jsl_batch_get_variants.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 5
     L.jsl_batch_destroy.argtypes = [C.c_void_p]
     L.jsl_batch_shape.argtypes = [C.c_void_p, C.POINTER(abi.Shape)]
     L.jsl_batch_set_env_base.argtypes = [C.c_void_p, C.c_int64]
@@ -134,10 +136,12 @@ class Batch:
         if variants is not None:
             om, od, lb, mat = (np.ascontiguousarray(a, dtype=np.int32) for a in variants)
             n_inst = om.shape[0]
+            self.n_variants = int(n_inst)
             self.h = self.L.jsl_batch_create_variants(self.instances[0].h, n_inst, om.ctypes.data, od.ctypes.data,
                                                       lb.ctypes.data, mat.ctypes.data, self.B, self.device, seed,
                                                       C.byref(self.cfg))
         else:
+            self.n_variants = len(self.instances)
             arr = (C.c_void_p * len(self.instances))(*[i.h for i in self.instances])
             self.h = self.L.jsl_batch_create(arr, len(self.instances), self.B, self.device, seed, C.byref(self.cfg))
         if not self.h:
@@ -200,6 +204,35 @@ class Batch:
                 assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
                 ptrs.append(a.ctypes.data)
         self._check(self.L.jsl_batch_load_variants(self.h, *ptrs, self._stream()))
+
+    def randomize(self, seed: int, min_duration: int | None = None, max_duration: int | None = None, mask=None):
+        """InstanceRandomizer (compiler/manipulators.py:99-150) for the variants of this batch, on the device:
+        per job a random permutation of its operations and durations uniform in [min_duration, max_duration)
+        (defaults: min / max duration of the template instance, as the reference takes them from the instance
+        it manipulates).  `mask`: uint8 CUDA tensor [n_variants] selecting the variants to redraw.  Applies
+        from the next reset of the envs concerned."""
+        d = np.asarray(self.lowered[0].op_duration)
+        lo = int(d.min()) if min_duration is None else int(min_duration)
+        hi = int(d.max()) if max_duration is None else int(max_duration)
+        mp = None
+        if mask is not None:
+            assert mask.is_cuda and mask.dtype == self.torch.uint8 and mask.is_contiguous()
+            mp = mask.data_ptr()
+        rc = self.L.jsl_batch_randomize(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF, lo, hi, mp, self._stream())
+        if rc != 0:
+            raise InvalidValue("randomize", (lo, hi), _err(self.L))
+
+    def get_variants(self, first: int = 0, count: int | None = None):
+        """(op_machine, op_tool, op_duration, lower_bound, max_allowed_time) of variants [first, first+count) as
+        numpy int32 arrays (synchronises)."""
+        n_var = int(self.n_variants)
+        count = n_var - first if count is None else int(count)
+        N = self.shape.n_ops
+        om, ot, od = (np.zeros((count, N), np.int32) for _ in range(3))
+        lb, mat = np.zeros(count, np.int32), np.zeros(count, np.int32)
+        self._check(self.L.jsl_batch_get_variants(self.h, int(first), count, om.ctypes.data, ot.ctypes.data, od.ctypes.data,
+                                                  lb.ctypes.data, mat.ctypes.data))
+        return om, ot, od, lb, mat
 
     def set_sample_tape(self, tape=None):
         """Replay recorded StochasticTimeConfig.update() results (int32 CUDA tensor [B, L]) instead of drawing

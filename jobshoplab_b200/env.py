@@ -78,14 +78,33 @@ class BatchedJobShopLabEnv:
                  instances=None, variants=None, record_ops: bool = False, auto_reset: bool = False):
         self.config = config or Config()
         lowered = instances if instances is not None else _lower(self.config, compiler)
+        # compiler.manipulators = [InstanceRandomizer]: the reference recompiles -- and so re-randomises -- the
+        # instance on every env.reset (env.py:491).  Batched: every env owns a variant of the operation
+        # tables, redrawn on the device whenever that env is reset (engine.Batch.randomize).
+        self.randomize = "InstanceRandomizer" in [m for m in self.config.compiler.manipulators if m]
+        if self.randomize and variants is None and instances is None:
+            li = lowered
+            tile = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.int32), (num_envs, len(a))))
+            variants = (tile(li.op_machine), tile(li.op_duration), np.full(num_envs, li.lower_bound, np.int32),
+                        np.full(num_envs, li.max_allowed_time, np.int32))
         self.batch = Batch(lowered, num_envs, device=device, seed=seed, variants=variants, record_ops=record_ops,
                            **_cfg_kwargs(self.config))
         self.instance = self.batch.lowered[0]
         self.num_envs = num_envs
         self.auto_reset = auto_reset
         self.action_space = Discrete(2)
+        self._seed, self._epoch = int(seed), 0
+        d = np.asarray(self.instance.op_duration)
+        self._dur_range = (int(d.min()), int(d.max()))  # of the instance handed to the manipulator
+
+    def _redraw(self, mask=None):
+        self._epoch += 1
+        self.batch.randomize(seed=(self._seed * 0x9E3779B97F4A7C15 + self._epoch) & 0xFFFFFFFFFFFFFFFF,
+                             min_duration=self._dur_range[0], max_duration=self._dur_range[1], mask=mask)
 
     def reset(self, mask=None):
+        if self.randomize:
+            self._redraw(mask)
         out = self.batch.reset(mask)
         return self.batch.unpack_obs(out.obs), out
 
@@ -97,6 +116,8 @@ class BatchedJobShopLabEnv:
             if bool(done.any()):
                 final = {k: v.clone() for k, v in (("reward", out.reward), ("terminated", out.terminated),
                                                    ("truncated", out.truncated), ("makespan", out.makespan))}
+                if self.randomize:
+                    self._redraw(done)
                 self.batch.reset(done)
                 out.reward.copy_(final["reward"]); out.terminated.copy_(final["terminated"])
                 out.truncated.copy_(final["truncated"]); out.makespan.copy_(final["makespan"])

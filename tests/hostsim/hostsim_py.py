@@ -18,7 +18,7 @@ _lib = None
 
 def build(force=False):
     srcs = [HERE / "jsl_hostsim.cpp", ROOT / "jobshoplab_b200" / "csrc" / "jsl_engine.cuh",
-            ROOT / "jobshoplab_b200" / "csrc" / "jsl_tobj.hpp",
+            ROOT / "jobshoplab_b200" / "csrc" / "jsl_tobj.hpp", ROOT / "jobshoplab_b200" / "csrc" / "jsl_randomize.cuh",
             ROOT / "include" / "jobshoplab_b200.h"]
     if not force and LIB.exists() and LIB.stat().st_mtime >= max(s.stat().st_mtime for s in srcs):
         return LIB
@@ -60,6 +60,19 @@ def invariants():
     o = (C.c_long * 2)()
     lib().jsh_invariants(o)
     return int(o[0]), int(o[1])
+
+
+def randomize_variant(seed, variant, job_op_start, op_machine, op_tool, min_d, max_d):
+    """jsl_randomize.cuh randomize_variant on the CPU: returns (op_machine, op_tool, op_duration, job_work, lb, mat)."""
+    jos = np.ascontiguousarray(job_op_start, np.int32)
+    mt = np.ascontiguousarray(np.asarray(op_machine, np.int32) | (np.asarray(op_tool, np.int32) << 16))
+    N, J = len(mt), len(jos) - 1
+    dur, work, lm = np.zeros(N, np.int32), np.zeros(J, np.int32), np.zeros(2, np.int32)
+    L = lib()
+    L.jsh_randomize_variant.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
+    L.jsh_randomize_variant(int(seed), int(variant), J, jos.ctypes.data, int(min_d), int(max_d), mt.ctypes.data,
+                            dur.ctypes.data, work.ctypes.data, lm.ctypes.data)
+    return mt & 0xffff, mt >> 16, dur, work, int(lm[0]), int(lm[1])
 
 
 def fast_paths():

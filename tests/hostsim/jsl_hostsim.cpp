@@ -12,6 +12,7 @@
 
 #include <cmath>
 #include "../../jobshoplab_b200/csrc/jsl_engine.cuh"
+#include "../../jobshoplab_b200/csrc/jsl_randomize.cuh"
 #include "../../jobshoplab_b200/csrc/jsl_tobj.hpp"
 
 using namespace jsl;
@@ -214,6 +215,10 @@ void* jsh_create(const jsl_instance_desc* d, const jsl_env_cfg* cfg, uint64_t se
 void jsh_destroy(void* h) { delete (Sim*)h; }
 void jsh_set_tape(void* h, const int32_t* t, int n) { Sim* s = (Sim*)h; s->tape.assign(t, t + n); }
 void jsh_invariants(long* o) { o[0] = g_invariant_checks; o[1] = g_invariant_violations; }
+void jsh_randomize_variant(uint64_t seed, uint64_t variant, int J, const int32_t* job_op_start, int min_d, int max_d,
+                           int32_t* op_mt, int32_t* op_dur, int32_t* job_work, int32_t* lb_mat) {
+    randomize_variant(seed, variant, J, job_op_start, min_d, max_d, op_mt, op_dur, job_work, lb_mat);
+}
 void jsh_fast_paths(long* o) { o[0] = g_fast_start; o[1] = g_fast_complete; o[2] = g_general_batches; }
 void jsh_set_env_id(void* h, uint64_t id) { ((Sim*)h)->env_id = id; }
 void jsh_set_start_seeds(void* h, const int32_t* t, int n) { Sim* s = (Sim*)h; s->start_seeds.assign(t, t + n); }
