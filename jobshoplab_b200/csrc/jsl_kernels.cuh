@@ -228,6 +228,8 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = WARPS_PER_CTA == 1 ? 0 : warp_index();
     uint8_t* slot = smem + warp * Slot<JW, CL>::BYTES;
+    asm volatile("" : "+l"(slot));          // keep the slot address in registers instead of re-deriving it
+    __builtin_assume(__isShared(slot));
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
     void* outs_sm = bd.outs ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
     // persistent warps pull env indices from a global counter: episodes differ in length, a static
