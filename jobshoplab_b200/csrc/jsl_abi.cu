@@ -269,7 +269,7 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     int os = b->JW == 1 ? outs_bytes_jw1() : b->JW == 2 ? outs_bytes_jw2() : outs_bytes_jw4();
     b->bd.state_stride = ss;
     b->bd.outs_stride = (I.has_m_out || I.has_t_out) ? os : 0;
-    b->smem_per_warp = slot_bytes(b->JW, b->bd.classic != 0);
+    b->smem_per_warp = slot_bytes(b->JW, b->bd.outs_stride != 0);
     void* p = nullptr;
     if (cudaMalloc(&p, (size_t)B * ss) != cudaSuccess) { set_err("cudaMalloc(state) failed"); jsl_batch_destroy(b); return nullptr; }
     b->allocs.push_back(p); b->bd.state = (uint8_t*)p;
@@ -525,9 +525,11 @@ int jsl_rollout(jsl_batch_t* b, int policy, const uint8_t* action_tape, int64_t 
     if (policy == JSL_POLICY_TAPE && !action_tape) { set_err("tape policy needs an action tape"); return JSL_E_INVALID; }
     CK(cudaSetDevice(b->device));
     int smem = WARPS_PER_CTA * b->smem_per_warp;
-    if (b->rollout_ctas_per_sm == 0)
-        b->rollout_ctas_per_sm = b->JW == 1 ? rollout_occupancy_jw1(smem) : b->JW == 2 ? rollout_occupancy_jw2(smem)
-                                                                                        : rollout_occupancy_jw4(smem);
+    if (b->rollout_ctas_per_sm == 0) {
+        const bool st = b->bd.tcur != nullptr, cl = b->bd.classic != 0;
+        b->rollout_ctas_per_sm = b->JW == 1 ? rollout_occupancy_jw1(smem, st, cl)
+                                 : b->JW == 2 ? rollout_occupancy_jw2(smem, st, cl) : rollout_occupancy_jw4(smem, st, cl);
+    }
     int64_t need = (b->bd.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     int64_t persistent = (int64_t)b->sm_count * b->rollout_ctas_per_sm;  // one full wave of resident CTAs
     LaunchCfg lc = {(int)(need < persistent ? need : persistent), smem, (cudaStream_t)stream};

@@ -25,6 +25,9 @@ constexpr int WARPS_PER_CTA = JSL_WARPS_PER_CTA;
 #ifndef JSL_STEP_MIN_CTAS
 #define JSL_STEP_MIN_CTAS 24
 #endif
+#ifndef JSL_ROLLOUT_MIN_CTAS_GENERAL
+#define JSL_ROLLOUT_MIN_CTAS_GENERAL 32  // same budget for the general (non-classic) rollout kernels
+#endif
 
 struct BatchDev {
     InstDev inst;
@@ -73,25 +76,31 @@ __device__ __forceinline__ void copy_in(void* dst, const void* src, int bytes) {
     __syncwarp();
 }
 
-// per-warp shared-memory slot: EnvS | OutS (not in the classic kernels) | EnvAux -- compile-time offsets, so
-// that every address inside the slot is "slot base + immediate"
-template <int JW, bool CL>
+// per-warp shared-memory slot: EnvS | EnvAux | OutS (only for instances with outages).  The offsets inside the
+// slot are compile-time constants, so every address is "slot base + immediate"; only the slot stride of the
+// general kernels depends on the batch (a bigger slot would cost them L1 capacity for nothing).
+template <int JW>
 struct Slot {
-    static constexpr int OUTS = (int)sizeof(EnvS<JW, false, false>);
-    static constexpr int AUX = OUTS + (CL ? 0 : (int)sizeof(OutS<JW>));
-    static constexpr int BYTES = AUX + (int)sizeof(EnvAux);
+    static constexpr int AUX = (int)sizeof(EnvS<JW, false, false>);
+    static constexpr int OUTS = AUX + (int)sizeof(EnvAux);
+    static constexpr int BYTES = OUTS;                              // without outage bookkeeping
+    static constexpr int BYTES_OUTS = OUTS + (int)sizeof(OutS<JW>);  // with it
 };
-inline int slot_bytes(int JW, bool classic) {
-    return JW == 1 ? (classic ? Slot<1, true>::BYTES : Slot<1, false>::BYTES)
-         : JW == 2 ? (classic ? Slot<2, true>::BYTES : Slot<2, false>::BYTES)
-                   : (classic ? Slot<4, true>::BYTES : Slot<4, false>::BYTES);
+inline int slot_bytes(int JW, bool has_outs) {
+    return JW == 1 ? (has_outs ? Slot<1>::BYTES_OUTS : Slot<1>::BYTES)
+         : JW == 2 ? (has_outs ? Slot<2>::BYTES_OUTS : Slot<2>::BYTES)
+                   : (has_outs ? Slot<4>::BYTES_OUTS : Slot<4>::BYTES);
+}
+template <int JW, bool CL>
+__device__ __forceinline__ int slot_stride(const BatchDev& bd) {
+    return (CL || !bd.outs) ? Slot<JW>::BYTES : Slot<JW>::BYTES_OUTS;
 }
 
 template <int JW, bool ST, bool CL>
 __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env, uint8_t* slot) {
     const InstDev& I = bd.inst;
     const int64_t v = I.n_inst == 1 ? 0 : (env < I.n_inst ? env : (int64_t)((uint64_t)env % (uint32_t)I.n_inst));
-    EnvAux* aux = (EnvAux*)(slot + Slot<JW, CL>::AUX);
+    EnvAux* aux = (EnvAux*)(slot + Slot<JW>::AUX);
     c.I = &bd.inst;
     c.C = &bd.cfg;
     c.aux = aux;
@@ -103,7 +112,7 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
     aux->op_dur = I.op_dur + v * I.N;
     aux->job_work = I.job_work + v * I.J;
     aux->op_log = bd.op_log ? bd.op_log + env * 2 * (int64_t)I.N : nullptr;
-    aux->outs = (!CL && bd.outs) ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
+    aux->outs = (!CL && bd.outs) ? (void*)(slot + Slot<JW>::OUTS) : nullptr;
     if (ST) {
         aux->tcur = bd.tcur + env * (int64_t)I.n_tobj;
         aux->tseed = bd.tseed ? bd.tseed + env * (int64_t)I.n_tobj : nullptr;
@@ -166,9 +175,9 @@ k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, j
     const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
     if (env >= bd.B) return;
     if (mask && !mask[env]) return;
-    uint8_t* slot = smem + warp * Slot<JW, CL>::BYTES;
+    uint8_t* slot = smem + warp * slot_stride<JW, CL>(bd);
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
-    void* outs_sm = bd.outs ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
+    void* outs_sm = bd.outs ? (void*)(slot + Slot<JW>::OUTS) : nullptr;
     Ctx c;
     make_ctx<JW, ST, CL>(c, bd, env, slot);
     run_env_op(s, c, OP_RESET);
@@ -186,9 +195,9 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     const int warp = WARPS_PER_CTA == 1 ? 0 : warp_index();
     const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
     if (env >= bd.B) return;
-    uint8_t* slot = smem + warp * Slot<JW, CL>::BYTES;
+    uint8_t* slot = smem + warp * slot_stride<JW, CL>(bd);
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
-    void* outs_sm = bd.outs ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
+    void* outs_sm = bd.outs ? (void*)(slot + Slot<JW>::OUTS) : nullptr;
     uint8_t* g_state = bd.state + env * (int64_t)bd.state_stride;
     uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
     copy_fixed<(int)sizeof(EnvS<JW, ST, CL>)>(&s, g_state);
@@ -222,16 +231,16 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
 }
 
 template <int JW, bool ST, bool CL>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_ROLLOUT_MIN_CTAS)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CL ? JSL_ROLLOUT_MIN_CTAS : JSL_ROLLOUT_MIN_CTAS_GENERAL)
 k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __restrict__ tape, int64_t tape_stride,
           int max_steps, int flags, jsl_rollout_out out) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = WARPS_PER_CTA == 1 ? 0 : warp_index();
-    uint8_t* slot = smem + warp * Slot<JW, CL>::BYTES;
+    uint8_t* slot = smem + warp * slot_stride<JW, CL>(bd);
     asm volatile("" : "+l"(slot));          // keep the slot address in registers instead of re-deriving it
     __builtin_assume(__isShared(slot));
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
-    void* outs_sm = bd.outs ? (void*)(slot + Slot<JW, CL>::OUTS) : nullptr;
+    void* outs_sm = bd.outs ? (void*)(slot + Slot<JW>::OUTS) : nullptr;
     // persistent warps pull env indices from a global counter: episodes differ in length, a static
     // grid-stride split leaves the tail of the launch half empty
     for (;;) {
@@ -294,7 +303,7 @@ k_digest(const __grid_constant__ BatchDev bd, int64_t env, int32_t* out, int cap
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* slot = smem;
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)smem;
-    void* outs_sm = bd.outs ? (void*)(smem + Slot<JW, CL>::OUTS) : nullptr;
+    void* outs_sm = bd.outs ? (void*)(smem + Slot<JW>::OUTS) : nullptr;
     copy_in(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
     if (bd.outs) copy_in(outs_sm, bd.outs + env * (int64_t)bd.outs_stride, bd.outs_stride);
     Ctx c;
@@ -348,7 +357,7 @@ int rollout_occupancy(int smem) {  // resident CTAs per SM for the persistent ro
     cudaError_t launch_rollout_jw##N(const BatchDev&, const LaunchCfg&, int, const uint8_t*, int64_t, int, int,      \
                                      jsl_rollout_out);                                                                \
     cudaError_t launch_digest_jw##N(const BatchDev&, const LaunchCfg&, int64_t, int32_t*, int, int32_t*);            \
-    int rollout_occupancy_jw##N(int smem);                                                                            \
+    int rollout_occupancy_jw##N(int smem, bool stochastic, bool classic);                                                                            \
     int state_bytes_jw##N();                                                                                          \
     int outs_bytes_jw##N();
 JSL_DECLARE_JW(1)
@@ -377,7 +386,10 @@ JSL_DECLARE_JW(4)
                : bd.classic ? launch_digest<N, false, true>(bd, lc, e, o, c, n)                                  \
                             : launch_digest<N, false, false>(bd, lc, e, o, c, n);                                                                  \
     }                                                                                                                 \
-    int rollout_occupancy_jw##N(int smem) { return rollout_occupancy<N, false, false>(smem); }                                      \
+    int rollout_occupancy_jw##N(int smem, bool st, bool cl) {                                                         \
+        return st ? rollout_occupancy<N, true, false>(smem) : cl ? rollout_occupancy<N, false, true>(smem)           \
+                                                                 : rollout_occupancy<N, false, false>(smem);           \
+    }                                      \
     int state_bytes_jw##N() { return (int)sizeof(EnvS<N, false, false>); }                                                          \
     int outs_bytes_jw##N() { return (int)sizeof(OutS<N>); }
 

@@ -36,7 +36,9 @@ def timed(batch, policy, reps=3):
 
 
 def main():
-    for inst in ("ft10", "la16", "ta01", "ta41"):
+    import os
+    only_general = os.environ.get("JSL_SECONDARY") == "general"
+    for inst in (() if only_general else ("ft10", "la16", "ta01", "ta41")):
         li = compiler.compile_spec_text(G.Scenario("classic", f"{inst}/fifo").source_text)
         batch = engine.Batch(li, B)
         for pol in ("spt", "mwkr", "fifo", "random"):
