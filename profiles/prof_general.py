@@ -1,0 +1,22 @@
+"""Workload for ncu captures of the general (non-classic) kernels: ta41-t (30x20 with travel times) replicas,
+3 fused rollouts under the random policy.
+
+    python profiles/prof_general.py [envs]
+"""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import _golden as G  # noqa: E402
+from jobshoplab_b200 import compiler, engine  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+li = compiler.compile_dsl_text(G.Scenario("transport", "ta41-t/fifo").source_text)
+batch = engine.Batch(li, B)
+for _ in range(3):
+    r = batch.rollout("random", reset_first=True, writeback=False)
+torch.cuda.synchronize()
+print("rollout env-steps per launch:", int(r.n_steps.sum()))
