@@ -266,6 +266,14 @@ int jsl_get_state(jsl_batch_t*, int64_t idx, int32_t* host_out, int cap);
 /* Per-op (start,end) log of env idx, host int32 [n_ops][2]; needs cfg.record_ops. */
 int jsl_get_op_log(jsl_batch_t*, int64_t idx, int32_t* host_out);
 
+/* Transport tasks of env idx in creation order, what env.render() draws for the AGVs
+ * (rendering/gant_dashboard.py:299-359): host int32 [n][5] = agv (< 0: a task that ran entirely inside
+ * env.reset, which keeps no history), job, start, end (-1: no time),
+ * route = place | pickup buffer idx << 8 | drop place << 24.  Needs cfg.record_ops and the logging build of the
+ * library (libjsl_b200_log.so: same sources with -DJSL_LEG_LOG, same ABI; the throughput build compiles the
+ * logging out and answers JSL_E_UNSUPPORTED).  Returns n (<= cap) or a negative error (JSL_E_NOMEM: overflow). */
+int jsl_get_leg_log(jsl_batch_t*, int64_t idx, int32_t* host_out, int cap);
+
 /* How many kernels this batch has launched so far (bench.py "gpu_launches"). */
 int64_t jsl_launch_count(const jsl_batch_t*);
 

@@ -17,6 +17,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / "csrc"
 INCLUDE = Path(__file__).resolve().parent.parent / "include"
 LIB = Path(os.environ.get("JSL_LIB_OUT", CSRC / "libjsl_b200.so"))
+LOG_LIB = CSRC / "libjsl_b200_log.so"
 EXTRA = os.environ.get("JSL_NVCC_EXTRA", "").split()
 OBJ_TAG = os.environ.get("JSL_OBJ_TAG", "")
 UNITS = ["jsl_abi.cu", "jsl_kernels_jw1.cu", "jsl_kernels_jw2.cu", "jsl_kernels_jw4.cu"]
@@ -32,24 +33,34 @@ def nvcc() -> str:
     return exe
 
 
-def _compile(unit: str, force: bool) -> Path:
-    src, obj = CSRC / unit, CSRC / (unit[:-3] + OBJ_TAG + ".o")
+def _compile(unit: str, force: bool, tag: str = "", extra=()) -> Path:
+    tag = OBJ_TAG + tag
+    src, obj = CSRC / unit, CSRC / (unit[:-3] + tag + ".o")
     newest = max(p.stat().st_mtime for p in [src, *HEADERS])
     if not force and obj.exists() and obj.stat().st_mtime >= newest:
         return obj
-    log = subprocess.run([nvcc(), *NVCC_FLAGS, *EXTRA, "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
-    (CSRC / (unit[:-3] + OBJ_TAG + ".ptxas.log")).write_text(log.stderr)
+    log = subprocess.run([nvcc(), *NVCC_FLAGS, *EXTRA, *extra, "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
+    (CSRC / (unit[:-3] + tag + ".ptxas.log")).write_text(log.stderr)
     if log.returncode != 0:
         raise RuntimeError(f"nvcc failed for {unit}:\n{log.stderr[-4000:]}")
     return obj
 
 
-def build(force: bool = False) -> Path:
-    with ThreadPoolExecutor(len(UNITS)) as ex:
-        objs = list(ex.map(lambda u: _compile(u, force), UNITS))
-    if force or not LIB.exists() or LIB.stat().st_mtime < max(o.stat().st_mtime for o in objs):
-        subprocess.check_call([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB),
+def _link(lib: Path, objs, force: bool):
+    if force or not lib.exists() or lib.stat().st_mtime < max(o.stat().st_mtime for o in objs):
+        subprocess.check_call([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(lib),
                                *map(str, objs), "-lcudart"])
+
+
+def build(force: bool = False) -> Path:
+    """libjsl_b200.so (throughput build) and libjsl_b200_log.so (same sources with -DJSL_LEG_LOG: keeps the
+    transport-task log env.render() needs; used for batches created with record_ops)."""
+    jobs = [(u, "", ()) for u in UNITS] + ([] if OBJ_TAG else [(u, "_log", ("-DJSL_LEG_LOG",)) for u in UNITS])
+    with ThreadPoolExecutor(len(jobs)) as ex:
+        objs = list(ex.map(lambda j: _compile(j[0], force, j[1], j[2]), jobs))
+    _link(LIB, objs[:len(UNITS)], force)
+    if not OBJ_TAG:
+        _link(LOG_LIB, objs[len(UNITS):], force)
     return LIB
 
 

@@ -290,6 +290,12 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
         if (cudaMalloc(&p, (size_t)B * N * 2 * sizeof(int32_t)) != cudaSuccess) { set_err("cudaMalloc(op_log) failed"); jsl_batch_destroy(b); return nullptr; }
         b->allocs.push_back(p); b->bd.op_log = (int32_t*)p;
     }
+    if (cfg->record_ops && LEG_LOG_BUILD) {  // (not for the op log the Tassel observation needs on big batches)
+        b->bd.leg_stride = 2 + 32 * b->JW + 5 * (N + 2 * I.J + 8);
+        if (cudaMalloc(&p, (size_t)B * b->bd.leg_stride * sizeof(int32_t)) != cudaSuccess) { set_err("cudaMalloc(leg_log) failed"); jsl_batch_destroy(b); return nullptr; }
+        b->allocs.push_back(p); b->bd.leg_log = (int32_t*)p;
+        cudaMemset(p, 0, (size_t)B * b->bd.leg_stride * sizeof(int32_t));
+    }
     b->obs_bytes = cfg->obs_kind == JSL_OBS_BINARY_ACTION ? obs_bytes_binary(t->J, t->M)
                    : cfg->obs_kind == JSL_OBS_OPERATION_ARRAY ? obs_bytes_oparray(t->J, t->N)
                    : cfg->obs_kind == JSL_OBS_TASSEL ? obs_bytes_tassel(t->J) : 0;
@@ -550,6 +556,20 @@ int jsl_get_state(jsl_batch_t* b, int64_t idx, int32_t* host_out, int cap) {
     if (m > b->digest_cap) m = b->digest_cap;
     CK(cudaMemcpy(host_out, b->d_digest, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return n;
+}
+
+int jsl_get_leg_log(jsl_batch_t* b, int64_t idx, int32_t* host_out, int cap) {
+    if (!b || !host_out || idx < 0 || idx >= b->bd.B) return JSL_E_INVALID;
+    if (!LEG_LOG_BUILD) { set_err("this build has no transport-task log: use libjsl_b200_log.so"); return JSL_E_UNSUPPORTED; }
+    if (!b->bd.leg_log) { set_err("batch was created without record_ops"); return JSL_E_INVALID; }
+    CK(cudaSetDevice(b->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<int32_t> raw(b->bd.leg_stride);
+    CK(cudaMemcpy(raw.data(), b->bd.leg_log + idx * (int64_t)b->bd.leg_stride, raw.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    const int n = raw[0], hdr = 2 + 32 * b->JW;
+    if (n > cap) return JSL_E_INVALID;
+    std::memcpy(host_out, raw.data() + hdr, (size_t)n * 5 * sizeof(int32_t));
+    return raw[1] ? JSL_E_NOMEM : n;
 }
 
 int jsl_get_op_log(jsl_batch_t* b, int64_t idx, int32_t* host_out) {

@@ -203,7 +203,8 @@ struct alignas(16) EnvAux {
     int32_t lower_bound, max_allowed_time;
     uint32_t act_block;          // RANDOM policy: 1 + index of the 32-step block whose actions are in act_bits (0 = none)
     uint32_t act_bits;
-    int32_t pad[3];
+    int32_t pad;
+    int32_t* leg_log;            // transport-task log of this env (see LegLog) or nullptr
 };
 
 // per-call context: the few uniform values the hot loop keeps in registers
@@ -213,6 +214,7 @@ struct Ctx {
     EnvAux* aux;
     int raise;              // JSL_ST_* of an escaping exception, 0 = none
     int now;
+    bool log;               // aux->leg_log is set (derived from a kernel parameter: free to test)
 };
 
 #define JSL_UNLIKELY(x) __builtin_expect(!!(x), 0)
@@ -845,6 +847,69 @@ JSL_D bool apply_machine(EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int job) {
     return true;
 }
 
+// ------------------------------------------------------------------------------------ transport-task log
+// What env.render() needs of the transports (rendering/gant_dashboard.py:299-359): one record per transport task
+// -- the states an AGV passes through between IDLE->PICKUP and the drop-off share one `location` triple -- with
+//   start = `time` of the first recorded state carrying the triple.  state.py:199/266 records a state after the
+//           action's transitions (time unchanged) and after every batch of the loop once jump_to_event has run,
+//           so a task created inside the loop starts at the post-jump time (LEG_PENDING until then);
+//   end   = occupied_till of the last such state (the TRANSIT state's arrival time for a finished task);
+//   job, route = transport_job and the triple.
+// Layout (int32): [0] count, [1] overflow, [2 .. 2+MT) open record of each AGV (-1), then 5 per record:
+// agv (< 0: not visible, see run_env_op), job, start, end, route = place | pickup buffer << 8 | drop place << 24.
+// Only with cfg.record_ops.
+constexpr int LEG_PENDING = -2, LEG_NO_TIME = -1;
+JSL_D int leg_hdr(int MT) { return 2 + MT; }
+// Compiled in only with -DJSL_LEG_LOG (libjsl_b200_log.so, used for batches created with record_ops): even a
+// never-taken branch per transition costs the throughput kernels ~5 % of their instruction budget.
+#ifdef JSL_LEG_LOG
+template <int JW, bool ST, bool CL>
+JSL_D void leg_open(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j, int start, int end) {
+    if (!c.log) return;
+    int32_t* g = c.aux->leg_log;
+    constexpr int MT = EnvS<JW, ST, CL>::MT;
+    const int cap = c.I->N + 2 * c.I->J + 8;
+    const int idx = g[0];
+    if (idx >= cap) { g[1] = 1; g[2 + t] = -1; return; }
+    int32_t* e = g + leg_hdr(MT) + 5 * idx;
+    e[0] = t; e[1] = j; e[2] = start; e[3] = end;
+    e[4] = (int)s.t_loc0[t] | ((int)s.t_loc1[t] << 8) | ((int)s.t_loc2[t] << 24);
+    g[2 + t] = idx;
+    g[0] = idx + 1;
+}
+template <int JW, bool ST, bool CL>
+JSL_D void leg_end(EnvS<JW, ST, CL>& s, Ctx& c, int t, int end, bool close) {
+    if (!c.log) return;
+    int32_t* g = c.aux->leg_log;
+    constexpr int MT = EnvS<JW, ST, CL>::MT;
+    const int idx = g[2 + t];
+    if (idx >= 0 && end != LEG_PENDING) g[leg_hdr(MT) + 5 * idx + 3] = end;
+    if (close) g[2 + t] = -1;
+}
+// the state after the current batch is recorded at time `now`: tasks opened in it start there
+template <int JW, bool ST, bool CL>
+JSL_D void leg_stamp(EnvS<JW, ST, CL>& s, Ctx& c) {
+    if (!c.log) return;
+    int32_t* g = c.aux->leg_log;
+    constexpr int MT = EnvS<JW, ST, CL>::MT;
+    const int now = c.now;
+    JSL_SYNCWARP();
+    wp_for<JW>(c.I->T, [&](int t) {
+        const int idx = g[2 + t];
+        if (idx >= 0 && g[leg_hdr(MT) + 5 * idx + 2] == LEG_PENDING) g[leg_hdr(MT) + 5 * idx + 2] = now;
+    });
+}
+constexpr bool LEG_LOG_BUILD = true;
+#else
+template <int JW, bool ST, bool CL>
+JSL_D void leg_open(EnvS<JW, ST, CL>&, Ctx&, int, int, int, int) {}
+template <int JW, bool ST, bool CL>
+JSL_D void leg_end(EnvS<JW, ST, CL>&, Ctx&, int, int, bool) {}
+template <int JW, bool ST, bool CL>
+JSL_D void leg_stamp(EnvS<JW, ST, CL>&, Ctx&) {}
+constexpr bool LEG_LOG_BUILD = false;
+#endif
+
 // ------------------------------------------------------------------------------------ transport handlers
 // validate.py:85-118 + transitions.py:82-107,161-186
 template <int JW, bool ST, bool CL>
@@ -883,6 +948,7 @@ JSL_D void agv_idle_to_working(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     s.t_state[t] = JSL_T_PICKUP;
     s.t_job[t] = (uint8_t)j;
     s.j_agv[j] = (uint8_t)t;
+    leg_open(s, c, t, j, LEG_PENDING, c.now + ttp);
 }
 
 // handler.py:577-639 _get_waiting_time, :642-702, :989-1030
@@ -917,6 +983,7 @@ JSL_D void agv_to_waitingpickup(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     }
     s.t_occkind[t] = (uint8_t)kind; s.t_occ[t] = val;
     s.t_state[t] = JSL_T_WAITINGPICKUP;
+    leg_end(s, c, t, kind == OCC_TIME ? val : LEG_NO_TIME, false);
 }
 
 // handler.py:705-805 (waiting)pickup -> transit
@@ -944,6 +1011,7 @@ JSL_D void agv_to_transit(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     s.t_carry[t] = (uint8_t)j;
     s.t_state[t] = JSL_T_TRANSIT;
     s.t_occkind[t] = OCC_TIME; s.t_occ[t] = c.now + travel;
+    leg_end(s, c, t, c.now + travel, false);
 }
 
 // handler.py:905-958 + manipulate.py:45-114 transit -> outage (drop-off)
@@ -970,6 +1038,7 @@ JSL_D void agv_transit_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     s.t_lockind[t] = 0; s.t_loc0[t] = (uint8_t)dest;
     s.j_agv[j] = NONE8;
     s.t_job[t] = NONE8;
+    leg_end(s, c, t, LEG_PENDING, true);
 }
 
 // process one transport transition; false = validation error
@@ -1133,6 +1202,7 @@ JSL_D bool classic_start(EnvS<JW, ST, CL>& s, Ctx& c, const Trans& act) {
             s.t_state[a] = JSL_T_WAITINGPICKUP;
             s.t_job[a] = (uint8_t)j;
             s.j_agv[j] = (uint8_t)a;
+            leg_open(s, c, a, j, now, end);
             p.idle.w[a >> 5] &= ~(1u << (a & 31));
         } else {
             p.lr.w[j >> 5] |= 1u << (j & 31);
@@ -1209,6 +1279,7 @@ JSL_D bool classic_complete(EnvS<JW, ST, CL>& s, Ctx& c, const Mask<1>& mm, cons
         s.t_occkind[t] = OCC_TIME; s.t_occ[t] = now;
         s.t_lockind[t] = 0; s.t_loc0[t] = (uint8_t)dest;
         s.t_job[t] = NONE8;
+        leg_end(s, c, t, now, true);
     });
     s.seq_ctr = seq0 + nm + tm.count();
     JSL_SYNCWARP();
@@ -1295,6 +1366,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                     if (t2 != c.now) {  // re-evaluate the timed transitions at the new time
                         c.now = t2;
                         evaluated = true;
+                        leg_stamp(s, c);
                         if (++guard > 100000) { c.raise = JSL_ST_OTHER_INVALID; return true; }
                         continue;
                     }
@@ -1311,6 +1383,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
             }
 #endif
             evaluated = false;
+            leg_stamp(s, c);
             const Poss<JW> p = cached_poss(s);
             if (first && p.idle.any() && (p.lr.any() || p.li.any())) {
                 // teleports (state.py:229-232, :414-467): i-th idle AGV <- i-th lonely job with zero travel time
@@ -1385,7 +1458,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
 #pragma unroll
         for (int w = 0; w < JW; w++) { tm.w[w] = 0; tele.w[w] = 0; }
         JSL_SYNCWARP();
-        if (action_stage) action_stage = false;
+        if (action_stage) { action_stage = false; leg_stamp(s, c); }
         else first = false;
         if (++guard > 100000) { c.raise = JSL_ST_OTHER_INVALID; return true; }  // the reference would spin
     }
@@ -1539,6 +1612,10 @@ JSL_D double run_env_op(EnvS<JW, ST, CL>& s, Ctx& c, int op) {
     if (op == OP_RESET) {
         env_init(s, c);
         if (c.aux->op_log) wp_for_dyn(2 * c.I->N, [&](int i) { c.aux->op_log[i] = -1; });
+        if (LEG_LOG_BUILD && c.log) {
+            int32_t* g = c.aux->leg_log;
+            wp_for_dyn(leg_hdr(EnvS<JW, ST, CL>::MT), [&](int i) { g[i] = i < 2 ? 0 : -1; });
+        }
         plan.run_sm = true; plan.has_action = false; plan.time_machine = TM_JUMP;
         plan.act.kind = 0; plan.act.comp = 0; plan.act.new_state = 0; plan.act.job = 0;
     } else if (!env_step_pre(s, c, op, plan)) {
@@ -1547,6 +1624,19 @@ JSL_D double run_env_op(EnvS<JW, ST, CL>& s, Ctx& c, int op) {
     bool success = true;
     if (plan.run_sm) success = sm_step(s, c, plan.has_action, plan.act, plan.time_machine);
     if (op == OP_RESET) {
+        if (LEG_LOG_BUILD && c.log) {
+            // env.reset keeps no history (env.py:536): tasks that ran to their end inside the reset step are
+            // never seen (marked agv < 0), open ones are first seen in the state the next env.step starts from
+            int32_t* g = c.aux->leg_log;
+            constexpr int MT = EnvS<JW, ST, CL>::MT;
+            const int n = g[0], t0 = s.time;
+            JSL_SYNCWARP();
+            wp_for_dyn(n, [&](int i) {
+                int32_t* e = g + leg_hdr(MT) + 5 * i;
+                if (g[2 + e[0]] == i) e[2] = t0;
+                else e[0] = -1 - e[0];
+            });
+        }
         if (c.raise) s.status = c.raise;
         else if (!success) { s.n_possible = 0; s.skip = 0; }
         return 0.0;

@@ -36,6 +36,8 @@ struct BatchDev {
     uint8_t* state;      // [B][state_stride]
     uint8_t* outs;       // [B][outs_stride] or nullptr
     int32_t* op_log;     // [B][N][2] or nullptr
+    int32_t* leg_log;    // [B][leg_stride] transport-task log (jsl_engine.cuh) or nullptr
+    int leg_stride;
     int state_stride, outs_stride;
     uint64_t seed;
     int64_t env_base;    // global index of env 0 (RANDOM policy stream id)
@@ -106,12 +108,14 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
     c.aux = aux;
     c.raise = 0;
     c.now = 0;
+    c.log = LEG_LOG_BUILD && bd.leg_log != nullptr;
     __syncwarp();
     // every lane stores the same (warp-uniform) values: no divergent single-lane section
     aux->op_mt = I.op_mt + v * I.N;
     aux->op_dur = I.op_dur + v * I.N;
     aux->job_work = I.job_work + v * I.J;
     aux->op_log = bd.op_log ? bd.op_log + env * 2 * (int64_t)I.N : nullptr;
+    aux->leg_log = bd.leg_log ? bd.leg_log + env * (int64_t)bd.leg_stride : nullptr;
     aux->outs = (!CL && bd.outs) ? (void*)(slot + Slot<JW>::OUTS) : nullptr;
     if (ST) {
         aux->tcur = bd.tcur + env * (int64_t)I.n_tobj;

@@ -19,24 +19,27 @@ from .lowered import LoweredInstance
 import os
 
 LIB_PATH = Path(os.environ.get("JSL_LIB", Path(__file__).resolve().parent / "csrc" / "libjsl_b200.so"))
+LOG_LIB_PATH = Path(os.environ.get("JSL_LOG_LIB", Path(__file__).resolve().parent / "csrc" / "libjsl_b200_log.so"))
+_libs: dict = {}
 _lib = None
 
 ABI_SYMBOLS = ("jsl_last_error", "jsl_abi_version", "jsl_instance_create", "jsl_instance_destroy", "jsl_batch_create",
                "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_randomize", "jsl_batch_get_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
-               "jsl_reset", "jsl_step", "jsl_rollout", "jsl_get_state", "jsl_get_op_log", "jsl_launch_count")
+               "jsl_reset", "jsl_step", "jsl_rollout", "jsl_get_state", "jsl_get_op_log", "jsl_get_leg_log", "jsl_launch_count")
 
 RO_RESET_FIRST, RO_NO_WRITEBACK = 1, 2
 
 
-def load_library():
-    """dlopen the engine; raises EngineUnavailable (never falls back to anything else)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not LIB_PATH.exists():
-        raise EngineUnavailable(f"{LIB_PATH} is missing: build it with `python -m jobshoplab_b200.build` "
+def load_library(log: bool = False):
+    """dlopen the engine; raises EngineUnavailable (never falls back to anything else).  `log`: the build that
+    keeps the transport-task log (libjsl_b200_log.so, same ABI), used for batches created with record_ops."""
+    if _libs.get(log) is not None:
+        return _libs[log]
+    path = LOG_LIB_PATH if log else LIB_PATH
+    if not path.exists():
+        raise EngineUnavailable(f"{path} is missing: build it with `python -m jobshoplab_b200.build` "
                                 "(there is no CPU fallback)")
-    L = C.CDLL(str(LIB_PATH))
+    L = C.CDLL(str(path))
     L.jsl_last_error.restype = C.c_char_p
     L.jsl_abi_version.restype = C.c_int
     L.jsl_instance_create.restype = C.c_void_p
@@ -61,11 +64,12 @@ def load_library():
     L.jsl_rollout.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, abi.RolloutOut, C.c_void_p]
     L.jsl_get_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
     L.jsl_get_op_log.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.jsl_get_leg_log.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
     L.jsl_launch_count.restype = C.c_int64
     L.jsl_launch_count.argtypes = [C.c_void_p]
     if L.jsl_abi_version() != abi.ABI_VERSION:
-        raise EngineUnavailable("libjsl_b200.so ABI version mismatch: rebuild it")
-    _lib = L
+        raise EngineUnavailable(f"{path.name} ABI version mismatch: rebuild it")
+    _libs[log] = L
     return L
 
 
@@ -84,8 +88,8 @@ def _torch():
 class Instance:
     """jsl_instance_t for one LoweredInstance."""
 
-    def __init__(self, lowered: LoweredInstance):
-        self.L = load_library()
+    def __init__(self, lowered: LoweredInstance, log: bool = False):
+        self.L = load_library(log)
         self.lowered = lowered
         self._desc = abi.make_desc(lowered)
         self.h = self.L.jsl_instance_create(C.byref(self._desc))
@@ -125,14 +129,14 @@ class Batch:
     def __init__(self, lowered, B: int, device: int = 0, seed: int = 0, variants=None, **cfg):
         torch = _torch()
         self.torch = torch
-        self.L = load_library()
+        self.L = load_library(log=bool(cfg.get("record_ops")))
         self.B = int(B)
         self.device = int(device)
         self.cfg = abi.make_cfg(**cfg)
         if isinstance(lowered, LoweredInstance):
             lowered = [lowered]
         self.lowered = list(lowered)
-        self.instances = [Instance(li) for li in self.lowered]
+        self.instances = [Instance(li, log=bool(cfg.get("record_ops"))) for li in self.lowered]
         if variants is not None:
             om, od, lb, mat = (np.ascontiguousarray(a, dtype=np.int32) for a in variants)
             n_inst = om.shape[0]
@@ -285,6 +289,16 @@ class Batch:
         if n < 0:
             raise InvalidValue("jsl_get_state", n, _err(self.L))
         return out[:n].copy()
+
+    def get_leg_log(self, idx: int) -> np.ndarray:
+        """Transport tasks of env idx: int32 [n][5] = agv (< 0: invisible to env.history), job, start, end, route
+        (jsl_get_leg_log; needs record_ops)."""
+        cap = self.shape.n_ops + 2 * self.shape.n_jobs + 8
+        out = np.zeros((cap, 5), dtype=np.int32)
+        n = self.L.jsl_get_leg_log(self.h, int(idx), out.ctypes.data, cap)
+        if n < 0:
+            raise InvalidValue("leg log", n, _err(self.L))
+        return out[:n]
 
     def get_op_log(self, idx: int) -> np.ndarray:
         out = np.zeros((self.shape.n_ops, 2), dtype=np.int32)

@@ -248,17 +248,23 @@ class JobShopLabEnv:
         """Per-op (start, end) times so far -- what render() / the Gantt dashboard consume (8(f)1)."""
         return self._batch.get_op_log(0)
 
+    def gantt_data(self) -> dict:
+        """The data model of the reference's dashboard, DashboardDataMapper.map_states_to_gant_data(env.history)
+        (rendering/gant_dashboard.py:414-429): {"schedules", "transports", "buffer"} -- rebuilt from the engine's
+        state digest and transport-task log instead of a history of states (8(f)1).  Feed it to the reference's
+        JobShopDashboard(data=..., ...) to get the Dash / Plotly view."""
+        from .state_view import gantt_data
+        return gantt_data(self.instance, self.state, self._batch.get_leg_log(0))
+
     def render(self, mode: str = "normal"):
-        """Text Gantt of the finished operations (the reference's Dash dashboard is out of scope)."""
-        log = self.op_log()
-        li = self.instance
-        rows = []
-        for j in range(li.n_jobs):
-            for k in range(int(li.job_op_start[j + 1] - li.job_op_start[j])):
-                o = int(li.job_op_start[j]) + k
-                if log[o, 1] >= 0:
-                    rows.append((int(log[o, 0]), int(log[o, 1]), f"m-{int(li.op_machine[o])}", f"j-{j}", f"o-{j}-{k}"))
-        text = "\n".join(f"{a:>8} {b:>8}  {m:<6} {j:<6} {o}" for a, b, m, j, o in sorted(rows))
+        """Text Gantt of the same bars the reference's dashboard draws (machines, then transports); the Dash
+        application itself is out of scope.  Returns the text."""
+        data = self.gantt_data()
+        rows = [(d["start"], d["end"], d["id"], d["job"], "") for d in data["schedules"]]
+        rows += [(d["start"], d["end"] if d["end"] is not None else -1, d["id"], d["job"], d["meta_info"])
+                 for d in data["transports"]]
+        key = lambda r: (r[2][0] != "m", int(r[2][2:]), r[0])
+        text = "\n".join(f"{a:>8} {b:>8}  {c:<6} {j:<6} {info}".rstrip() for a, b, c, j, info in sorted(rows, key=key))
         print(text)
         return text
 

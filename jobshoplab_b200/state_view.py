@@ -138,3 +138,46 @@ def parse_digest(li, d: np.ndarray) -> ResultView:
         poss.append(ComponentTransition(f"m-{comp}" if kind == 0 else f"t-{comp}",
                                         M_STATES[ns] if kind == 0 else T_STATES[ns], None if job < 0 else f"j-{job}"))
     return ResultView(StateView(Time(time), tuple(jobs), tuple(machines), tuple(transports), buffers), tuple(poss))
+
+
+def gantt_data(li, view: ResultView, legs: np.ndarray) -> dict:
+    """rendering/gant_dashboard.py:414-429 map_states_to_gant_data: what the reference's dashboard draws.
+    `view`: the current state (parse_digest), `legs`: the transport-task log (jsl_get_leg_log, int32 [n][5]).
+
+    schedules  (:250-296) DONE operations of every job, then its PROCESSING one, from the last state;
+    transports (:299-359) per AGV in id order, one bar per run of recorded non-idle states sharing a route
+               (consecutive tasks with the same route therefore merge: start of the first, job / end of the last);
+    buffer     (:362-376) not implemented upstream: ()."""
+    M, T = li.n_machines, li.n_transports
+
+    def buf_name(b):
+        return f"b-{int(li.buf_ref_id[b])}"
+
+    def place_name(x):
+        return f"m-{x}" if x < M else buf_name(3 * M + T + (x - M))
+
+    schedules = []
+    for job in view.state.jobs:
+        for op in job.operations:
+            if op.state == "Done":
+                schedules.append({"job": job.id, "start": op.start_time, "end": op.end_time, "id": op.machine_id,
+                                  "type": "Schedule", "meta_info": None})
+        active = next((op for op in job.operations if op.state == "Processing"), None)
+        if active is not None:
+            schedules.append({"job": job.id, "start": active.start_time, "end": active.end_time, "id": active.machine_id,
+                              "type": "Schedule", "meta_info": None})
+    transports = []
+    legs = np.asarray(legs, dtype=np.int64).reshape(-1, 5)
+    for t in range(T):
+        prev = None
+        for agv, job, start, end, route in legs[legs[:, 0] == t]:
+            loc = (place_name(int(route & 0xff)), buf_name(int((route >> 8) & 0xffff)), place_name(int((route >> 24) & 0xff)))
+            if prev is not None and prev["_loc"] == loc:
+                prev["job"], prev["end"] = f"j-{job}", (None if end < 0 else int(end))
+                continue
+            prev = {"type": "Transport", "id": f"t-{t}", "job": f"j-{job}", "start": int(start),
+                    "end": None if end < 0 else int(end), "meta_info": f"route: {loc}", "_loc": loc}
+            transports.append(prev)
+    for d in transports:
+        del d["_loc"]
+    return {"schedules": tuple(schedules), "transports": tuple(transports), "buffer": ()}

@@ -23,7 +23,7 @@ def build(force=False):
     if not force and LIB.exists() and LIB.stat().st_mtime >= max(s.stat().st_mtime for s in srcs):
         return LIB
     subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
-                           "-Wno-unknown-pragmas", "-o", str(LIB), str(srcs[0])])
+                           "-Wno-unknown-pragmas", "-DJSL_LEG_LOG", "-o", str(LIB), str(srcs[0])])
     return LIB
 
 
@@ -140,6 +140,14 @@ class HostSimEnv:
         if n < 0:
             raise RuntimeError(f"obs raised status {-n}")
         return out[:n].tobytes()
+
+    def leg_log(self):
+        cap = self.li.n_ops + 2 * self.li.n_jobs + 8
+        out = np.zeros((cap, 5), dtype=np.int32)
+        self.L.jsh_leg_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        n = self.L.jsh_leg_log(self.h, out.ctypes.data, cap)
+        assert n >= 0, n
+        return out[:n]
 
     def rollout(self, policy, tape=None, max_steps=1 << 30, env_idx=0):
         if tape is not None:

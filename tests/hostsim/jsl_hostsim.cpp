@@ -28,7 +28,7 @@ struct Sim {
     std::vector<uint8_t> pre_type, post_type, sbuf_type, sbuf_role, agv_init_place, job_lex, mach_lex;
     std::vector<uint16_t> job_init_buf;
     std::vector<float> tr_comp, tr_job;
-    std::vector<int32_t> op_log;
+    std::vector<int32_t> op_log, leg_log;
     std::vector<uint8_t> state, backup, outs, outs_backup;
     int state_bytes, outs_bytes;
     uint64_t seed;
@@ -67,6 +67,8 @@ void make_ctx(Sim* s, Ctx& c) {
     c.I = &s->I; c.C = &s->C; a.op_mt = s->op_mt.data(); a.op_dur = s->op_dur.data(); a.job_work = s->job_work.data();
     c.aux = &a; c.raise = 0; c.now = 0;
     a.op_log = s->C.record_ops ? s->op_log.data() : nullptr;
+    a.leg_log = s->C.record_ops ? s->leg_log.data() : nullptr;
+    c.log = a.leg_log != nullptr;
     a.outs = s->outs_bytes ? (void*)s->outs.data() : nullptr;
     a.tcur = s->tobj.stochastic ? s->tcur.data() : nullptr;
     a.tseed = s->tobj.stochastic ? s->tseed.data() : nullptr;
@@ -198,6 +200,7 @@ void* jsh_create(const jsl_instance_desc* d, const jsl_env_cfg* cfg, uint64_t se
     s->outs_bytes = (I.has_m_out || I.has_t_out) ? (s->JW == 1 ? sizeof(OutS<1>) : s->JW == 2 ? sizeof(OutS<2>) : sizeof(OutS<4>)) : 0;
     s->state.assign(s->state_bytes + 16, 0); s->outs.assign(s->outs_bytes + 16, 0);
     s->op_log.assign((size_t)2 * I.N + 2, -1);
+    s->leg_log.assign((size_t)2 + 32 * s->JW + 5 * (I.N + 2 * I.J + 8) + 8, 0);
     s->seed = seed; s->last_reward = 0.0;
     s->tobj = make_tobj(*d);
     if (s->tobj.stochastic) {
@@ -218,6 +221,13 @@ void jsh_invariants(long* o) { o[0] = g_invariant_checks; o[1] = g_invariant_vio
 void jsh_randomize_variant(uint64_t seed, uint64_t variant, int J, const int32_t* job_op_start, int min_d, int max_d,
                            int32_t* op_mt, int32_t* op_dur, int32_t* job_work, int32_t* lb_mat) {
     randomize_variant(seed, variant, J, job_op_start, min_d, max_d, op_mt, op_dur, job_work, lb_mat);
+}
+int jsh_leg_log(void* h, int32_t* out, int cap) {
+    Sim* s = (Sim*)h;
+    const int n = s->leg_log[0], hdr = 2 + 32 * s->JW;
+    if (n > cap) return -1;
+    std::memcpy(out, s->leg_log.data() + hdr, (size_t)n * 5 * sizeof(int32_t));
+    return s->leg_log[1] ? -4 : n;
 }
 void jsh_fast_paths(long* o) { o[0] = g_fast_start; o[1] = g_fast_complete; o[2] = g_general_batches; }
 void jsh_set_env_id(void* h, uint64_t id) { ((Sim*)h)->env_id = id; }

@@ -122,3 +122,24 @@ def test_multi_instance_batch_and_variants():
     v.load_variants(torch.from_numpy(od * 0 + om).pin_memory(), torch.from_numpy(od[::-1].copy()).pin_memory(),
                     torch.from_numpy(lb), torch.from_numpy(mat))
     batch.close(); v.close()
+
+
+def test_render_data_matches_reference_dashboard_model():
+    """env.gantt_data() == DashboardDataMapper.map_states_to_gant_data(env.history) of the reference
+    (tests/golden/gantt.json), through the public env; render() prints one line per bar."""
+    import json
+    from pathlib import Path
+
+    gold = json.loads((Path(__file__).parent / "golden" / "gantt.json").read_text())
+    for key in ("transport:ft06-t/random1", "classic:ft06/random0"):
+        group, name = key.split(":")
+        env, sc = _env(group, name)
+        for a in sc.actions[: gold[key]["final"]["steps"]].tolist():
+            env.step(int(a))
+        data = env.gantt_data()
+        want = gold[key]["final"]["data"]
+        assert [dict(x) for x in data["schedules"]] == want["schedules"]
+        assert [dict(x) for x in data["transports"]] == want["transports"]
+        text = env.render()
+        assert len(text.splitlines()) == len(want["schedules"]) + len(want["transports"])
+        env.close()

@@ -56,16 +56,17 @@ def test_state_view_from_digest():
 def test_abi_library_exports_every_declared_symbol():
     from jobshoplab_b200 import engine
 
-    if not engine.LIB_PATH.exists():
+    if not (engine.LIB_PATH.exists() and engine.LOG_LIB_PATH.exists()):
         from jobshoplab_b200 import build
         build.build()
-    lib = ctypes.CDLL(str(engine.LIB_PATH))
     header = (ROOT / "include" / "jobshoplab_b200.h").read_text()
     declared = set(re.findall(r"\b(jsl_[a-z_]+)\s*\(", header))
     assert declared >= set(engine.ABI_SYMBOLS) and len(declared) >= 15
-    for sym in declared:
-        getattr(lib, sym)
-    assert lib.jsl_abi_version() == 1
+    for path in (engine.LIB_PATH, engine.LOG_LIB_PATH):  # throughput build and logging build: one ABI
+        lib = ctypes.CDLL(str(path))
+        for sym in declared:
+            getattr(lib, sym)
+        assert lib.jsl_abi_version() == 1
 
 
 def test_no_cpu_fallback():
