@@ -24,15 +24,17 @@ EXC_TO_STATUS = {"BufferFullError": abi.ST_BUFFER_FULL, "UnsuccessfulStateMachin
                  "InvalidValue": abi.ST_NO_POSSIBLE, "NotImplementedError": abi.ST_OTHER_INVALID}
 
 
-def step_replay(sc: G.Scenario, B=5):
-    """Step mode: every env of a small batch gets the golden tape; env 0 and env B-1 are checked each step."""
+def step_replay(sc: G.Scenario, B=5, record=True):
+    """Step mode: every env of a small batch gets the golden tape; env 0 and env B-1 are checked each step.
+    record=True runs the logging build of the library (the digest of DONE operations needs the op log);
+    record=False runs the throughput build -- the one bench.py measures -- and checks everything but the digest."""
     eng = _engine()
-    batch = eng.Batch(sc.lowered, B, record_ops=True, **sc.cfg)
+    batch = eng.Batch(sc.lowered, B, record_ops=record, **sc.cfg)
     out = batch.reset()
     torch.cuda.synchronize()
     probe = (0, B - 1)
     for e in probe:
-        assert G.hash_i32(batch.get_state(e)) == int(sc.state_hash[0]), "reset state"
+        assert not record or G.hash_i32(batch.get_state(e)) == int(sc.state_hash[0]), "reset state"
     obs = out.obs.cpu().numpy()
     for e in probe:
         assert G.hash_bytes(obs[e].tobytes()) == int(sc.obs_hash[0]), "reset obs"
@@ -47,7 +49,7 @@ def step_replay(sc: G.Scenario, B=5):
         term = out.terminated.cpu().numpy(); trunc = out.truncated.cpu().numpy()
         obs = out.obs.cpu().numpy(); cand = out.cand.cpu().numpy()
         for e in probe:
-            assert G.hash_i32(batch.get_state(e)) == int(sc.state_hash[i + 1]), f"state after step {i}"
+            assert not record or G.hash_i32(batch.get_state(e)) == int(sc.state_hash[i + 1]), f"state after step {i}"
             assert rew[e] == float(sc.reward[i]), f"reward at step {i}"
             assert tm[e] == int(sc.time[i + 1])
             assert (int(term[e]) | (int(trunc[e]) << 1)) == int(sc.flags[i])
@@ -58,7 +60,7 @@ def step_replay(sc: G.Scenario, B=5):
         st = batch.step(acts).status.cpu().numpy()
         assert (st == EXC_TO_STATUS[sc.exception]).all(), (sc.exception, st)
     else:
-        assert np.array_equal(batch.get_state(0), sc.final_digest)
+        assert not record or np.array_equal(batch.get_state(0), sc.final_digest)
         mk = batch.out.makespan.cpu().numpy()
         terminated = bool(int(sc.flags[-1]) & 1) if n else False
         assert (mk == (sc.meta["makespan"] if terminated else -1)).all()  # info["makespan"], env.py:408
@@ -95,6 +97,20 @@ def test_step_mode_matches_reference_traces(group):
             raise AssertionError(f"{group}:{name}: {ex}") from ex
 
 
+@pytest.mark.parametrize("group", ["classic", "solutions", "transport", "buffers", "features", "truncation", "oparray", "tassel"])
+def test_throughput_build_step_mode(group):
+    """The same traces through libjsl_b200.so proper (no logs compiled in): reward, time, flags, candidate count
+    and the observation of every step."""
+    names = SHORT.get(group) or _deterministic(group)
+    if group in ("transport", "buffers", "features"):
+        names = names[::5]
+    for name in names:
+        try:
+            step_replay(G.Scenario(group, name), record=False)
+        except AssertionError as ex:
+            raise AssertionError(f"{group}:{name}: {ex}") from ex
+
+
 @pytest.mark.parametrize("group", ["classic", "solutions", "transport", "buffers", "features", "truncation", "big"])
 def test_rollout_tape_matches_reference(group):
     """Rollout mode (state resident in shared memory for the whole episode): every deterministic golden
@@ -112,23 +128,24 @@ def test_rollout_tape_matches_reference(group):
         tape = np.full((B, L), 2, dtype=np.uint8)  # past its tape an env gets an out-of-space action and stops
         for i, s in enumerate(scs):
             tape[i, : len(s.actions)] = s.actions
-        batch = eng.Batch(scs[0].lowered, B, record_ops=True, **scs[0].cfg)
-        batch.reset()
-        r = batch.rollout("tape", tape=torch.from_numpy(tape).cuda())
-        mk, ns = r.makespan.cpu().numpy(), r.n_steps.cpu().numpy()
-        ret, st, noop = r.ret.cpu().numpy(), r.status.cpu().numpy(), r.no_op_count.cpu().numpy()
-        for i, s in enumerate(scs):
-            tag = f"{group}:{s.name}"
-            if s.exception:
-                assert st[i] == EXC_TO_STATUS[s.exception], tag
-                continue
-            assert ns[i] == s.meta["n_steps"], tag
-            assert mk[i] == s.meta["makespan"], tag
-            assert noop[i] == s.meta["no_op_count"], tag
-            assert ret[i] == float(np.sum(s.reward[: 0]) + sum(float(x) for x in s.reward)), tag
-            assert st[i] in (abi.ST_DONE, abi.ST_TRUNCATED) or (s.cut and st[i] == abi.ST_ACTION_OUT_OF_SPACE), tag
-            assert np.array_equal(batch.get_state(i), s.final_digest), tag
-        batch.close()
+        for record in (True, False):  # logging build (+ final digest) and throughput build
+            batch = eng.Batch(scs[0].lowered, B, record_ops=record, **scs[0].cfg)
+            batch.reset()
+            r = batch.rollout("tape", tape=torch.from_numpy(tape).cuda())
+            mk, ns = r.makespan.cpu().numpy(), r.n_steps.cpu().numpy()
+            ret, st, noop = r.ret.cpu().numpy(), r.status.cpu().numpy(), r.no_op_count.cpu().numpy()
+            for i, s in enumerate(scs):
+                tag = f"{group}:{s.name}"
+                if s.exception:
+                    assert st[i] == EXC_TO_STATUS[s.exception], tag
+                    continue
+                assert ns[i] == s.meta["n_steps"], tag
+                assert mk[i] == s.meta["makespan"], tag
+                assert noop[i] == s.meta["no_op_count"], tag
+                assert ret[i] == float(np.sum(s.reward[: 0]) + sum(float(x) for x in s.reward)), tag
+                assert st[i] in (abi.ST_DONE, abi.ST_TRUNCATED) or (s.cut and st[i] == abi.ST_ACTION_OUT_OF_SPACE), tag
+                assert not record or np.array_equal(batch.get_state(i), s.final_digest), tag
+            batch.close()
 
 
 def test_rollout_policies_match_reference_rules():
