@@ -21,7 +21,6 @@ import os
 LIB_PATH = Path(os.environ.get("JSL_LIB", Path(__file__).resolve().parent / "csrc" / "libjsl_b200.so"))
 LOG_LIB_PATH = Path(os.environ.get("JSL_LOG_LIB", Path(__file__).resolve().parent / "csrc" / "libjsl_b200_log.so"))
 _libs: dict = {}
-_lib = None
 
 ABI_SYMBOLS = ("jsl_last_error", "jsl_abi_version", "jsl_instance_create", "jsl_instance_destroy", "jsl_batch_create",
                "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_randomize", "jsl_batch_get_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
