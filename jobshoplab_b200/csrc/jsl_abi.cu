@@ -258,8 +258,9 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     I.flex_pre = all_equal(t->pre_type, JSL_BUF_FLEX);
     I.flex_post = all_equal(t->post_type, JSL_BUF_FLEX) && all_equal(t->sbuf_type, JSL_BUF_FLEX);
     I.caps_inf = all_equal(t->pre_cap, JSL_CAP_INF) && all_equal(t->post_cap, JSL_CAP_INF) && all_equal(t->sbuf_cap, JSL_CAP_INF);
-    b->bd.classic = I.flex_pre && I.flex_post && I.caps_inf && !I.has_m_out && !I.has_t_out && !I.setup && !I.travel &&
-                    !t->stochastic && I.out_buf >= 0;
+    const bool simple = I.flex_pre && I.flex_post && I.caps_inf && !I.has_m_out && !I.has_t_out && !I.setup &&
+                        !t->stochastic && I.out_buf >= 0;
+    b->bd.classic = !simple ? 0 : I.travel ? 1 : 2;
     CfgDev& C = b->bd.cfg;
     C.allow_early_transport = cfg->allow_early_transport; C.truncation_joker = cfg->truncation_joker;
     C.truncation_active = cfg->truncation_active; C.obs_kind = cfg->obs_kind; C.record_ops = cfg->record_ops;
@@ -532,9 +533,8 @@ int jsl_rollout(jsl_batch_t* b, int policy, const uint8_t* action_tape, int64_t 
     CK(cudaSetDevice(b->device));
     int smem = WARPS_PER_CTA * b->smem_per_warp;
     if (b->rollout_ctas_per_sm == 0) {
-        const bool st = b->bd.tcur != nullptr, cl = b->bd.classic != 0;
-        b->rollout_ctas_per_sm = b->JW == 1 ? rollout_occupancy_jw1(smem, st, cl)
-                                 : b->JW == 2 ? rollout_occupancy_jw2(smem, st, cl) : rollout_occupancy_jw4(smem, st, cl);
+        b->rollout_ctas_per_sm = b->JW == 1 ? rollout_occupancy_jw1(b->bd, smem)
+                                 : b->JW == 2 ? rollout_occupancy_jw2(b->bd, smem) : rollout_occupancy_jw4(b->bd, smem);
     }
     int64_t need = (b->bd.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     int64_t persistent = (int64_t)b->sm_count * b->rollout_ctas_per_sm;  // one full wave of resident CTAs

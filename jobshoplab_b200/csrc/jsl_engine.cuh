@@ -12,8 +12,9 @@
 // element k is recovered arithmetically in the reference's order.
 //
 // Template parameters of everything below: JW = lane words (ceil(max(J,T)/32)), ST = the instance has
-// stochastic time objects, CL = "classic" specialisation (all buffers FLEX and unbounded, zero travel and
-// setup times, no outages): capacity / position / TimeDependency / outage / lookup code is compiled out.
+// stochastic time objects, CL = specialisation level: 0 general; 1 "simple" (all buffers FLEX and unbounded, no
+// setup times, no outages, deterministic: capacity / position / TimeDependency / outage / setup code is compiled
+// out); 2 "classic" (simple + all travel times zero: no travel lookups, start / completion chains in one batch).
 // The hot loop has to stay inside the instruction cache: one call site per phase (sm_step, run_env_op),
 // rare paths out of line (JSL_DN), rarely used per-env constants in EnvAux (shared memory).
 //
@@ -132,7 +133,7 @@ struct CfgDev {
 // ------------------------------------------------------------------------------------ state
 // Mutable state of one env.  JW = ceil(max(J,T)/32) lane words; machines <= 32.
 // The same struct is the HBM image (step mode) and the shared-memory working copy.
-template <int JW, bool ST = false, bool CL = false>
+template <int JW, bool ST = false, int CL = false>
 struct alignas(16) EnvS {
     static constexpr int MJ = 32 * JW, MT = 32 * JW, MM = 32;
     // scalars (uniform)
@@ -387,13 +388,13 @@ JSL_D int place_of_buf(const InstDev& I, int b) {
 JSL_D int job_nops(const InstDev& I, int j) { return I.job_op_start[j + 1] - I.job_op_start[j]; }
 
 // ------------------------------------------------------------------------------------ buffers as (loc, seq)
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_DN int buf_count(const EnvS<JW, ST, CL>& s, const InstDev& I, int b) {
     return wp_ballot<JW>(I.J, [&](int j) { return s.j_loc[j] == b; }).count();
 }
 
 // buffer_type_utils.py:236-262 get_next_job_from_buffer; -1 = None
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_DN int next_job_from_buffer(const EnvS<JW, ST, CL>& s, const InstDev& I, int b) {
     int ty = buf_type(I, b);
     if (ty == JSL_BUF_FLEX) return -1;
@@ -410,7 +411,7 @@ JSL_DN int next_job_from_buffer(const EnvS<JW, ST, CL>& s, const InstDev& I, int
 }
 
 // buffer_type_utils.py:328-353 is_job_ready_for_pickup_from_postbuffer (uniform j)
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_DN bool ready_for_pickup(const EnvS<JW, ST, CL>& s, const InstDev& I, int j) {
     int b = s.j_loc[j];
     bool right = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
@@ -423,7 +424,7 @@ JSL_DN bool ready_for_pickup(const EnvS<JW, ST, CL>& s, const InstDev& I, int j)
     return !wp_ballot<JW>(I.J, [&](int q) { return s.j_loc[q] == b && s.j_seq[q] < sq; }).any();
 }
 // same test evaluated by one lane for its own job (serial scan; only used when early transport is off)
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D bool ready_for_pickup_lane(const EnvS<JW, ST, CL>& s, const InstDev& I, int j) {
     int b = s.j_loc[j];
     bool right = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
@@ -438,7 +439,7 @@ JSL_D bool ready_for_pickup_lane(const EnvS<JW, ST, CL>& s, const InstDev& I, in
 }
 
 // buffer_type_utils.py:77-105 put_in_buffer (multi-slot buffers)
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void put_in_buffer(EnvS<JW, ST, CL>& s, Ctx& c, int b, int j) {
     const InstDev& I = *c.I;
     if (JSL_UNLIKELY(!CL && !I.caps_inf)) {
@@ -462,7 +463,7 @@ struct Poss {
 };
 
 // machine of the next IDLE op of job j and whether it has one (lane-local)
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D int next_idle_place(const EnvS<JW, ST, CL>& s, const Ctx& c, int j) {  // -1 = none -> output buffer
     const InstDev& I = *c.I;
     int k = s.j_k[j] + (s.j_proc[j] ? 1 : 0);
@@ -470,7 +471,7 @@ JSL_D int next_idle_place(const EnvS<JW, ST, CL>& s, const Ctx& c, int j) {  // 
     return c.aux->op_mt[I.job_op_start[j] + k] & 0xffff;
 }
 
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D Poss<JW> compute_poss(const EnvS<JW, ST, CL>& s, const Ctx& c) {
     const InstDev& I = *c.I;
     Poss<JW> p;
@@ -501,7 +502,7 @@ struct Trans {
 };
 
 // idx-th element of get_possible_transitions(state) (state.py:298-341 ordering)
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D Trans nth_possible(const EnvS<JW, ST, CL>& s, const Ctx& c, const Poss<JW>& p, int idx) {
     Trans t;
     int n1 = p.p1.count();
@@ -517,14 +518,14 @@ JSL_D Trans nth_possible(const EnvS<JW, ST, CL>& s, const Ctx& c, const Poss<JW>
     return t;
 }
 
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D Poss<JW> cached_poss(const EnvS<JW, ST, CL>& s) {
     Poss<JW> p;
 #pragma unroll
     for (int w = 0; w < JW; w++) { p.p1.w[w] = s.c_p1[w]; p.idle.w[w] = s.c_idle[w]; p.lr.w[w] = s.c_lr[w]; p.li.w[w] = s.c_li[w]; }
     return p;
 }
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void store_poss(EnvS<JW, ST, CL>& s, const Poss<JW>& p, bool clear) {
 #pragma unroll
     for (int w = 0; w < JW; w++) {
@@ -533,7 +534,7 @@ JSL_D void store_poss(EnvS<JW, ST, CL>& s, const Poss<JW>& p, bool clear) {
     }
 }
 // the candidate the agent is looking at: possible_transitions[0] after `skip` dropped ones
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D Trans current_candidate(const EnvS<JW, ST, CL>& s, const Ctx& c) {
     return nth_possible(s, c, cached_poss(s), s.skip);
 }
@@ -542,15 +543,15 @@ JSL_D Trans current_candidate(const EnvS<JW, ST, CL>& s, const Ctx& c) {
 // .time of a time object (no resample)
 template <bool ST>
 JSL_D int op_duration(const Ctx& c, int o) { return ST ? c.aux->tcur[o] : c.aux->op_dur[o]; }
-template <bool ST, bool CL>
+template <bool ST, int CL>
 JSL_D int setup_time_cur(const Ctx& c, int i) {
     if (ST) return c.aux->tcur[c.I->off_setup + i];
     return (!CL && c.I->setup) ? c.I->setup[i] : 0;
 }
-template <bool ST, bool CL>
+template <bool ST, int CL>
 JSL_D int travel_time_cur(const Ctx& c, int a, int b) {
     if (ST) return c.aux->tcur[c.I->off_travel + a * c.I->NP + b];
-    return (!CL && c.I->travel) ? c.I->travel[a * c.I->NP + b] : 0;
+    return (CL != 2 && c.I->travel) ? c.I->travel[a * c.I->NP + b] : 0;
 }
 
 struct Rng4 { uint32_t x, y, z, w; };
@@ -735,7 +736,7 @@ JSL_D void release_outages(int n, uint8_t* active, int32_t* a, int32_t* b) {
 
 // ------------------------------------------------------------------------------------ machine handlers
 // validate.py:30-82.  returns false on a validation error (StateMachineResult.success = False)
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D bool machine_valid(const EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int job) {
     int from = s.m_state[m];
     if (from == to) return false;
@@ -753,7 +754,7 @@ JSL_D bool machine_valid(const EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int j
 }
 
 // handler.py:414-457 + manipulate.py:378-444
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void machine_idle_to_setup(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -775,7 +776,7 @@ JSL_D void machine_idle_to_setup(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
     s.m_state[m] = JSL_M_SETUP; s.m_occ[m] = c.now + setup; s.m_tool[m] = (uint8_t)tool;
 }
 // handler.py:460-503 + manipulate.py:225-276
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void machine_setup_to_working(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8 || s.j_loc[j] != 3 * m + 2) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -786,7 +787,7 @@ JSL_D void machine_setup_to_working(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
     s.m_state[m] = JSL_M_WORKING; s.m_occ[m] = c.now + dur;
 }
 // handler.py:506-543 + manipulate.py:328-375
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void machine_working_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     int occupied_for = 0;
@@ -802,7 +803,7 @@ JSL_D void machine_working_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) 
     s.j_end[j] = c.now + occupied_for;
 }
 // handler.py:546-574 + manipulate.py:117-193
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void machine_outage_to_idle(EnvS<JW, ST, CL>& s, Ctx& c, int m) {
     const InstDev& I = *c.I;
     int j = s.m_job[m];
@@ -831,7 +832,7 @@ JSL_D void machine_outage_to_idle(EnvS<JW, ST, CL>& s, Ctx& c, int m) {
 }
 
 // process one machine transition (validate + handle); false = validation error
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D bool apply_machine(EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int job) {
     // every machine transition is created from that machine's own current state (timed) or from the candidate
     // masks of the unchanged state (action); only the TimeDependency hand-me-downs of non-FLEX postbuffers
@@ -863,7 +864,7 @@ JSL_D int leg_hdr(int MT) { return 2 + MT; }
 // Compiled in only with -DJSL_LEG_LOG (libjsl_b200_log.so, used for batches created with record_ops): even a
 // never-taken branch per transition costs the throughput kernels ~5 % of their instruction budget.
 #ifdef JSL_LEG_LOG
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void leg_open(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j, int start, int end) {
     if (!c.log) return;
     int32_t* g = c.aux->leg_log;
@@ -877,7 +878,7 @@ JSL_D void leg_open(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j, int start, int en
     g[2 + t] = idx;
     g[0] = idx + 1;
 }
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void leg_end(EnvS<JW, ST, CL>& s, Ctx& c, int t, int end, bool close) {
     if (!c.log) return;
     int32_t* g = c.aux->leg_log;
@@ -887,7 +888,7 @@ JSL_D void leg_end(EnvS<JW, ST, CL>& s, Ctx& c, int t, int end, bool close) {
     if (close) g[2 + t] = -1;
 }
 // the state after the current batch is recorded at time `now`: tasks opened in it start there
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void leg_stamp(EnvS<JW, ST, CL>& s, Ctx& c) {
     if (!c.log) return;
     int32_t* g = c.aux->leg_log;
@@ -901,18 +902,18 @@ JSL_D void leg_stamp(EnvS<JW, ST, CL>& s, Ctx& c) {
 }
 constexpr bool LEG_LOG_BUILD = true;
 #else
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void leg_open(EnvS<JW, ST, CL>&, Ctx&, int, int, int, int) {}
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void leg_end(EnvS<JW, ST, CL>&, Ctx&, int, int, bool) {}
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void leg_stamp(EnvS<JW, ST, CL>&, Ctx&) {}
 constexpr bool LEG_LOG_BUILD = false;
 #endif
 
 // ------------------------------------------------------------------------------------ transport handlers
 // validate.py:85-118 + transitions.py:82-107,161-186
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D bool transport_valid(const EnvS<JW, ST, CL>& s, int t, int to) {
     // bit (from*6 + to): idle->running, running->running|outage (same state only for WAITINGPICKUP), outage->idle
     constexpr uint64_t R = (1ull << JSL_T_WORKING) | (1ull << JSL_T_PICKUP) | (1ull << JSL_T_TRANSIT) | (1ull << JSL_T_WAITINGPICKUP);
@@ -930,7 +931,7 @@ JSL_D int output_place(Ctx& c) {
 }
 
 // handler.py:808-902 idle -> working (PICKUP)
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void agv_idle_to_working(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -952,7 +953,7 @@ JSL_D void agv_idle_to_working(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
 }
 
 // handler.py:577-639 _get_waiting_time, :642-702, :989-1030
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void agv_to_waitingpickup(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -987,7 +988,7 @@ JSL_D void agv_to_waitingpickup(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
 }
 
 // handler.py:705-805 (waiting)pickup -> transit
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void agv_to_transit(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -1015,7 +1016,7 @@ JSL_D void agv_to_transit(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
 }
 
 // handler.py:905-958 + manipulate.py:45-114 transit -> outage (drop-off)
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void agv_transit_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     const InstDev& I = *c.I;
     if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -1042,7 +1043,7 @@ JSL_D void agv_transit_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
 }
 
 // process one transport transition; false = validation error
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D bool apply_transport(EnvS<JW, ST, CL>& s, Ctx& c, int t, int to, int job) {
     if (!CL && !c.I->flex_post && !transport_valid(s, t, to)) return false;
     int from = s.t_state[t];
@@ -1063,7 +1064,7 @@ JSL_D bool apply_transport(EnvS<JW, ST, CL>& s, Ctx& c, int t, int to, int job) 
 
 // ------------------------------------------------------------------------------------ time machines
 // time_machines.py:133-221
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D int force_jump_to_event(const EnvS<JW, ST, CL>& s, Ctx& c) {
     const InstDev& I = *c.I;
     int bj = wp_min<JW>(I.J, [&](int j) { return s.j_proc[j] ? s.j_end[j] : INT_BIG; });
@@ -1087,7 +1088,7 @@ JSL_D int force_jump_to_event(const EnvS<JW, ST, CL>& s, Ctx& c) {
 // ------------------------------------------------------------------------------------ timed transitions
 // handler.py:55-153, :329-379: evaluate on the current snapshot into the x_* scratch arrays.
 // returns true when at least one transition was created.
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D bool create_timed(EnvS<JW, ST, CL>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, bool& time_due) {
     const InstDev& I = *c.I;
     const int now = c.now;
@@ -1176,7 +1177,7 @@ JSL_D bool create_timed(EnvS<JW, ST, CL>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, 
 // batch).  Preconditions: no lonely job in the quiet state the step starts from (so the started job is the only
 // teleport candidate) and a positive duration (else WORKING->OUTAGE is due in the second batch).  Leaves the
 // candidate masks of the resulting state in s.c_*.
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D bool classic_start(EnvS<JW, ST, CL>& s, Ctx& c, const Trans& act) {
     const InstDev& I = *c.I;
     Poss<JW> p = cached_poss(s);
@@ -1221,7 +1222,7 @@ JSL_D bool classic_start(EnvS<JW, ST, CL>& s, Ctx& c, const Trans& act) {
 // of the AGVs waiting for exactly those jobs.  The chain is OUTAGE->IDLE (job into the postbuffer) |
 // WAITINGPICKUP->TRANSIT | TRANSIT->OUTAGE (job into the next prebuffer / output buffer) | OUTAGE->IDLE, all at
 // `now`; buffer stamps keep the reference's order (machines by index, then AGVs by index).
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D bool classic_complete(EnvS<JW, ST, CL>& s, Ctx& c, const Mask<1>& mm, const Mask<JW>& tm) {
     const InstDev& I = *c.I;
     const bool bad_m = wp_ballot<1>(I.M, [&](int m) {
@@ -1297,7 +1298,7 @@ constexpr int TM_JUMP = 0, TM_FORCE = 1;
 // was applied after them), so they double as the new possible_transitions.
 // Returns success (false = validation error -> StateMachineResult.success=False); escaping exceptions
 // are left in c.raise.
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int time_machine) {
     const InstDev& I = *c.I;
     c.now = s.time;
@@ -1314,9 +1315,9 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
     // `now`), and the classic fast paths end in one: no timed transition can exist in the next batch
     bool known_quiet = !has_action && time_machine == TM_FORCE;  // (a reset starts from the initial state instead)
     bool poss_fresh = known_quiet;  // s.c_* already describe the current state
-    bool moved = !CL || (!has_action && time_machine == TM_JUMP);  // a job may have reached an output buffer (reset: unknown)
+    bool moved = CL != 2 || (!has_action && time_machine == TM_JUMP);  // a job may have reached an output buffer (reset: unknown)
     int guard = 0;
-    if (CL && has_action && act.kind == 0 && classic_start(s, c, act)) {
+    if (CL == 2 && has_action && act.kind == 0 && classic_start(s, c, act)) {
         action_stage = false; first = false; known_quiet = true; poss_fresh = true;
 #ifdef JSL_HOST_SIM
         g_fast_start++;
@@ -1399,7 +1400,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                     return tt == 0;
                 };
                 Mask<JW> zr, zi;
-                if (CL) {  // every travel time is zero: all lonely jobs qualify
+                if (CL == 2) {  // every travel time is zero: all lonely jobs qualify
                     zr = p.lr; zi = p.li;
                 } else {
                     zr = wp_ballot<JW>(I.J, [&](int j) { bool bd = false; return p.lr.test(j) && zero_travel(j, bd); });
@@ -1423,7 +1424,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                 }
             }
             if (!have && !tele.any()) break;
-            if (CL && !tele.any() && classic_complete(s, c, mm, tm)) {
+            if (CL == 2 && !tele.any() && classic_complete(s, c, mm, tm)) {
                 mm.w[0] = 0;
 #pragma unroll
                 for (int w = 0; w < JW; w++) tm.w[w] = 0;
@@ -1435,7 +1436,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
             }
         }
 #ifdef JSL_HOST_SIM
-        if (CL) g_general_batches++;
+        if (CL == 2) g_general_batches++;
 #endif
         // apply: machines, then timed transports, then teleports -- in creation order
         moved = true;
@@ -1479,7 +1480,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
 }
 
 // ------------------------------------------------------------------------------------ reset
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void env_init(EnvS<JW, ST, CL>& s, Ctx& c) {
     const InstDev& I = *c.I;
     s.time = I.start_time; s.seq_ctr = 0; s.n_possible = 0; s.skip = 0;
@@ -1523,7 +1524,7 @@ JSL_D void env_init(EnvS<JW, ST, CL>& s, Ctx& c) {
 
 // ------------------------------------------------------------------------------------ reward / step
 // rewards.py:118-148 BinaryActionJsspReward.make, IEEE double without contraction
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D double make_reward(EnvS<JW, ST, CL>& s, const Ctx& c) {
     double sr;
     if (s.truncated) sr = (c.C->truncation_bias * 1.0) / c.C->sparse_bias;
@@ -1551,7 +1552,7 @@ struct StepPlan {
 
 // everything before the state machine: argument checks, SubTimeStepper, what to run.
 // returns false when env.step raises before touching the state machine (status is set).
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D bool env_step_pre(EnvS<JW, ST, CL>& s, Ctx& c, int action, StepPlan& plan) {
     plan.run_sm = false; plan.has_action = false; plan.time_machine = TM_JUMP;
     plan.act.kind = 0; plan.act.comp = 0; plan.act.new_state = 0; plan.act.job = 0;
@@ -1573,7 +1574,7 @@ JSL_D bool env_step_pre(EnvS<JW, ST, CL>& s, Ctx& c, int action, StepPlan& plan)
 }
 
 // everything after it: middleware bookkeeping, terminated/truncated, reward.
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D double env_step_post(EnvS<JW, ST, CL>& s, Ctx& c, int action, const StepPlan& plan, bool success) {
     if (c.raise) { s.status = c.raise; return 0.0; }
     const bool action_empty = action == 0;
@@ -1606,7 +1607,7 @@ JSL_D double env_step_post(EnvS<JW, ST, CL>& s, Ctx& c, int action, const StepPl
 // One env operation: OP_RESET (env.reset: init + dummy step) or an env.step(action).  The only place
 // sm_step is instantiated.
 constexpr int OP_RESET = -1;
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D double run_env_op(EnvS<JW, ST, CL>& s, Ctx& c, int op) {
     StepPlan plan;
     if (op == OP_RESET) {
@@ -1661,7 +1662,7 @@ JSL_D uint32_t philox_bit(uint64_t seed, uint64_t env_idx, uint32_t step) {
 }
 
 // dipatching_benchmark.py:17-67 + dispatch_rules_uitls.py:57-111
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D int policy_action(const EnvS<JW, ST, CL>& s, const Ctx& c, int policy) {
     const InstDev& I = *c.I;
     if (policy == JSL_POLICY_RANDOM) {
@@ -1714,7 +1715,7 @@ JSL_HD int obs_bytes_binary(int J, int M) { return (16 + 4 * J + 4 * M + 2 * J +
 JSL_HD int obs_bytes_oparray(int J, int N) { return (16 + 4 * N + 4 * J + 15) & ~15; }
 JSL_HD int obs_bytes_tassel(int J) { return (7 * 4 * J + 15) & ~15; }
 
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void cand_floats(const EnvS<JW, ST, CL>& s, const Ctx& c, float* tr, const Trans* known = nullptr) {
     const InstDev& I = *c.I;
     if (!s.obs_done && s.n_possible - s.skip > 0) {
@@ -1728,7 +1729,7 @@ JSL_D void cand_floats(const EnvS<JW, ST, CL>& s, const Ctx& c, float* tr, const
     }
 }
 
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* out, const Trans* cand = nullptr) {
     const InstDev& I = *c.I;
     const int J = I.J, M = I.M;
@@ -1774,7 +1775,7 @@ JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* ou
 
 // BinaryOperationArrayObservation.make (observations.py:631-693 over :588-618):
 //   f32 current_transition[3] | f32 0 | f32 operation_state[N] | f32 job_locations[J]
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void write_obs_oparray(const EnvS<JW, ST, CL>& s, Ctx& c, uint8_t* out, const Trans* cand = nullptr) {
     const InstDev& I = *c.I;
     float tr[3];
@@ -1810,7 +1811,7 @@ JSL_D void write_obs_oparray(const EnvS<JW, ST, CL>& s, Ctx& c, uint8_t* out, co
 // TasselJsspObservation.make (observations.py:738-918): f32 [7][J] = allocatable | left_over_time |
 // percent_finished | total_completion | time_until_next_machine_is_free | idle_since_last_op | cum_idle_time.
 // Needs the per-op (start, end) log (cfg.record_ops is forced on for this observation kind).
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D void write_obs_tassel(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* out) {
     const InstDev& I = *c.I;
     const int J = I.J;
@@ -1856,7 +1857,7 @@ JSL_D void write_obs_tassel(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* ou
 // ------------------------------------------------------------------------------------ canonical digest
 // Layout documented in DESIGN.md / oracle/ref_harness.py.  Executed by one env's warp (diagnostics,
 // parity tests, render()).  Returns the number of int32 produced (writes at most cap).
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 JSL_D int write_digest(const EnvS<JW, ST, CL>& s, const Ctx& c, int32_t* out, int cap) {
     const InstDev& I = *c.I;
     int n = 0;

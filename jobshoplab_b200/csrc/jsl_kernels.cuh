@@ -44,7 +44,7 @@ struct BatchDev {
     int32_t* tcur;       // [B][n_tobj] current .time of every time object (stochastic instances) or nullptr
     const int32_t* tape; // [B][tape_stride] replayed update() results or nullptr
     int64_t tape_stride;
-    int classic;         // all-FLEX unbounded buffers, zero travel/setup, no outages: the CL specialisation applies
+    int classic;         // specialisation level CL of jsl_engine.cuh: 0 general, 1 simple, 2 classic
     unsigned long long* work_counter;  // next env index of the persistent rollout grid (dynamic work queue)
     uint16_t* tseed;     // [B][n_tobj] numpy seed of every stochastic time object
     const int32_t* start_seeds;  // [B][n_tobj] or nullptr
@@ -83,7 +83,7 @@ __device__ __forceinline__ void copy_in(void* dst, const void* src, int bytes) {
 // general kernels depends on the batch (a bigger slot would cost them L1 capacity for nothing).
 template <int JW>
 struct Slot {
-    static constexpr int AUX = (int)sizeof(EnvS<JW, false, false>);
+    static constexpr int AUX = (int)sizeof(EnvS<JW, false, 0>);
     static constexpr int OUTS = AUX + (int)sizeof(EnvAux);
     static constexpr int BYTES = OUTS;                              // without outage bookkeeping
     static constexpr int BYTES_OUTS = OUTS + (int)sizeof(OutS<JW>);  // with it
@@ -93,12 +93,12 @@ inline int slot_bytes(int JW, bool has_outs) {
          : JW == 2 ? (has_outs ? Slot<2>::BYTES_OUTS : Slot<2>::BYTES)
                    : (has_outs ? Slot<4>::BYTES_OUTS : Slot<4>::BYTES);
 }
-template <int JW, bool CL>
+template <int JW, int CL>
 __device__ __forceinline__ int slot_stride(const BatchDev& bd) {
     return (CL || !bd.outs) ? Slot<JW>::BYTES : Slot<JW>::BYTES_OUTS;
 }
 
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env, uint8_t* slot) {
     const InstDev& I = bd.inst;
     const int64_t v = I.n_inst == 1 ? 0 : (env < I.n_inst ? env : (int64_t)((uint64_t)env % (uint32_t)I.n_inst));
@@ -135,7 +135,7 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
     __syncwarp();
 }
 
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c, const jsl_step_out& out, int64_t env,
                                                double reward, int obs_bytes) {
     const int remaining = s.n_possible - s.skip;
@@ -171,7 +171,7 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c
     }
 }
 
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -192,7 +192,7 @@ k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, j
     if (bd.outs) copy_in(bd.outs + env * (int64_t)bd.outs_stride, outs_sm, bd.outs_stride);
 }
 
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_STEP_MIN_CTAS)
 k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -234,7 +234,7 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     if (g_outs) copy_in(g_outs, outs_sm, bd.outs_stride);
 }
 
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CL ? JSL_ROLLOUT_MIN_CTAS : JSL_ROLLOUT_MIN_CTAS_GENERAL)
 k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __restrict__ tape, int64_t tape_stride,
           int max_steps, int flags, jsl_rollout_out out) {
@@ -301,7 +301,7 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
     }
 }
 
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 __global__ void __launch_bounds__(32)
 k_digest(const __grid_constant__ BatchDev bd, int64_t env, int32_t* out, int cap, int32_t* n_out) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -322,31 +322,31 @@ struct LaunchCfg {
     cudaStream_t stream;
 };
 
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 cudaError_t launch_reset(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* mask, jsl_step_out out, int obs_bytes) {
     if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_reset<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
     k_reset<JW, ST, CL><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, mask, out, obs_bytes);
     return cudaGetLastError();
 }
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 cudaError_t launch_step(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* actions, jsl_step_out out, int obs_bytes) {
     if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_step<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
     k_step<JW, ST, CL><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, actions, out, obs_bytes);
     return cudaGetLastError();
 }
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 cudaError_t launch_rollout(const BatchDev& bd, const LaunchCfg& lc, int policy, const uint8_t* tape, int64_t tape_stride,
                            int max_steps, int flags, jsl_rollout_out out) {
     if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
     k_rollout<JW, ST, CL><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, policy, tape, tape_stride, max_steps, flags, out);
     return cudaGetLastError();
 }
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 cudaError_t launch_digest(const BatchDev& bd, const LaunchCfg& lc, int64_t env, int32_t* out, int cap, int32_t* n_out) {
     k_digest<JW, ST, CL><<<1, 32, lc.smem, lc.stream>>>(bd, env, out, cap, n_out);
     return cudaGetLastError();
 }
-template <int JW, bool ST, bool CL>
+template <int JW, bool ST, int CL>
 int rollout_occupancy(int smem) {  // resident CTAs per SM for the persistent rollout grid
     int n = 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -361,40 +361,35 @@ int rollout_occupancy(int smem) {  // resident CTAs per SM for the persistent ro
     cudaError_t launch_rollout_jw##N(const BatchDev&, const LaunchCfg&, int, const uint8_t*, int64_t, int, int,      \
                                      jsl_rollout_out);                                                                \
     cudaError_t launch_digest_jw##N(const BatchDev&, const LaunchCfg&, int64_t, int32_t*, int, int32_t*);            \
-    int rollout_occupancy_jw##N(int smem, bool stochastic, bool classic);                                                                            \
+    int rollout_occupancy_jw##N(const BatchDev& bd, int smem);                                                                            \
     int state_bytes_jw##N();                                                                                          \
     int outs_bytes_jw##N();
 JSL_DECLARE_JW(1)
 JSL_DECLARE_JW(2)
 JSL_DECLARE_JW(4)
 
+// one instantiation per (lane words, kind): stochastic | classic (level 2) | simple (level 1) | general
+#define JSL_BY_KIND(bd, F, N, ...)                                                                \
+    ((bd).tcur           ? F<N, true, 0>(__VA_ARGS__)                                             \
+     : (bd).classic == 2 ? F<N, false, 2>(__VA_ARGS__)                                            \
+     : (bd).classic == 1 ? F<N, false, 1>(__VA_ARGS__)                                            \
+                         : F<N, false, 0>(__VA_ARGS__))
 #define JSL_DEFINE_JW(N)                                                                                              \
     cudaError_t launch_reset_jw##N(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* m, jsl_step_out o, int ob) { \
-        return bd.tcur ? launch_reset<N, true, false>(bd, lc, m, o, ob)                                           \
-               : bd.classic ? launch_reset<N, false, true>(bd, lc, m, o, ob)                                     \
-                            : launch_reset<N, false, false>(bd, lc, m, o, ob);                                                                     \
+        return JSL_BY_KIND(bd, launch_reset, N, bd, lc, m, o, ob);                                                    \
     }                                                                                                                 \
     cudaError_t launch_step_jw##N(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* a, jsl_step_out o, int ob) { \
-        return bd.tcur ? launch_step<N, true, false>(bd, lc, a, o, ob)                                            \
-               : bd.classic ? launch_step<N, false, true>(bd, lc, a, o, ob)                                      \
-                            : launch_step<N, false, false>(bd, lc, a, o, ob);                                                                      \
+        return JSL_BY_KIND(bd, launch_step, N, bd, lc, a, o, ob);                                                     \
     }                                                                                                                 \
     cudaError_t launch_rollout_jw##N(const BatchDev& bd, const LaunchCfg& lc, int p, const uint8_t* t, int64_t ts,    \
                                      int ms, int f, jsl_rollout_out o) {                                              \
-        return bd.tcur ? launch_rollout<N, true, false>(bd, lc, p, t, ts, ms, f, o)                               \
-               : bd.classic ? launch_rollout<N, false, true>(bd, lc, p, t, ts, ms, f, o)                         \
-                            : launch_rollout<N, false, false>(bd, lc, p, t, ts, ms, f, o);                                                         \
+        return JSL_BY_KIND(bd, launch_rollout, N, bd, lc, p, t, ts, ms, f, o);                                        \
     }                                                                                                                 \
     cudaError_t launch_digest_jw##N(const BatchDev& bd, const LaunchCfg& lc, int64_t e, int32_t* o, int c, int32_t* n) { \
-        return bd.tcur ? launch_digest<N, true, false>(bd, lc, e, o, c, n)                                        \
-               : bd.classic ? launch_digest<N, false, true>(bd, lc, e, o, c, n)                                  \
-                            : launch_digest<N, false, false>(bd, lc, e, o, c, n);                                                                  \
+        return JSL_BY_KIND(bd, launch_digest, N, bd, lc, e, o, c, n);                                                 \
     }                                                                                                                 \
-    int rollout_occupancy_jw##N(int smem, bool st, bool cl) {                                                         \
-        return st ? rollout_occupancy<N, true, false>(smem) : cl ? rollout_occupancy<N, false, true>(smem)           \
-                                                                 : rollout_occupancy<N, false, false>(smem);           \
-    }                                      \
-    int state_bytes_jw##N() { return (int)sizeof(EnvS<N, false, false>); }                                                          \
+    int rollout_occupancy_jw##N(const BatchDev& bd, int smem) { return JSL_BY_KIND(bd, rollout_occupancy, N, smem); } \
+    int state_bytes_jw##N() { return (int)sizeof(EnvS<N, false, 0>); }                                                \
     int outs_bytes_jw##N() { return (int)sizeof(OutS<N>); }
 
 }  // namespace jsl

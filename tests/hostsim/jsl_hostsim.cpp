@@ -38,7 +38,7 @@ struct Sim {
     std::vector<uint16_t> tseed;
     uint64_t env_id = 0;
     EnvAux aux;
-    bool classic = false;
+    int classic = 0;  // specialisation level, as in jsl_abi.cu
 };
 
 template <class T, class U>
@@ -78,14 +78,14 @@ void make_ctx(Sim* s, Ctx& c) {
     a.lower_bound = s->lb_mat[0]; a.max_allowed_time = s->lb_mat[1]; a.neg_inv_n = -1.0 / (double)s->I.N;
 }
 
-template <int JW, bool ST, bool CL> int do_reset(Sim* s) {
+template <int JW, bool ST, int CL> int do_reset(Sim* s) {
     EnvS<JW, ST, CL>& st = *(EnvS<JW, ST, CL>*)s->state.data();
     Ctx c; make_ctx(s, c);
     run_env_op(st, c, OP_RESET);
     s->last_reward = 0.0;
     return st.status;
 }
-template <int JW, bool ST, bool CL> int do_step(Sim* s, int action) {
+template <int JW, bool ST, int CL> int do_step(Sim* s, int action) {
     EnvS<JW, ST, CL>& st = *(EnvS<JW, ST, CL>*)s->state.data();
     s->backup = s->state; s->outs_backup = s->outs;
     Ctx c; make_ctx(s, c);
@@ -101,12 +101,12 @@ template <int JW, bool ST, bool CL> int do_step(Sim* s, int action) {
     s->last_reward = r;
     return ((EnvS<JW, ST, CL>*)s->state.data())->status;
 }
-template <int JW, bool ST, bool CL> int do_digest(Sim* s, int32_t* out, int cap) {
+template <int JW, bool ST, int CL> int do_digest(Sim* s, int32_t* out, int cap) {
     EnvS<JW, ST, CL>& st = *(EnvS<JW, ST, CL>*)s->state.data();
     Ctx c; make_ctx(s, c);
     return write_digest(st, c, out, cap);
 }
-template <int JW, bool ST, bool CL> int do_obs(Sim* s, uint8_t* out) {
+template <int JW, bool ST, int CL> int do_obs(Sim* s, uint8_t* out) {
     EnvS<JW, ST, CL>& st = *(EnvS<JW, ST, CL>*)s->state.data();
     Ctx c; make_ctx(s, c);
     if (s->C.obs_kind == JSL_OBS_OPERATION_ARRAY) { write_obs_oparray(st, c, out); return c.raise ? -c.raise : obs_bytes_oparray(s->I.J, s->I.N); }
@@ -114,7 +114,7 @@ template <int JW, bool ST, bool CL> int do_obs(Sim* s, uint8_t* out) {
     write_obs_binary(st, c, out);
     return obs_bytes_binary(s->I.J, s->I.M);
 }
-template <int JW, bool ST, bool CL> int do_rollout(Sim* s, int policy, const uint8_t* tape, int n_tape, int max_steps, uint64_t env_idx) {
+template <int JW, bool ST, int CL> int do_rollout(Sim* s, int policy, const uint8_t* tape, int n_tape, int max_steps, uint64_t env_idx) {
     EnvS<JW, ST, CL>& st = *(EnvS<JW, ST, CL>*)s->state.data();
     Ctx c; make_ctx(s, c);
     int n = 0;
@@ -127,16 +127,16 @@ template <int JW, bool ST, bool CL> int do_rollout(Sim* s, int policy, const uin
     }
     return n;
 }
-template <int JW, bool ST, bool CL> void get_scalars(Sim* s, int32_t* o) {
+template <int JW, bool ST, int CL> void get_scalars(Sim* s, int32_t* o) {
     EnvS<JW, ST, CL>& st = *(EnvS<JW, ST, CL>*)s->state.data();
     o[0] = st.time; o[1] = st.terminated; o[2] = st.truncated; o[3] = st.status; o[4] = st.n_steps; o[5] = st.noop_count;
     o[6] = st.n_possible - st.skip;
 }
-template <int JW, bool ST, bool CL> double get_ret(Sim* s) { return ((EnvS<JW, ST, CL>*)s->state.data())->ret; }
+template <int JW, bool ST, int CL> double get_ret(Sim* s) { return ((EnvS<JW, ST, CL>*)s->state.data())->ret; }
 
 }  // namespace
 
-#define DISPATCH1(s, F, N, ...) ((s)->tobj.stochastic ? F<N, true, false>(__VA_ARGS__) : (s)->classic ? F<N, false, true>(__VA_ARGS__) : F<N, false, false>(__VA_ARGS__))
+#define DISPATCH1(s, F, N, ...) ((s)->tobj.stochastic ? F<N, true, 0>(__VA_ARGS__) : (s)->classic == 2 ? F<N, false, 2>(__VA_ARGS__) : (s)->classic == 1 ? F<N, false, 1>(__VA_ARGS__) : F<N, false, 0>(__VA_ARGS__))
 #define DISPATCH(s, F, ...) ((s)->JW == 1 ? DISPATCH1(s, F, 1, __VA_ARGS__) : (s)->JW == 2 ? DISPATCH1(s, F, 2, __VA_ARGS__) : DISPATCH1(s, F, 4, __VA_ARGS__))
 
 extern "C" {
@@ -196,7 +196,7 @@ void* jsh_create(const jsl_instance_desc* d, const jsl_env_cfg* cfg, uint64_t se
     C.allow_early_transport = cfg->allow_early_transport; C.truncation_joker = cfg->truncation_joker;
     C.truncation_active = cfg->truncation_active; C.obs_kind = cfg->obs_kind; C.record_ops = cfg->record_ops;
     C.sparse_bias = cfg->sparse_bias; C.dense_bias = cfg->dense_bias; C.truncation_bias = cfg->truncation_bias;
-    s->state_bytes = s->JW == 1 ? sizeof(EnvS<1, false, false>) : s->JW == 2 ? sizeof(EnvS<2, false, false>) : sizeof(EnvS<4, false, false>);
+    s->state_bytes = s->JW == 1 ? sizeof(EnvS<1, false, 0>) : s->JW == 2 ? sizeof(EnvS<2, false, 0>) : sizeof(EnvS<4, false, 0>);
     s->outs_bytes = (I.has_m_out || I.has_t_out) ? (s->JW == 1 ? sizeof(OutS<1>) : s->JW == 2 ? sizeof(OutS<2>) : sizeof(OutS<4>)) : 0;
     s->state.assign(s->state_bytes + 16, 0); s->outs.assign(s->outs_bytes + 16, 0);
     s->op_log.assign((size_t)2 * I.N + 2, -1);
@@ -211,8 +211,13 @@ void* jsh_create(const jsl_instance_desc* d, const jsl_env_cfg* cfg, uint64_t se
         I.off_travel = s->tobj.off_travel; I.off_mof = s->tobj.off_mof; I.off_mod = s->tobj.off_mod;
         I.off_tof = s->tobj.off_tof; I.off_tod = s->tobj.off_tod;
     }
-    s->classic = I.flex_pre && I.flex_post && I.caps_inf && !I.has_m_out && !I.has_t_out && !I.setup && !I.travel &&
-                 !s->tobj.stochastic && I.out_buf >= 0 && !std::getenv("JSL_HOSTSIM_NO_CLASSIC");
+    {
+        const bool simple = I.flex_pre && I.flex_post && I.caps_inf && !I.has_m_out && !I.has_t_out && !I.setup &&
+                            !s->tobj.stochastic && I.out_buf >= 0;
+        const char* lvl = std::getenv("JSL_HOSTSIM_MAX_LEVEL");  // cap the specialisation level (tests)
+        s->classic = !simple ? 0 : I.travel ? 1 : 2;
+        if (lvl && s->classic > std::atoi(lvl)) s->classic = std::atoi(lvl);
+    }
     return s;
 }
 void jsh_destroy(void* h) { delete (Sim*)h; }
