@@ -11,4 +11,8 @@ def __getattr__(name):
         from . import env
 
         return getattr(env, name)
+    if name == "SB3VecEnv":
+        from . import vec_env
+
+        return vec_env.SB3VecEnv
     raise AttributeError(name)

@@ -41,7 +41,6 @@
 #define JSL_SYNCWARP() __syncwarp()
 #define JSL_POPC(x) __popc(x)
 #define JSL_FFS(x) __ffs(x)
-#define JSL_FNS(x, n) __fns((x), 0, (n))
 #else
 #define JSL_D static inline
 #define JSL_M inline
@@ -49,13 +48,6 @@
 #define JSL_SYNCWARP() ((void)0)
 #define JSL_POPC(x) __builtin_popcount(x)
 #define JSL_FFS(x) __builtin_ffs((int)(x))
-static inline unsigned jsl_fns_host(unsigned x, int n) {
-    for (unsigned b = 0; b < 32; b++)
-        if ((x >> b) & 1u)
-            if (--n == 0) return b;
-    return 0xffffffffu;
-}
-#define JSL_FNS(x, n) jsl_fns_host((x), (n))
 #endif
 
 namespace jsl {

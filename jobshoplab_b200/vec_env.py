@@ -1,0 +1,202 @@
+"""Vector-env adapters over BatchedJobShopLabEnv.
+
+The reference reserved jobshoplab/env/env_wrapper.py and tests/end_to_end_tests/test_vec_env_end_to_end.py for a
+vectorised env and shipped neither; its notebooks train PPO (stable-baselines3) on the single env.  `SB3VecEnv`
+speaks the stable_baselines3 ``VecEnv`` protocol -- ``reset() -> obs``, ``step_async(actions)``,
+``step_wait() -> (obs, rewards, dones, infos)`` with SB3's auto-reset convention (a finished env is reset at once,
+its last observation goes to ``infos[i]["terminal_observation"]``, ``infos[i]["TimeLimit.truncated"]`` tells a
+truncation from a termination), ``get_attr / set_attr / env_method / env_is_wrapped / seed / close`` -- with numpy
+observations, so PPO consumes B GPU envs like any other VecEnv.  If stable_baselines3 is importable the class derives
+from its ``VecEnv``; it does not need it (neither SB3 nor gymnasium exist in the build container: spaces fall back to
+the small stand-ins below, which carry the reference's shapes / dtypes / bounds, observations.py:388-409, :507).
+
+Everything on the device stays in BatchedJobShopLabEnv; this module only moves the observation record and the
+per-step scalars to the host once per step.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+
+from . import abi
+from .env import BatchedJobShopLabEnv
+
+try:  # pragma: no cover - not installed in the build container
+    from gymnasium import spaces as _spaces
+except Exception:  # noqa: BLE001
+    _spaces = None
+
+try:  # pragma: no cover
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
+except Exception:  # noqa: BLE001
+    _VecEnvBase = object
+
+
+class Box:
+    """Stand-in for gymnasium.spaces.Box (shape / dtype / bounds only)."""
+
+    def __init__(self, low, high, shape, dtype):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), np.dtype(dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low)) and bool(np.all(x <= self.high))
+
+    def __repr__(self):
+        return f"Box({self.low}, {self.high}, {self.shape}, {self.dtype})"
+
+
+class DictSpace:
+    """Stand-in for gymnasium.spaces.Dict."""
+
+    def __init__(self, spaces):
+        self.spaces = OrderedDict(spaces)
+
+    def __getitem__(self, k):
+        return self.spaces[k]
+
+    def keys(self):
+        return self.spaces.keys()
+
+    def __repr__(self):
+        return f"Dict({dict(self.spaces)})"
+
+
+class DiscreteSpace:
+    def __init__(self, n):
+        self.n = int(n)
+
+    def contains(self, x):
+        return 0 <= int(x) < self.n
+
+    def sample(self):
+        return int(np.random.randint(0, self.n))
+
+
+def observation_space(obs_kind: int, J: int, M: int, N: int):
+    """The declared spaces of the reference's observation factories (observations.py:388-409, :507, :575-586,
+    :712-741), as gymnasium spaces when gymnasium is installed."""
+    box = _spaces.Box if _spaces else Box
+    dct = _spaces.Dict if _spaces else DictSpace
+    if obs_kind == abi.OBS_BINARY_ACTION:
+        sp = OrderedDict(
+            job_running=box(low=0, high=1, shape=(J,), dtype=np.int8),
+            job_executed_on_machine=box(low=0, high=1, shape=(J, M), dtype=np.int8),
+            job_progression=box(low=0, high=J, shape=(J,), dtype=np.int32),
+            machine_running=box(low=0, high=1, shape=(M,), dtype=np.int8),
+            machine_progression=box(low=0, high=J, shape=(M,), dtype=np.int32),
+            available_jobs=box(low=0, high=1, shape=(J,), dtype=np.int8),
+            current_time=box(low=0, high=1.0, shape=(1,), dtype=np.float32),
+            current_transition=box(low=0, high=1, shape=(3,), dtype=np.float32))
+    elif obs_kind == abi.OBS_OPERATION_ARRAY:
+        sp = OrderedDict(
+            operation_state=box(low=0, high=1, shape=(1, N), dtype=np.float32),
+            job_locations=box(low=0, high=1, shape=(1, J), dtype=np.float32),
+            current_transition=box(low=0, high=1, shape=(3,), dtype=np.float32))
+    elif obs_kind == abi.OBS_TASSEL:
+        keys = ("allocatable", "left_over_time", "percent_finished", "total_completion",
+                "time_until_next_machine_is_free", "idle_since_last_op", "cum_idle_time")
+        sp = OrderedDict((k, box(low=0, high=1, shape=(J,), dtype=np.float32)) for k in keys)
+    else:
+        sp = OrderedDict()
+    return dct(sp)
+
+
+class SB3VecEnv(_VecEnvBase):
+    """stable_baselines3-style VecEnv over B GPU envs (see the module docstring)."""
+
+    def __init__(self, config=None, num_envs: int = 1, **kw):
+        self.venv = kw.pop("venv", None) or BatchedJobShopLabEnv(config, num_envs=num_envs, auto_reset=False, **kw)
+        b = self.venv.batch
+        self.num_envs = self.venv.num_envs
+        self.observation_space = observation_space(b.cfg.obs_kind, b.shape.n_jobs, b.shape.n_machines, b.shape.n_ops)
+        self.action_space = _spaces.Discrete(2) if _spaces else DiscreteSpace(2)
+        self.render_mode = None
+        self.metadata = {"render_modes": []}
+        self._torch = b.torch
+        self._actions = self._torch.zeros(self.num_envs, dtype=self._torch.uint8, device=f"cuda:{b.device}")
+        self._episode_return = np.zeros(self.num_envs, np.float64)
+        self._episode_length = np.zeros(self.num_envs, np.int64)
+        self._pending = False
+
+    # ------------------------------------------------------------------ helpers
+    def _host_obs(self, views) -> "OrderedDict[str, np.ndarray]":
+        return OrderedDict((k, views[k].cpu().numpy().copy()) for k in self.observation_space.keys())
+
+    # ------------------------------------------------------------------ VecEnv protocol
+    def reset(self):
+        views, _ = self.venv.reset()
+        self._episode_return[:] = 0
+        self._episode_length[:] = 0
+        return self._host_obs(views)
+
+    def step_async(self, actions):
+        a = np.asarray(actions).astype(np.uint8).reshape(self.num_envs)
+        self._actions.copy_(self._torch.from_numpy(a), non_blocking=True)
+        self._out = self.venv.batch.step(self._actions)
+        self._pending = True
+
+    def step_wait(self):
+        assert self._pending, "step_wait() without step_async()"
+        self._pending = False
+        out, batch = self._out, self.venv.batch
+        rewards = out.reward.cpu().numpy().astype(np.float32)
+        terminated = out.terminated.cpu().numpy().astype(bool)
+        truncated = out.truncated.cpu().numpy().astype(bool)
+        makespan = out.makespan.cpu().numpy()
+        status = out.status.cpu().numpy()
+        dones = terminated | truncated
+        self._episode_return += rewards
+        self._episode_length += 1
+        obs = self._host_obs(batch.unpack_obs(out.obs))
+        infos = [{} for _ in range(self.num_envs)]
+        if dones.any():
+            idx = np.nonzero(dones)[0]
+            for i in idx:
+                infos[i] = {"terminal_observation": OrderedDict((k, v[i].copy()) for k, v in obs.items()),
+                            "TimeLimit.truncated": bool(truncated[i] and not terminated[i]),
+                            "makespan": int(makespan[i]) if terminated[i] else None, "status": int(status[i]),
+                            "episode": {"r": float(self._episode_return[i]), "l": int(self._episode_length[i])}}
+            mask = self._torch.from_numpy(dones.astype(np.uint8)).to(self._actions.device)
+            views, _ = self.venv.reset(mask)  # (redraws the instances of those envs under InstanceRandomizer)
+            fresh = self._host_obs(views)
+            for k in obs:
+                obs[k][idx] = fresh[k][idx]
+            self._episode_return[idx] = 0
+            self._episode_length[idx] = 0
+        return obs, rewards, dones, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        self.venv.close()
+
+    def seed(self, seed=None):
+        return [None] * self.num_envs  # the engine is deterministic given the batch seed
+
+    def _indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        return [indices] if isinstance(indices, int) else indices
+
+    def get_attr(self, attr_name, indices=None):
+        src = self.venv if hasattr(self.venv, attr_name) else self.venv.batch
+        return [getattr(src, attr_name) for _ in self._indices(indices)]
+
+    def set_attr(self, attr_name, value, indices=None):
+        setattr(self.venv, attr_name, value)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        return [getattr(self.venv, method_name)(*args, **kwargs) for _ in self._indices(indices)]
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False for _ in self._indices(indices)]
+
+    def get_images(self):
+        return [None] * self.num_envs
+
+    def render(self, mode=None):
+        return None

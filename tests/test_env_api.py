@@ -143,3 +143,42 @@ def test_render_data_matches_reference_dashboard_model():
         text = env.render()
         assert len(text.splitlines()) == len(want["schedules"]) + len(want["transports"])
         env.close()
+
+
+def test_sb3_style_vec_env_matches_single_env():
+    """the stable_baselines3 VecEnv protocol over B GPU envs; env 3 of the vector env is compared with
+    the single drop-in env fed the same actions, across auto-resets."""
+    from jobshoplab_b200 import Config
+    from jobshoplab_b200 import compiler as C
+    from jobshoplab_b200.vec_env import SB3VecEnv
+
+    sc = G.Scenario("classic", "ft06/fifo")
+    li = C.compile_spec_text(sc.source_text)
+    B = 16
+    venv = SB3VecEnv(Config(), num_envs=B, compiler=li, seed=1)
+    single, _ = _env("classic", "ft06/fifo")
+    obs = venv.reset()
+    sp = venv.observation_space
+    for k in sp.keys():
+        assert obs[k].shape == (B,) + tuple(sp[k].shape) and obs[k].dtype == sp[k].dtype, k
+    rng = np.random.default_rng(0)
+    episodes = 0
+    for step in range(400):
+        acts = rng.integers(0, 2, B)
+        venv.step_async(acts)
+        obs, rew, dones, infos = venv.step_wait()
+        o1, r1, term, trunc, info1 = single.step(int(acts[3]))
+        assert rew.dtype == np.float32 and np.float32(r1) == rew[3] and dones[3] == (term or trunc)
+        if dones[3]:
+            episodes += 1
+            t = infos[3]["terminal_observation"]
+            assert np.allclose(t["current_transition"], 1.0) and infos[3]["makespan"] == info1["makespan"]
+            assert infos[3]["TimeLimit.truncated"] is False and infos[3]["episode"]["l"] > 36
+            for k in sp.keys():
+                assert np.array_equal(np.asarray(o1[k]).astype(t[k].dtype).reshape(t[k].shape), t[k]), k
+            o1, _ = single.reset()
+        for k in sp.keys():
+            assert np.array_equal(np.asarray(o1[k]).astype(obs[k].dtype).reshape(obs[k][3].shape), obs[k][3]), (step, k)
+    assert episodes >= 3
+    assert venv.env_is_wrapped(object) == [False] * B and len(venv.get_attr("num_envs")) == B
+    venv.close(); single.close()
