@@ -17,7 +17,9 @@ from jobshoplab_b200 import lowered as L  # noqa: E402
 from oracle import oracle_py as op  # noqa: E402
 
 
-def random_instance(rng) -> tuple[L.LoweredInstance, dict]:
+def random_instance(rng, simple=None) -> tuple[L.LoweredInstance, dict]:
+    """simple: None = anything; 1 = a 'simple' instance (FLEX unbounded buffers, no setup / outages: specialisation
+    level 1 of the engine); 2 = 'classic' (simple with zero travel times: level 2, the fast paths)."""
     J, M = int(rng.integers(1, 8)), int(rng.integers(1, 6))
     T = int(rng.integers(1, J + 2))
     S = 2
@@ -59,14 +61,23 @@ def random_instance(rng) -> tuple[L.LoweredInstance, dict]:
     if rng.random() < 0.3:
         for _ in range(int(rng.integers(1, 3))):
             t_of.append(int(rng.integers(0, 30))); t_od.append(int(rng.integers(0, 5)))
+    if simple:
+        btypes = lambda n: [L.BUF_FLEX] * n
+        caps = lambda n: [L.CAP_INF] * n
+        setup = np.zeros((M, nt, nt), dtype=np.int32)
+        m_out_start, m_of, m_od, t_of, t_od = [0] * (M + 1), [], [], [], []
+        if simple == 2:
+            travel = np.zeros((NP, NP), dtype=np.int32)
+        elif not travel.any():
+            travel[0, NP - 1] = 2
     NB = 3 * M + T + S
     li = L.LoweredInstance(
         description="fuzz", n_jobs=J, n_machines=M, n_transports=T, n_sbuf=S, n_tools=nt,
         job_op_start=job_op_start, op_machine=op_machine, op_tool=op_tool, op_duration=op_dur,
         pre_type=btypes(M), pre_cap=caps(M), post_type=btypes(M), post_cap=caps(M),
         setup_time=setup.reshape(-1), default_tool=0,
-        sbuf_type=[int(rng.choice([L.BUF_FLEX, L.BUF_FIFO, L.BUF_LIFO])) if rng.random() < 0.3 else L.BUF_FLEX, L.BUF_FLEX],
-        sbuf_cap=[L.CAP_INF, L.CAP_INF if rng.random() < 0.8 else max(1, J - 1)],
+        sbuf_type=[int(rng.choice([L.BUF_FLEX, L.BUF_FIFO, L.BUF_LIFO])) if (rng.random() < 0.3 and not simple) else L.BUF_FLEX, L.BUF_FLEX],
+        sbuf_cap=[L.CAP_INF, L.CAP_INF if (rng.random() < 0.8 or simple) else max(1, J - 1)],
         sbuf_role=[L.ROLE_INPUT, L.ROLE_OUTPUT], buf_ref_id=np.arange(NB), travel_time=travel.reshape(-1),
         agv_init_place=[int(rng.integers(0, NP if rng.random() < 0.2 else M)) for _ in range(T)],
         job_init_buf=[3 * M + T] * J, start_time=int(rng.choice([0, 0, 3])),
@@ -77,8 +88,8 @@ def random_instance(rng) -> tuple[L.LoweredInstance, dict]:
     return li, cfg
 
 
-def run_one(rng, max_steps=400):
-    li, cfg = random_instance(rng)
+def run_one(rng, max_steps=400, simple=None):
+    li, cfg = random_instance(rng, simple)
     e, o = HostSimEnv(li, **cfg), op.OracleEnv(li, **cfg)
     p = float(rng.choice([0.5, 0.8, 1.0]))
     steps = 0
@@ -113,7 +124,7 @@ def main(n=300, seed=0):
         sub = np.random.default_rng(rng.integers(0, 2**63))
         state = sub.bit_generator.state
         try:
-            steps, st = run_one(sub)
+            steps, st = run_one(sub, simple=(None, None, 1, 2)[i % 4])  # half general, a quarter each specialised level
         except AssertionError as ex:
             print(f"FUZZ FAILURE at instance {i} (seed {seed}): {str(ex)[:3000]}")
             raise SystemExit(1)
