@@ -1,6 +1,7 @@
 """Throughput + correctness of the other BASELINE.json configs on one GPU (rollout mode, 65 536 replicas):
 ft10 / la16 SPT / MWKR (bit-exact makespans), transport ft10-t / la01-t with random actions, the stochastic
-ft20-t variant (setup times, breakdowns, Poisson travel).  Prints one JSON line per workload.
+ft20-t variant (setup times, breakdowns, Poisson travel), FIFO buffers with capacity 5 (BASELINE config 4).
+Prints one JSON line per workload.
 
     python profiles/secondary_bench.py [B]
 """
@@ -61,6 +62,19 @@ def main():
                               "makespan_max": int(r.makespan.max()),
                               "bit_exact_vs_reference": None if exp is None else bool((r.makespan == exp).all()),
                               "terminated": int((r.status == 1).sum())}))
+        batch.close()
+    # BASELINE config 4: FIFO pre/post buffers with capacity 5 (general kernel); random actions may run a buffer full
+    for name in ("la01-t/fifo5/random0", "ft06-t/fifo5/random0"):
+        sc = G.Scenario("buffers", name)
+        batch = engine.Batch(sc.lowered, B, seed=sc.meta["seed"], **sc.cfg)
+        r, rate = timed(batch, "random")
+        st = r.status.cpu().numpy()
+        e0 = sc.meta["env_idx"]
+        print(json.dumps({"workload": f"{name.rsplit('/', 1)[0]} (FIFO buffers, capacity 5) x{B} random",
+                          "env_steps_per_sec": rate, "terminated": int((st == 1).sum()),
+                          "buffer_full": int((st == 4).sum()), "other_status": int(((st != 1) & (st != 4)).sum()),
+                          "bit_exact_vs_reference": bool(int(r.makespan[e0]) == sc.meta["makespan"] and
+                                                         int(r.n_steps[e0]) == sc.meta["n_steps"])}))
         batch.close()
     fx = G.KsFixture("ft20-t_features")
     batch = engine.Batch(fx.lowered, B, seed=5)

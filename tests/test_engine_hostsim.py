@@ -54,6 +54,19 @@ def test_engine_source_matches_reference_traces(group):
             raise AssertionError(f"{group}:{name}: {ex}") from ex
 
 
+@pytest.mark.parametrize("level", ["0", "1"])
+def test_specialisation_levels_agree(level, monkeypatch):
+    """Classic instances are normally served by the level-2 code (fast paths), transport instances by level 1:
+    forced down to the simple / general code they must reproduce the same reference traces."""
+    monkeypatch.setenv("JSL_HOSTSIM_MAX_LEVEL", level)
+    for group in ("classic", "transport"):
+        for name in PICK[group][:6]:
+            try:
+                replay(G.Scenario(group, name))
+            except AssertionError as ex:
+                raise AssertionError(f"level {level} {group}:{name}: {ex}") from ex
+
+
 def test_engine_policies():
     for name in ("ft06/spt", "ft10/mwkr", "la16/spt", "ta01/fifo", "ft06/random2"):
         sc = G.Scenario("classic", name)
