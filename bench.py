@@ -252,22 +252,43 @@ def main():
     ok = int((batch.rout.status == 1).sum().item())
 
     # ---- e2e: host buffers in, host results out, through the public API -----------------------------
-    def e2e_pass():
-        batch.load_variants(*pin)
+    # Every pass uploads its own inputs (the 1.26 GB of op tables) from pinned host memory and reads its results
+    # back.  The upload of pass k+1 goes to staging buffers on a copy stream while pass k's rollout runs; the
+    # staged tables are committed (packed into the live tables) on the compute stream between the rollouts.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    packed = torch.cuda.Event()
+
+    def stage():
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(packed)      # the previous commit has consumed the staging area
+            batch.stage_variants(*pin)
+
+    def e2e_pass(more):
+        main_stream.wait_stream(copy_stream)    # this pass's inputs are on the device
+        batch.commit_variants()
+        packed.record(main_stream)
+        if more:
+            stage()                             # next pass's upload overlaps this pass's rollout
         r = batch.rollout("random", reset_first=True, writeback=False)
         for h, d in zip(host_out, (r.makespan, r.n_steps, r.ret, r.status)):
             h.copy_(d, non_blocking=True)
 
-    e2e_pass()
+    packed.record(main_stream)
+    stage()
+    e2e_pass(False)                             # untimed warm-up pass
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        e2e_pass()
+    copy_stream.wait_event(e0)
+    stage()                                     # the first timed pass's upload: nothing to hide it behind
+    for k in range(args.steps):
+        e2e_pass(k + 1 < args.steps)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     e2e_steps = int(host_out[1].sum().item())
+    assert e2e_steps == steps_per_pass, "the pipelined upload changed the instances"  # same tables, same streams
     h2d = sum(t.numel() * t.element_size() for t in pin)
     d2h = sum(t.numel() * t.element_size() for t in host_out)
 
@@ -340,8 +361,9 @@ def main():
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": total_e2e_steps / (e2e_ms / 1e3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
-                    "what": "jsl_batch_load_variants (pinned host op tables -> device) + jsl_rollout + D2H of "
-                            "makespan/n_steps/return/status, per pass"},
+                    "what": "per pass: pinned host op tables -> device (jsl_batch_stage_variants on a copy stream, "
+                            "overlapping the previous pass's rollout) + jsl_batch_commit_variants + jsl_rollout + D2H of "
+                            "makespan/n_steps/return/status; the first timed pass's upload is inside the timed region"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_rollout<1>", "peak_source": peak_src,
                          "bytes_per_env_step": BYTES_PER_STEP,

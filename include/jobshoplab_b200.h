@@ -213,6 +213,13 @@ jsl_batch_t* jsl_batch_create_variants(const jsl_instance_t* tmpl, int64_t n_ins
  * jsl_batch_create_variants; packed on the device by a small kernel on `stream`. */
 int jsl_batch_load_variants(jsl_batch_t*, const int32_t* op_machine, const int32_t* op_duration,
                             const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream);
+/* The two halves of jsl_batch_load_variants, for pipelining: `stage` only copies the host arrays into staging
+ * buffers on `stream` (it may overlap a rollout that still reads the live tables, e.g. on a copy stream);
+ * `commit` packs the staged tables into the live ones on `stream` (order it after the kernels that read them and
+ * after the staging copies).  One staging area per batch: stage again only after the commit has run. */
+int jsl_batch_stage_variants(jsl_batch_t*, const int32_t* op_machine, const int32_t* op_duration,
+                             const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream);
+int jsl_batch_commit_variants(jsl_batch_t*, void* stream);
 /* compiler/manipulators.py:99-150 InstanceRandomizer.manipulate for every variant of the batch, on the device:
  * per job a uniformly random permutation of its operations (machine and tool travel together) and durations
  * uniform in [min_duration, max_duration) (random.randrange); per-job work, the lower bound and

@@ -388,8 +388,9 @@ jsl_batch_t* jsl_batch_create_variants(const jsl_instance_t* tmpl, int64_t n_ins
     return build_batch(tmpl, n_inst, op_machine, op_duration, lower_bound, max_allowed_time, B, device, seed, cfg);
 }
 
-int jsl_batch_load_variants(jsl_batch_t* b, const int32_t* op_machine, const int32_t* op_duration,
-                            const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream) {
+// stage: host -> device staging buffers (overlaps a running rollout: the live tables are not touched)
+int jsl_batch_stage_variants(jsl_batch_t* b, const int32_t* op_machine, const int32_t* op_duration,
+                             const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream) {
     if (!b || !op_machine || !op_duration || !lower_bound || !max_allowed_time) return JSL_E_INVALID;
     CK(cudaSetDevice(b->device));
     const InstDev& I = b->bd.inst;
@@ -406,12 +407,29 @@ int jsl_batch_load_variants(jsl_batch_t* b, const int32_t* op_machine, const int
     CK(cudaMemcpyAsync(sd, op_duration, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(sl, lower_bound, ni * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(sa, max_allowed_time, ni * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    k_pack_variants<<<b->sm_count * 8, 256, 0, st>>>(I.n_inst, I.N, I.J, I.job_op_start, b->d_op_tool, sm, sd, sl, sa,
-                                                     (int32_t*)I.op_mt, (int32_t*)I.op_dur, (int32_t*)I.job_work,
-                                                     (int32_t*)I.lb_mat);
+    return JSL_OK;
+}
+
+// commit: pack the staged tables into the live ones (must be ordered after the last kernel that reads them)
+int jsl_batch_commit_variants(jsl_batch_t* b, void* stream) {
+    if (!b) return JSL_E_INVALID;
+    if (!b->d_stage) { set_err("nothing staged"); return JSL_E_INVALID; }
+    CK(cudaSetDevice(b->device));
+    const InstDev& I = b->bd.inst;
+    const size_t n = (size_t)I.n_inst * I.N, ni = (size_t)I.n_inst;
+    int32_t *sm = b->d_stage, *sd = sm + n, *sl = sd + n, *sa = sl + ni;
+    k_pack_variants<<<b->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(I.n_inst, I.N, I.J, I.job_op_start, b->d_op_tool, sm, sd, sl, sa,
+                                                                      (int32_t*)I.op_mt, (int32_t*)I.op_dur, (int32_t*)I.job_work,
+                                                                      (int32_t*)I.lb_mat);
     b->launches++;
     CK(cudaGetLastError());
     return JSL_OK;
+}
+
+int jsl_batch_load_variants(jsl_batch_t* b, const int32_t* op_machine, const int32_t* op_duration,
+                            const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream) {
+    int rc = jsl_batch_stage_variants(b, op_machine, op_duration, lower_bound, max_allowed_time, stream);
+    return rc != JSL_OK ? rc : jsl_batch_commit_variants(b, stream);
 }
 
 int jsl_batch_randomize(jsl_batch_t* b, uint64_t seed, int min_duration, int max_duration, const uint8_t* mask,

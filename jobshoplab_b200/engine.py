@@ -23,7 +23,7 @@ LOG_LIB_PATH = Path(os.environ.get("JSL_LOG_LIB", Path(__file__).resolve().paren
 _libs: dict = {}
 
 ABI_SYMBOLS = ("jsl_last_error", "jsl_abi_version", "jsl_instance_create", "jsl_instance_destroy", "jsl_batch_create",
-               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_randomize", "jsl_batch_get_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
+               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_stage_variants", "jsl_batch_commit_variants", "jsl_batch_randomize", "jsl_batch_get_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
                "jsl_reset", "jsl_step", "jsl_rollout", "jsl_get_state", "jsl_get_op_log", "jsl_get_leg_log", "jsl_launch_count")
 
 RO_RESET_FIRST, RO_NO_WRITEBACK = 1, 2
@@ -51,6 +51,8 @@ def load_library(log: bool = False):
     L.jsl_batch_create_variants.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int64, C.c_int, C.c_uint64, C.POINTER(abi.EnvCfg)]
     L.jsl_batch_load_variants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.jsl_batch_stage_variants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.jsl_batch_commit_variants.argtypes = [C.c_void_p, C.c_void_p]
     L.jsl_batch_randomize.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.jsl_batch_get_variants.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 5
     L.jsl_batch_destroy.argtypes = [C.c_void_p]
@@ -195,18 +197,32 @@ class Batch:
     def set_env_base(self, env_base: int):
         self._check(self.L.jsl_batch_set_env_base(self.h, int(env_base)))
 
-    def load_variants(self, op_machine, op_duration, lower_bound, max_allowed_time):
-        """Upload new operation tables for every variant from HOST int32 tensors/arrays (pinned torch
-        tensors make the copies asynchronous on the current stream)."""
+    def _host_ptrs(self, arrays):
         ptrs = []
-        for a in (op_machine, op_duration, lower_bound, max_allowed_time):
+        for a in arrays:
             if hasattr(a, "data_ptr"):
                 assert not a.is_cuda and a.dtype == self.torch.int32 and a.is_contiguous()
                 ptrs.append(a.data_ptr())
             else:
                 assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
                 ptrs.append(a.ctypes.data)
+        return ptrs
+
+    def load_variants(self, op_machine, op_duration, lower_bound, max_allowed_time):
+        """Upload new operation tables for every variant from HOST int32 tensors/arrays (pinned torch
+        tensors make the copies asynchronous on the current stream)."""
+        ptrs = self._host_ptrs((op_machine, op_duration, lower_bound, max_allowed_time))
         self._check(self.L.jsl_batch_load_variants(self.h, *ptrs, self._stream()))
+
+    def stage_variants(self, op_machine, op_duration, lower_bound, max_allowed_time):
+        """First half of load_variants: host -> staging buffers on the current stream (e.g. a copy stream, while a
+        rollout still runs on the tables in use)."""
+        ptrs = self._host_ptrs((op_machine, op_duration, lower_bound, max_allowed_time))
+        self._check(self.L.jsl_batch_stage_variants(self.h, *ptrs, self._stream()))
+
+    def commit_variants(self):
+        """Second half: staged tables -> live tables on the current stream."""
+        self._check(self.L.jsl_batch_commit_variants(self.h, self._stream()))
 
     def randomize(self, seed: int, min_duration: int | None = None, max_duration: int | None = None, mask=None):
         """InstanceRandomizer (compiler/manipulators.py:99-150) for the variants of this batch, on the device:
