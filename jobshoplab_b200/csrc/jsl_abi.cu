@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -258,9 +259,15 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     I.flex_pre = all_equal(t->pre_type, JSL_BUF_FLEX);
     I.flex_post = all_equal(t->post_type, JSL_BUF_FLEX) && all_equal(t->sbuf_type, JSL_BUF_FLEX);
     I.caps_inf = all_equal(t->pre_cap, JSL_CAP_INF) && all_equal(t->post_cap, JSL_CAP_INF) && all_equal(t->sbuf_cap, JSL_CAP_INF);
-    const bool simple = I.flex_pre && I.flex_post && I.caps_inf && !I.has_m_out && !I.has_t_out && !I.setup &&
-                        !t->stochastic && I.out_buf >= 0;
-    b->bd.classic = !simple ? 0 : I.travel ? 1 : 2;
+    // specialisation level (jsl_engine.cuh): which features the instance needs compiled in
+    const bool plain = !I.has_m_out && !I.has_t_out && !I.setup && !t->stochastic && I.out_buf >= 0;
+    const bool simple = plain && I.flex_pre && I.flex_post && I.caps_inf;
+    b->bd.classic = simple ? (I.travel ? 1 : 2) : plain ? 3 : 0;
+    if (const char* cap = std::getenv("JSL_MAX_LEVEL")) {  // diagnostics: force a less specialised kernel
+        const int lv = std::atoi(cap);
+        if (b->bd.classic == 3) { if (lv == 0) b->bd.classic = 0; }
+        else if (b->bd.classic > lv) b->bd.classic = lv < 0 ? 0 : lv;
+    }
     CfgDev& C = b->bd.cfg;
     C.allow_early_transport = cfg->allow_early_transport; C.truncation_joker = cfg->truncation_joker;
     C.truncation_active = cfg->truncation_active; C.obs_kind = cfg->obs_kind; C.record_ops = cfg->record_ops;

@@ -14,7 +14,9 @@
 // Template parameters of everything below: JW = lane words (ceil(max(J,T)/32)), ST = the instance has
 // stochastic time objects, CL = specialisation level: 0 general; 1 "simple" (all buffers FLEX and unbounded, no
 // setup times, no outages, deterministic: capacity / position / TimeDependency / outage / setup code is compiled
-// out); 2 "classic" (simple + all travel times zero: no travel lookups, start / completion chains in one batch).
+// out); 2 "classic" (simple + all travel times zero: no travel lookups, start / completion chains in one batch);
+// 3 "queues" (deterministic, no setup times, no outages, but FIFO / LIFO / DUMMY buffers and finite capacities:
+// only the outage and setup code is compiled out).  JSL_LVL_BUF / JSL_LVL_OUT name what a level keeps.
 // The hot loop has to stay inside the instruction cache: one call site per phase (sm_step, run_env_op),
 // rare paths out of line (JSL_DN), rarely used per-env constants in EnvAux (shared memory).
 //
@@ -211,6 +213,8 @@ struct Ctx {
 };
 
 #define JSL_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define JSL_LVL_BUF(CL) ((CL) == 0 || (CL) == 3)  // ordered / bounded buffers, TimeDependency, state-graph validation
+#define JSL_LVL_OUT(CL) ((CL) == 0)               // outages, setup times
 #define JSL_RAISE(c, code)          \
     do {                            \
         if (!(c).raise) (c).raise = (code); \
@@ -425,16 +429,33 @@ JSL_D bool ready_for_pickup_lane(const EnvS<JW, ST, CL>& s, const InstDev& I, in
     if (ty == JSL_BUF_FLEX) return true;
     uint32_t sq = s.j_seq[j];
     bool ok = true;
+#pragma unroll 1
     for (int q = 0; q < I.J; q++)
         if (s.j_loc[q] == b && (ty == JSL_BUF_LIFO ? s.j_seq[q] > sq : s.j_seq[q] < sq)) ok = false;
     return ok;
+}
+
+// get_next_job_from_buffer (buffer_type_utils.py:236-262) evaluated by ONE lane with a serial scan over the jobs:
+// every lane can look at a different buffer, so all queues of a batch are resolved in one pass.  -1 = None.
+template <int JW, bool ST, int CL>
+JSL_D int queue_next_lane(const EnvS<JW, ST, CL>& s, const InstDev& I, int b, int ty) {
+    if (ty == JSL_BUF_FLEX) return -1;
+    const bool lifo = ty == JSL_BUF_LIFO;
+    int best = -1;
+    uint32_t bs = 0;
+#pragma unroll 1
+    for (int j = 0; j < I.J; j++) {
+        const uint32_t sq = s.j_seq[j];
+        if (s.j_loc[j] == b && (best < 0 || (lifo ? sq > bs : sq < bs))) { best = j; bs = sq; }
+    }
+    return best;
 }
 
 // buffer_type_utils.py:77-105 put_in_buffer (multi-slot buffers)
 template <int JW, bool ST, int CL>
 JSL_D void put_in_buffer(EnvS<JW, ST, CL>& s, Ctx& c, int b, int j) {
     const InstDev& I = *c.I;
-    if (JSL_UNLIKELY(!CL && !I.caps_inf)) {
+    if (JSL_UNLIKELY(JSL_LVL_BUF(CL) && !I.caps_inf)) {
         int cap = buf_cap(I, b);
         if (cap != JSL_CAP_INF && buf_count(s, I, b) >= cap) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
     }
@@ -538,7 +559,7 @@ JSL_D int op_duration(const Ctx& c, int o) { return ST ? c.aux->tcur[o] : c.aux-
 template <bool ST, int CL>
 JSL_D int setup_time_cur(const Ctx& c, int i) {
     if (ST) return c.aux->tcur[c.I->off_setup + i];
-    return (!CL && c.I->setup) ? c.I->setup[i] : 0;
+    return (JSL_LVL_OUT(CL) && c.I->setup) ? c.I->setup[i] : 0;
 }
 template <bool ST, int CL>
 JSL_D int travel_time_cur(const Ctx& c, int a, int b) {
@@ -754,7 +775,7 @@ JSL_D void machine_idle_to_setup(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
     int o = I.job_op_start[j] + s.j_k[j];
     int tool = (c.aux->op_mt[o] >> 16) & 0xffff;
     int setup = 0;
-    if (JSL_UNLIKELY(!CL && (I.setup || ST))) {
+    if (JSL_UNLIKELY(JSL_LVL_OUT(CL) && (I.setup || ST))) {
         const int si = (m * I.NT + s.m_tool[m]) * I.NT + tool;
         setup = setup_time_cur<ST, CL>(c, si);
         if (setup == JSL_NO_TIME && !(ST && I.tobj_kind[I.off_setup + si] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
@@ -783,7 +804,7 @@ template <int JW, bool ST, int CL>
 JSL_D void machine_working_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
     int occupied_for = 0;
-    if (JSL_UNLIKELY(!CL && I.has_m_out)) {
+    if (JSL_UNLIKELY(JSL_LVL_OUT(CL) && I.has_m_out)) {
         int b = I.m_out_start[m], n = I.m_out_start[m + 1] - b;
         OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
         occupied_for = sample_outages<ST>(c, s.draw_ctr, c.now, n, I.m_out_freq + b, I.m_out_dur + b, I.off_mof + b,
@@ -815,7 +836,7 @@ JSL_D void machine_outage_to_idle(EnvS<JW, ST, CL>& s, Ctx& c, int m) {
     s.m_job[m] = NONE8;
     put_in_buffer(s, c, 3 * m + 1, j);
     if (JSL_UNLIKELY(c.raise)) return;
-    if (JSL_UNLIKELY(!CL && I.has_m_out)) {
+    if (JSL_UNLIKELY(JSL_LVL_OUT(CL) && I.has_m_out)) {
         OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
         release_outages(I.m_out_start[m + 1] - I.m_out_start[m], o.mo_active + m * MAX_OUT, o.mo_a + m * MAX_OUT,
                         o.mo_b + m * MAX_OUT);
@@ -830,7 +851,7 @@ JSL_D bool apply_machine(EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int job) {
     // masks of the unchanged state (action); only the TimeDependency hand-me-downs of non-FLEX postbuffers
     // (handler.py:632) can put two transitions of one component into a batch, so the state-graph check
     // (validate.py:30-82) can only fail there
-    if (!CL && !c.I->flex_post && !machine_valid(s, c, m, to, job)) return false;
+    if (JSL_LVL_BUF(CL) && !c.I->flex_post && !machine_valid(s, c, m, to, job)) return false;
     if (JSL_UNLIKELY(c.raise)) return true;
     int from = s.m_state[m];
     if (from == JSL_M_IDLE) machine_idle_to_setup(s, c, m, job);
@@ -956,7 +977,7 @@ JSL_D void agv_to_waitingpickup(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     } else if (is_agv_buf(I, loc)) {
         JSL_RAISE(c, JSL_ST_OTHER_INVALID);
     } else if (loc % 3 == 1) {  // in the machine's postbuffer
-        if (!CL && !ready_for_pickup(s, I, j)) {  // FLEX postbuffers: always ready
+        if (JSL_LVL_BUF(CL) && !ready_for_pickup(s, I, j)) {  // FLEX postbuffers: always ready
             int nxt = next_job_from_buffer(s, I, loc);
             if (nxt < 0) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
             int other = s.j_agv[nxt];
@@ -1020,7 +1041,7 @@ JSL_D void agv_transit_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
     put_in_buffer(s, c, to_buf, j);
     if (JSL_UNLIKELY(c.raise)) return;
     int occupied_for = 0;
-    if (JSL_UNLIKELY(!CL && I.has_t_out)) {
+    if (JSL_UNLIKELY(JSL_LVL_OUT(CL) && I.has_t_out)) {
         OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
         occupied_for = sample_outages<ST>(c, s.draw_ctr, c.now, I.n_t_out, I.t_out_freq, I.t_out_dur, I.off_tof, I.off_tod,
                                       o.to_active + t * MAX_OUT, o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
@@ -1037,14 +1058,14 @@ JSL_D void agv_transit_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
 // process one transport transition; false = validation error
 template <int JW, bool ST, int CL>
 JSL_D bool apply_transport(EnvS<JW, ST, CL>& s, Ctx& c, int t, int to, int job) {
-    if (!CL && !c.I->flex_post && !transport_valid(s, t, to)) return false;
+    if (JSL_LVL_BUF(CL) && !c.I->flex_post && !transport_valid(s, t, to)) return false;
     int from = s.t_state[t];
     if (from == JSL_T_IDLE && to == JSL_T_WORKING) agv_idle_to_working(s, c, t, job);
     else if (from == JSL_T_PICKUP && to == JSL_T_WAITINGPICKUP) agv_to_waitingpickup(s, c, t, job);
     else if ((from == JSL_T_WAITINGPICKUP || from == JSL_T_PICKUP) && to == JSL_T_TRANSIT) agv_to_transit(s, c, t, job);
     else if ((from == JSL_T_WORKING || from == JSL_T_TRANSIT) && to == JSL_T_OUTAGE) agv_transit_to_outage(s, c, t, job);
     else if (from == JSL_T_OUTAGE && to == JSL_T_IDLE) {  // handler.py:961-986
-        if (!CL && c.I->has_t_out) {
+        if (JSL_LVL_OUT(CL) && c.I->has_t_out) {
             OutS<JW>& o = *(OutS<JW>*)c.aux->outs;
             release_outages(c.I->n_t_out, o.to_active + t * MAX_OUT, o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
         }
@@ -1093,24 +1114,22 @@ JSL_D bool create_timed(EnvS<JW, ST, CL>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, 
     });
     time_due = mm.any();
     JSL_SYNCWARP();
-    if (JSL_UNLIKELY(!CL && !I.flex_pre)) {  // handler.py:117-153: automatic start from FIFO/LIFO/DUMMY prebuffers
-        Mask<1> cand = wp_ballot<1>(I.M, [&](int m) {
-            return !mm.test(m) && s.m_state[m] == JSL_M_IDLE && I.pre_type[m] != JSL_BUF_FLEX;
+    if (JSL_UNLIKELY(JSL_LVL_BUF(CL) && !I.flex_pre)) {  // handler.py:117-153: automatic start from FIFO/LIFO/DUMMY prebuffers
+        // lane m scans the jobs for the head / tail of its own prebuffer (one pass for all machines)
+        const Mask<1> started = wp_ballot<1>(I.M, [&](int m) {
+            if (mm.test(m) || s.m_state[m] != JSL_M_IDLE) return false;
+            const int j = queue_next_lane(s, I, 3 * m, I.pre_type[m]);
+            if (j < 0) return false;
+            s.x_mkind[m] = JSL_M_SETUP; s.x_mjob[m] = (uint8_t)j;
+            return true;
         });
-        while (cand.any()) {
-            int m = cand.pop_first();
-            int j = next_job_from_buffer(s, I, 3 * m);
-            if (j >= 0) {
-                s.x_mkind[m] = JSL_M_SETUP; s.x_mjob[m] = (uint8_t)j;
-                mm.w[0] |= 1u << m;
-            }
-        }
+        mm.w[0] |= started.w[0];
     }
     // (a due machine with an empty buffer -- IndexError in the reference -- is caught by the handlers: job == NONE8)
     // transports (a PICKUP/WAITINGPICKUP transport without a job or a TRANSIT one without cargo -- raises in
     // the reference -- is caught by the handlers: job == NONE8)
-    Mask<JW> need_ready, td;
-    const bool flex_post = CL || I.flex_post != 0;
+    Mask<JW> td;
+    const bool flex_post = !JSL_LVL_BUF(CL) || I.flex_post != 0;
     tm = wp_ballot<JW>(I.T, [&](int t) {
         s.x_tkind[t] = NONE8;
         if (s.t_occkind[t] != OCC_TIME || s.t_occ[t] > now) return false;
@@ -1125,33 +1144,31 @@ JSL_D bool create_timed(EnvS<JW, ST, CL>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, 
         } else if (st == JSL_T_TRANSIT) { kind = JSL_T_OUTAGE; job = s.t_carry[t]; }
         else if (st == JSL_T_OUTAGE) { kind = JSL_T_IDLE; job = NONE8; }
         s.x_tkind[t] = (uint8_t)kind; s.x_tjob[t] = (uint8_t)job;
-        if (!CL) s.x_tcomp[t] = (uint8_t)t;
+        if (JSL_LVL_BUF(CL)) s.x_tcomp[t] = (uint8_t)t;
         return true;
     });
     time_due = time_due || tm.any();
     JSL_SYNCWARP();
     if (JSL_UNLIKELY(!flex_post)) {
-        need_ready = wp_ballot<JW>(I.T, [&](int t) { return tm.test(t) && s.t_state[t] == JSL_T_WAITINGPICKUP && s.t_job[t] != NONE8; });
-        while (need_ready.any()) {  // handler.py:191-252: WAITINGPICKUP & ready -> TRANSIT
-            int t = need_ready.pop_first();
-            if (ready_for_pickup(s, I, s.t_job[t])) s.x_tkind[t] = JSL_T_TRANSIT;
-        }
+        // handler.py:191-252: WAITINGPICKUP & ready -> TRANSIT (lane t tests its own job's queue position)
+        wp_for<JW>(I.T, [&](int t) {
+            if (tm.test(t) && s.t_state[t] == JSL_T_WAITINGPICKUP && s.t_job[t] != NONE8 &&
+                ready_for_pickup_lane(s, I, s.t_job[t]))
+                s.x_tkind[t] = JSL_T_TRANSIT;
+        });
     }
-    if (JSL_UNLIKELY(!CL && !I.flex_post)) {  // handler.py:278-326,356-359 resolved TimeDependency -> stored transition
-        td = wp_ballot<JW>(I.T, [&](int t) { return s.t_occkind[t] == OCC_TD; });
-        while (td.any()) {
-            int t = td.pop_first();
-            int b = s.t_tdbuf[t];
-            int nxt = next_job_from_buffer(s, I, b);
-            int mine = s.t_job[t] == NONE8 ? -1 : (int)s.t_job[t];
-            bool resolved = mine == nxt;
-            int blocking = s.t_occ[t];
-            if (!resolved) resolved = s.j_agv[blocking] != NONE8;
-            if (resolved) {
-                s.x_tkind[t] = JSL_T_WAITINGPICKUP; s.x_tcomp[t] = s.t_tdcomp[t]; s.x_tjob[t] = s.t_tdjob[t];
-                tm.w[t >> 5] |= 1u << (t & 31);
-            }
-        }
+    if (JSL_UNLIKELY(JSL_LVL_BUF(CL) && !I.flex_post)) {  // handler.py:278-326,356-359 resolved TimeDependency -> stored transition
+        td = wp_ballot<JW>(I.T, [&](int t) {
+            if (s.t_occkind[t] != OCC_TD) return false;
+            const int b = s.t_tdbuf[t];
+            const int nxt = queue_next_lane(s, I, b, buf_type(I, b));
+            const int mine = s.t_job[t] == NONE8 ? -1 : (int)s.t_job[t];
+            if (mine != nxt && s.j_agv[s.t_occ[t]] == NONE8) return false;  // still blocked, nobody fetches the blocker
+            s.x_tkind[t] = JSL_T_WAITINGPICKUP; s.x_tcomp[t] = s.t_tdcomp[t]; s.x_tjob[t] = s.t_tdjob[t];
+            return true;
+        });
+#pragma unroll
+        for (int w = 0; w < JW; w++) tm.w[w] |= td.w[w];
     }
     JSL_SYNCWARP();
     return mm.any() || tm.any();
@@ -1323,7 +1340,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                 mm.w[0] = 1u << act.comp;
             } else {
                 s.x_tkind[act.comp] = (uint8_t)act.new_state;
-                if (!CL) s.x_tcomp[act.comp] = (uint8_t)act.comp;
+                if (JSL_LVL_BUF(CL)) s.x_tcomp[act.comp] = (uint8_t)act.comp;
                 s.x_tjob[act.comp] = (uint8_t)act.job;
                 tm.w[act.comp >> 5] = 1u << (act.comp & 31);
             }
@@ -1411,7 +1428,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                     int t = idle.pop_first();
                     int j = zr.any() ? zr.pop_first() : zi.pop_first();
                     s.x_tkind[t] = JSL_T_WORKING; s.x_tjob[t] = (uint8_t)j;
-                    if (!CL) s.x_tcomp[t] = (uint8_t)t;
+                    if (JSL_LVL_BUF(CL)) s.x_tcomp[t] = (uint8_t)t;
                     tele.w[t >> 5] |= 1u << (t & 31);
                 }
             }
@@ -1443,7 +1460,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
             Mask<JW> cur = ph == 0 ? tm : tele;
             while (cur.any()) {
                 int t = cur.pop_first();
-                bool ok = apply_transport(s, c, CL ? t : (int)s.x_tcomp[t], s.x_tkind[t], s.x_tjob[t]);
+                bool ok = apply_transport(s, c, JSL_LVL_BUF(CL) ? (int)s.x_tcomp[t] : t, s.x_tkind[t], s.x_tjob[t]);
                 if (JSL_UNLIKELY(c.raise)) return true;
                 if (JSL_UNLIKELY(!ok)) return false;
             }

@@ -44,7 +44,7 @@ struct BatchDev {
     int32_t* tcur;       // [B][n_tobj] current .time of every time object (stochastic instances) or nullptr
     const int32_t* tape; // [B][tape_stride] replayed update() results or nullptr
     int64_t tape_stride;
-    int classic;         // specialisation level CL of jsl_engine.cuh: 0 general, 1 simple, 2 classic
+    int classic;         // specialisation level CL of jsl_engine.cuh: 0 general, 1 simple, 2 classic, 3 queues
     unsigned long long* work_counter;  // next env index of the persistent rollout grid (dynamic work queue)
     uint16_t* tseed;     // [B][n_tobj] numpy seed of every stochastic time object
     const int32_t* start_seeds;  // [B][n_tobj] or nullptr
@@ -95,7 +95,7 @@ inline int slot_bytes(int JW, bool has_outs) {
 }
 template <int JW, int CL>
 __device__ __forceinline__ int slot_stride(const BatchDev& bd) {
-    return (CL || !bd.outs) ? Slot<JW>::BYTES : Slot<JW>::BYTES_OUTS;
+    return (!JSL_LVL_OUT(CL) || !bd.outs) ? Slot<JW>::BYTES : Slot<JW>::BYTES_OUTS;
 }
 
 template <int JW, bool ST, int CL>
@@ -116,7 +116,7 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
     aux->job_work = I.job_work + v * I.J;
     aux->op_log = bd.op_log ? bd.op_log + env * 2 * (int64_t)I.N : nullptr;
     aux->leg_log = bd.leg_log ? bd.leg_log + env * (int64_t)bd.leg_stride : nullptr;
-    aux->outs = (!CL && bd.outs) ? (void*)(slot + Slot<JW>::OUTS) : nullptr;
+    aux->outs = (JSL_LVL_OUT(CL) && bd.outs) ? (void*)(slot + Slot<JW>::OUTS) : nullptr;
     if (ST) {
         aux->tcur = bd.tcur + env * (int64_t)I.n_tobj;
         aux->tseed = bd.tseed ? bd.tseed + env * (int64_t)I.n_tobj : nullptr;
@@ -368,11 +368,12 @@ JSL_DECLARE_JW(1)
 JSL_DECLARE_JW(2)
 JSL_DECLARE_JW(4)
 
-// one instantiation per (lane words, kind): stochastic | classic (level 2) | simple (level 1) | general
+// one instantiation per (lane words, kind): stochastic | classic (level 2) | simple (level 1) | queues (level 3) | general
 #define JSL_BY_KIND(bd, F, N, ...)                                                                \
     ((bd).tcur           ? F<N, true, 0>(__VA_ARGS__)                                             \
      : (bd).classic == 2 ? F<N, false, 2>(__VA_ARGS__)                                            \
      : (bd).classic == 1 ? F<N, false, 1>(__VA_ARGS__)                                            \
+     : (bd).classic == 3 ? F<N, false, 3>(__VA_ARGS__)                                            \
                          : F<N, false, 0>(__VA_ARGS__))
 #define JSL_DEFINE_JW(N)                                                                                              \
     cudaError_t launch_reset_jw##N(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* m, jsl_step_out o, int ob) { \

@@ -1,7 +1,8 @@
-"""Workload for ncu captures of the general (non-classic) kernels: ta41-t (30x20 with travel times) replicas,
-3 fused rollouts under the random policy.
+"""Workload for ncu captures of the non-classic kernels: 3 fused rollouts under the random policy over replicas of
+ta41-t (30x20 with travel times: the "simple" level) or, with `fifo`, la01-t with FIFO buffers of capacity 5
+(BASELINE config 4: the general kernel).
 
-    python profiles/prof_general.py [envs]
+    python profiles/prof_general.py [envs] [fifo]
 """
 import sys
 from pathlib import Path
@@ -14,8 +15,12 @@ import _golden as G  # noqa: E402
 from jobshoplab_b200 import compiler, engine  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-li = compiler.compile_dsl_text(G.Scenario("transport", "ta41-t/fifo").source_text)
-batch = engine.Batch(li, B)
+if len(sys.argv) > 2 and sys.argv[2] == "fifo":
+    sc = G.Scenario("buffers", "la01-t/fifo5/random0")
+    batch = engine.Batch(sc.lowered, B, **sc.cfg)
+else:
+    li = compiler.compile_dsl_text(G.Scenario("transport", "ta41-t/fifo").source_text)
+    batch = engine.Batch(li, B)
 for _ in range(3):
     r = batch.rollout("random", reset_first=True, writeback=False)
 torch.cuda.synchronize()

@@ -56,8 +56,9 @@ def test_engine_source_matches_reference_traces(group):
 
 @pytest.mark.parametrize("level", ["0", "1"])
 def test_specialisation_levels_agree(level, monkeypatch):
-    """Classic instances are normally served by the level-2 code (fast paths), transport instances by level 1:
-    forced down to the simple / general code they must reproduce the same reference traces."""
+    """Classic instances are normally served by the level-2 code (fast paths), transport instances by level 1,
+    instances with ordered / bounded buffers but no setup times or outages by level 3: forced down to the simple /
+    general code they must reproduce the same reference traces."""
     monkeypatch.setenv("JSL_HOSTSIM_MAX_LEVEL", level)
     for group in ("classic", "transport"):
         for name in PICK[group][:6]:
@@ -65,6 +66,13 @@ def test_specialisation_levels_agree(level, monkeypatch):
                 replay(G.Scenario(group, name))
             except AssertionError as ex:
                 raise AssertionError(f"level {level} {group}:{name}: {ex}") from ex
+    if level == "0":  # the buffers group runs at level 3 by default (the other half of what the main test replays)
+        names = [n for n in G.names("buffers") if G.Scenario("buffers", n).lowered.is_deterministic]
+        for name in names[1::2]:
+            try:
+                replay(G.Scenario("buffers", name))
+            except AssertionError as ex:
+                raise AssertionError(f"level 0 buffers:{name}: {ex}") from ex
 
 
 def test_engine_policies():
@@ -84,7 +92,7 @@ def test_engine_source_differential_fuzz():
     oracle, step by step -- tests/fuzz_engine.py."""
     import fuzz_engine
 
-    fuzz_engine.main(250, 3)
+    fuzz_engine.main(400, 3)
     from hostsim.hostsim_py import invariants
     checks, violations = invariants()
     assert checks > 1000 and violations == 0
