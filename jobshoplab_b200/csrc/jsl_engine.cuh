@@ -313,6 +313,17 @@ JSL_D int wp_min(int n, F f) {  // f(i) -> int key (INT_BIG = not participating)
     return __reduce_min_sync(0xffffffffu, v);
 }
 template <int W, class F>
+JSL_D uint32_t wp_or(int n, F f) {  // OR of f(i) -> uint32 over i in [0,n)
+    uint32_t v = 0;
+    const int lane = JSL_LANE;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        int i = w * 32 + lane;
+        if (i < n) v |= f(i);
+    }
+    return __reduce_or_sync(0xffffffffu, v);
+}
+template <int W, class F>
 JSL_D void wp_for(int n, F f) {
     const int lane = JSL_LANE;
 #pragma unroll
@@ -343,6 +354,12 @@ JSL_D int wp_min(int n, F f) {
         int k = f(i);
         v = k < v ? k : v;
     }
+    return v;
+}
+template <int W, class F>
+JSL_D uint32_t wp_or(int n, F f) {
+    uint32_t v = 0;
+    for (int i = 0; i < n && i < 32 * W; i++) v |= f(i);
     return v;
 }
 template <int W, class F>
@@ -1115,15 +1132,33 @@ JSL_D bool create_timed(EnvS<JW, ST, CL>& s, Ctx& c, Mask<1>& mm, Mask<JW>& tm, 
     time_due = mm.any();
     JSL_SYNCWARP();
     if (JSL_UNLIKELY(JSL_LVL_BUF(CL) && !I.flex_pre)) {  // handler.py:117-153: automatic start from FIFO/LIFO/DUMMY prebuffers
-        // lane m scans the jobs for the head / tail of its own prebuffer (one pass for all machines)
-        const Mask<1> started = wp_ballot<1>(I.M, [&](int m) {
-            if (mm.test(m) || s.m_state[m] != JSL_M_IDLE) return false;
-            const int j = queue_next_lane(s, I, 3 * m, I.pre_type[m]);
-            if (j < 0) return false;
-            s.x_mkind[m] = JSL_M_SETUP; s.x_mjob[m] = (uint8_t)j;
-            return true;
+        // machines whose prebuffer holds a job (one OR-reduction over the jobs), then one min-reduction per
+        // machine that really starts: the head (smallest stamp) or, for LIFO, the tail of its queue
+        const int M3 = 3 * I.M;
+        const uint32_t pre_occ = wp_or<JW>(I.J, [&](int j) {
+            const int b = s.j_loc[j];
+            return (b < M3 && b % 3 == 0) ? 1u << (b / 3) : 0u;
         });
-        mm.w[0] |= started.w[0];
+        if (pre_occ) {
+            Mask<1> lifo;
+            lifo.w[0] = 0;
+            Mask<1> cand = wp_ballot<1>(I.M, [&](int m) {
+                return ((pre_occ >> m) & 1u) && !mm.test(m) && s.m_state[m] == JSL_M_IDLE && I.pre_type[m] != JSL_BUF_FLEX;
+            });
+            if (cand.any()) lifo = wp_ballot<1>(I.M, [&](int m) { return I.pre_type[m] == JSL_BUF_LIFO; });
+            while (cand.any()) {
+                const int m = cand.pop_first(), b = 3 * m;
+                const bool lf = lifo.test(m);
+                // seq stamps are unique per env, so the stamp identifies the job
+                const int k = wp_min<JW>(I.J, [&](int j) {
+                    return s.j_loc[j] == b ? (lf ? (int)(0x7ffffffe - s.j_seq[j]) : (int)s.j_seq[j]) : INT_BIG;
+                });
+                const uint32_t sq = lf ? (uint32_t)(0x7ffffffe - k) : (uint32_t)k;
+                const int j = wp_ballot<JW>(I.J, [&](int q) { return s.j_loc[q] == b && s.j_seq[q] == sq; }).first();
+                s.x_mkind[m] = JSL_M_SETUP; s.x_mjob[m] = (uint8_t)j;
+                mm.w[0] |= 1u << m;
+            }
+        }
     }
     // (a due machine with an empty buffer -- IndexError in the reference -- is caught by the handlers: job == NONE8)
     // transports (a PICKUP/WAITINGPICKUP transport without a job or a TRANSIT one without cargo -- raises in
