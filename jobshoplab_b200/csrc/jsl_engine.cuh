@@ -442,6 +442,7 @@ JSL_D bool ready_for_pickup_lane(const EnvS<JW, ST, CL>& s, const InstDev& I, in
     int b = s.j_loc[j];
     bool right = is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1);
     if (!right) return false;
+    if (!JSL_LVL_BUF(CL)) return true;  // every buffer is FLEX
     int ty = buf_type(I, b);
     if (ty == JSL_BUF_FLEX) return true;
     uint32_t sq = s.j_seq[j];
@@ -692,6 +693,21 @@ JSL_DN int stoch_update(const InstDev* I, int32_t* tcur, uint16_t* tseed, const 
 template <bool ST>
 JSL_D int tobj_update(Ctx& c, int32_t& draw_ctr, int idx, int static_value) {
     if (!ST) return static_value;
+    const InstDev& I = *c.I;
+    if (I.tobj_kind[idx] == JSL_TIME_STATIC) return c.aux->tcur[idx];
+#ifndef JSL_NO_INLINE_TABLE
+    // the usual case inline -- table mode, seed within the table: no call, nothing spilled around it
+    if (c.aux->tape == nullptr && I.sample_row != nullptr) {
+        const int row = I.sample_row[idx], sd = (int)c.aux->tseed[idx] + 1;
+        if (row >= 0 && sd < I.sample_depth) {
+            const int v = I.sample_table[row * I.sample_depth + sd];
+            c.aux->tseed[idx] = (uint16_t)sd;
+            c.aux->tcur[idx] = v;
+            draw_ctr = draw_ctr + 1;
+            return v;
+        }
+    }
+#endif
     int raise = 0;
     int32_t ctr = draw_ctr;
     int v = stoch_update(c.I, c.aux->tcur, c.aux->tseed, c.aux->tape, c.aux->tape_len, &ctr, c.aux->seed, c.aux->env_id, idx, &raise);

@@ -38,7 +38,8 @@ def timed(batch, policy, reps=3):
 
 def main():
     import os
-    only_general = os.environ.get("JSL_SECONDARY") == "general"
+    only_general = os.environ.get("JSL_SECONDARY") in ("general", "stoch")
+    only_stoch = os.environ.get("JSL_SECONDARY") == "stoch"
     for inst in (() if only_general else ("ft10", "la16", "ta01", "ta41")):
         li = compiler.compile_spec_text(G.Scenario("classic", f"{inst}/fifo").source_text)
         batch = engine.Batch(li, B)
@@ -52,7 +53,7 @@ def main():
                               "makespan_max": int(mk.max()), "bit_exact_vs_reference": ok,
                               "terminated": int((r.status == 1).sum())}))
         batch.close()
-    for name in ("ft10-t", "la01-t", "ta41-t"):
+    for name in (() if only_stoch else ("ft10-t", "la01-t", "ta41-t")):
         li = compiler.compile_dsl_text(G.Scenario("transport", f"{name}/fifo").source_text)
         batch = engine.Batch(li, B)
         for pol in ("fifo", "random"):
@@ -64,7 +65,7 @@ def main():
                               "terminated": int((r.status == 1).sum())}))
         batch.close()
     # BASELINE config 4: FIFO pre/post buffers with capacity 5 (general kernel); random actions may run a buffer full
-    for name in ("la01-t/fifo5/random0", "ft06-t/fifo5/random0"):
+    for name in (() if only_stoch else ("la01-t/fifo5/random0", "ft06-t/fifo5/random0")):
         sc = G.Scenario("buffers", name)
         batch = engine.Batch(sc.lowered, B, seed=sc.meta["seed"], **sc.cfg)
         r, rate = timed(batch, "random")
