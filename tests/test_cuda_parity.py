@@ -111,6 +111,23 @@ def test_throughput_build_step_mode(group):
             raise AssertionError(f"{group}:{name}: {ex}") from ex
 
 
+@pytest.mark.parametrize("level", ["0", "1"])
+def test_specialisation_levels_agree_on_gpu(level, monkeypatch):
+    """libjsl_b200.so picks the most specialised kernel an instance allows (classic: level 2, transport: level 1,
+    ordered / bounded buffers: level 3).  JSL_MAX_LEVEL (read by jsl_batch_create) forces the less specialised
+    kernels, which must reproduce the same reference traces -- otherwise the general code would only ever see the
+    setup-time / outage instances."""
+    monkeypatch.setenv("JSL_MAX_LEVEL", level)
+    picks = [("classic", n) for n in SHORT["classic"][:5]] + [("transport", n) for n in _deterministic("transport")[::6]]
+    if level == "0":
+        picks += [("buffers", n) for n in _deterministic("buffers")[1::3]]
+    for group, name in picks:
+        try:
+            step_replay(G.Scenario(group, name), record=False)
+        except AssertionError as ex:
+            raise AssertionError(f"level {level} {group}:{name}: {ex}") from ex
+
+
 @pytest.mark.parametrize("group", ["classic", "solutions", "transport", "buffers", "features", "truncation", "big"])
 def test_rollout_tape_matches_reference(group):
     """Rollout mode (state resident in shared memory for the whole episode): every deterministic golden
