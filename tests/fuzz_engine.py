@@ -17,12 +17,12 @@ from jobshoplab_b200 import lowered as L  # noqa: E402
 from oracle import oracle_py as op  # noqa: E402
 
 
-def random_instance(rng, simple=None) -> tuple[L.LoweredInstance, dict]:
+def random_instance(rng, simple=None, jrange=(1, 8)) -> tuple[L.LoweredInstance, dict]:
     """simple: None = anything; 1 = a 'simple' instance (FLEX unbounded buffers, no setup / outages: specialisation
     level 1 of the engine); 2 = 'classic' (simple with zero travel times: level 2, the fast paths); 3 = 'queues' (any
     buffer types and capacities but no setup times / outages: level 3)."""
-    J, M = int(rng.integers(1, 8)), int(rng.integers(1, 6))
-    T = int(rng.integers(1, J + 2))
+    J, M = int(rng.integers(*jrange)), int(rng.integers(1, 6))
+    T = int(rng.integers(1, min(J, 127) + 2))
     S = 2
     nt = int(rng.integers(1, 4))
     job_op_start = [0]
@@ -41,6 +41,8 @@ def random_instance(rng, simple=None) -> tuple[L.LoweredInstance, dict]:
     def caps(n):
         if rng.random() < 0.5:
             return [L.CAP_INF] * n
+        if J > 32:  # wide instances: capacities that let an episode get somewhere
+            return [int(rng.choice([max(4, J // 3), J, L.CAP_INF, L.CAP_INF])) for _ in range(n)]
         return [int(rng.choice([1, 2, 3, J, L.CAP_INF])) for _ in range(n)]
     NP = M + S
     if rng.random() < 0.3:
@@ -92,8 +94,8 @@ def random_instance(rng, simple=None) -> tuple[L.LoweredInstance, dict]:
     return li, cfg
 
 
-def run_one(rng, max_steps=400, simple=None):
-    li, cfg = random_instance(rng, simple)
+def run_one(rng, max_steps=400, simple=None, jrange=(1, 8)):
+    li, cfg = random_instance(rng, simple, jrange)
     e, o = HostSimEnv(li, **cfg), op.OracleEnv(li, **cfg)
     p = float(rng.choice([0.5, 0.8, 1.0]))
     steps = 0

@@ -96,3 +96,17 @@ def test_engine_source_differential_fuzz():
     from hostsim.hostsim_py import invariants
     checks, violations = invariants()
     assert checks > 1000 and violations == 0
+
+
+def test_engine_source_wide_instances():
+    """33..100 jobs (2 and 4 lane words) with ordered / bounded buffers, setup times and outages: the golden
+    groups only hold classic instances of that width."""
+    import fuzz_engine
+
+    rng = np.random.default_rng(77)
+    for i in range(24):
+        sub = np.random.default_rng(rng.integers(0, 2**63))
+        try:
+            fuzz_engine.run_one(sub, max_steps=600, simple=(3, None)[i % 2], jrange=((33, 64), (65, 101))[(i // 2) % 2])
+        except AssertionError as ex:
+            raise AssertionError(f"wide instance {i}: {str(ex)[:2000]}") from ex
