@@ -261,11 +261,12 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     I.caps_inf = all_equal(t->pre_cap, JSL_CAP_INF) && all_equal(t->post_cap, JSL_CAP_INF) && all_equal(t->sbuf_cap, JSL_CAP_INF);
     // specialisation level (jsl_engine.cuh): which features the instance needs compiled in
     const bool plain = !I.has_m_out && !I.has_t_out && !I.setup && !t->stochastic && I.out_buf >= 0;
-    const bool simple = plain && I.flex_pre && I.flex_post && I.caps_inf;
-    b->bd.classic = simple ? (I.travel ? 1 : 2) : plain ? 3 : 0;
+    const bool flexbuf = I.flex_pre && I.flex_post && I.caps_inf && I.out_buf >= 0;
+    const bool simple = plain && flexbuf;
+    b->bd.classic = simple ? (I.travel ? 1 : 2) : plain ? 3 : flexbuf ? 4 : 0;
     if (const char* cap = std::getenv("JSL_MAX_LEVEL")) {  // diagnostics: force a less specialised kernel
         const int lv = std::atoi(cap);
-        if (b->bd.classic == 3) { if (lv == 0) b->bd.classic = 0; }
+        if (b->bd.classic >= 3) { if (lv == 0) b->bd.classic = 0; }
         else if (b->bd.classic > lv) b->bd.classic = lv < 0 ? 0 : lv;
     }
     CfgDev& C = b->bd.cfg;

@@ -16,7 +16,9 @@
 // setup times, no outages, deterministic: capacity / position / TimeDependency / outage / setup code is compiled
 // out); 2 "classic" (simple + all travel times zero: no travel lookups, start / completion chains in one batch);
 // 3 "queues" (deterministic, no setup times, no outages, but FIFO / LIFO / DUMMY buffers and finite capacities:
-// only the outage and setup code is compiled out).  JSL_LVL_BUF / JSL_LVL_OUT name what a level keeps.
+// only the outage and setup code is compiled out); 4 "features" (setup times, outages, stochastic times, but all
+// buffers FLEX and unbounded: the queue / capacity / TimeDependency code is compiled out).  JSL_LVL_BUF / JSL_LVL_OUT
+// name what a level keeps.
 // The hot loop has to stay inside the instruction cache: one call site per phase (sm_step, run_env_op),
 // rare paths out of line (JSL_DN), rarely used per-env constants in EnvAux (shared memory).
 //
@@ -214,7 +216,7 @@ struct Ctx {
 
 #define JSL_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #define JSL_LVL_BUF(CL) ((CL) == 0 || (CL) == 3)  // ordered / bounded buffers, TimeDependency, state-graph validation
-#define JSL_LVL_OUT(CL) ((CL) == 0)               // outages, setup times
+#define JSL_LVL_OUT(CL) ((CL) == 0 || (CL) == 4)  // outages, setup times
 #define JSL_RAISE(c, code)          \
     do {                            \
         if (!(c).raise) (c).raise = (code); \

@@ -44,7 +44,7 @@ struct BatchDev {
     int32_t* tcur;       // [B][n_tobj] current .time of every time object (stochastic instances) or nullptr
     const int32_t* tape; // [B][tape_stride] replayed update() results or nullptr
     int64_t tape_stride;
-    int classic;         // specialisation level CL of jsl_engine.cuh: 0 general, 1 simple, 2 classic, 3 queues
+    int classic;         // specialisation level CL of jsl_engine.cuh: 0 general, 1 simple, 2 classic, 3 queues, 4 features
     unsigned long long* work_counter;  // next env index of the persistent rollout grid (dynamic work queue)
     uint16_t* tseed;     // [B][n_tobj] numpy seed of every stochastic time object
     const int32_t* start_seeds;  // [B][n_tobj] or nullptr
@@ -368,12 +368,14 @@ JSL_DECLARE_JW(1)
 JSL_DECLARE_JW(2)
 JSL_DECLARE_JW(4)
 
-// one instantiation per (lane words, kind): stochastic | classic (level 2) | simple (level 1) | queues (level 3) | general
+// one instantiation per (lane words, kind): stochastic (general | features) | classic (level 2) | simple (level 1) |
+// queues (level 3) | features (level 4) | general
 #define JSL_BY_KIND(bd, F, N, ...)                                                                \
-    ((bd).tcur           ? F<N, true, 0>(__VA_ARGS__)                                             \
+    ((bd).tcur           ? ((bd).classic == 4 ? F<N, true, 4>(__VA_ARGS__) : F<N, true, 0>(__VA_ARGS__)) \
      : (bd).classic == 2 ? F<N, false, 2>(__VA_ARGS__)                                            \
      : (bd).classic == 1 ? F<N, false, 1>(__VA_ARGS__)                                            \
      : (bd).classic == 3 ? F<N, false, 3>(__VA_ARGS__)                                            \
+     : (bd).classic == 4 ? F<N, false, 4>(__VA_ARGS__)                                            \
                          : F<N, false, 0>(__VA_ARGS__))
 #define JSL_DEFINE_JW(N)                                                                                              \
     cudaError_t launch_reset_jw##N(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* m, jsl_step_out o, int ob) { \

@@ -20,7 +20,8 @@ from oracle import oracle_py as op  # noqa: E402
 def random_instance(rng, simple=None, jrange=(1, 8)) -> tuple[L.LoweredInstance, dict]:
     """simple: None = anything; 1 = a 'simple' instance (FLEX unbounded buffers, no setup / outages: specialisation
     level 1 of the engine); 2 = 'classic' (simple with zero travel times: level 2, the fast paths); 3 = 'queues' (any
-    buffer types and capacities but no setup times / outages: level 3)."""
+    buffer types and capacities but no setup times / outages: level 3); 4 = 'features' (setup times / outages allowed,
+    FLEX unbounded buffers: level 4)."""
     J, M = int(rng.integers(*jrange)), int(rng.integers(1, 6))
     T = int(rng.integers(1, min(J, 127) + 2))
     S = 2
@@ -67,6 +68,9 @@ def random_instance(rng, simple=None, jrange=(1, 8)) -> tuple[L.LoweredInstance,
     if simple == 3:
         setup = np.zeros((M, nt, nt), dtype=np.int32)
         m_out_start, m_of, m_od, t_of, t_od = [0] * (M + 1), [], [], [], []
+    elif simple == 4:
+        btypes = lambda n: [L.BUF_FLEX] * n
+        caps = lambda n: [L.CAP_INF] * n
     elif simple:
         btypes = lambda n: [L.BUF_FLEX] * n
         caps = lambda n: [L.CAP_INF] * n
@@ -83,7 +87,7 @@ def random_instance(rng, simple=None, jrange=(1, 8)) -> tuple[L.LoweredInstance,
         pre_type=btypes(M), pre_cap=caps(M), post_type=btypes(M), post_cap=caps(M),
         setup_time=setup.reshape(-1), default_tool=0,
         sbuf_type=[int(rng.choice([L.BUF_FLEX, L.BUF_FIFO, L.BUF_LIFO])) if (rng.random() < 0.3 and simple in (None, 3)) else L.BUF_FLEX, L.BUF_FLEX],
-        sbuf_cap=[L.CAP_INF, L.CAP_INF if (rng.random() < 0.8 or simple in (1, 2)) else max(1, J - 1)],
+        sbuf_cap=[L.CAP_INF, L.CAP_INF if (rng.random() < 0.8 or simple in (1, 2, 4)) else max(1, J - 1)],
         sbuf_role=[L.ROLE_INPUT, L.ROLE_OUTPUT], buf_ref_id=np.arange(NB), travel_time=travel.reshape(-1),
         agv_init_place=[int(rng.integers(0, NP if rng.random() < 0.2 else M)) for _ in range(T)],
         job_init_buf=[3 * M + T] * J, start_time=int(rng.choice([0, 0, 3])),
@@ -130,7 +134,7 @@ def main(n=300, seed=0):
         sub = np.random.default_rng(rng.integers(0, 2**63))
         state = sub.bit_generator.state
         try:
-            steps, st = run_one(sub, simple=(None, 3, 1, 2)[i % 4])  # a quarter general, a quarter each specialised level
+            steps, st = run_one(sub, simple=(None, 3, 1, 2, 4)[i % 5])  # a fifth general, a fifth each specialised level
         except AssertionError as ex:
             print(f"FUZZ FAILURE at instance {i} (seed {seed}): {str(ex)[:3000]}")
             raise SystemExit(1)

@@ -136,7 +136,7 @@ template <int JW, bool ST, int CL> double get_ret(Sim* s) { return ((EnvS<JW, ST
 
 }  // namespace
 
-#define DISPATCH1(s, F, N, ...) ((s)->tobj.stochastic ? F<N, true, 0>(__VA_ARGS__) : (s)->classic == 2 ? F<N, false, 2>(__VA_ARGS__) : (s)->classic == 1 ? F<N, false, 1>(__VA_ARGS__) : (s)->classic == 3 ? F<N, false, 3>(__VA_ARGS__) : F<N, false, 0>(__VA_ARGS__))
+#define DISPATCH1(s, F, N, ...) ((s)->tobj.stochastic ? ((s)->classic == 4 ? F<N, true, 4>(__VA_ARGS__) : F<N, true, 0>(__VA_ARGS__)) : (s)->classic == 4 ? F<N, false, 4>(__VA_ARGS__) : (s)->classic == 2 ? F<N, false, 2>(__VA_ARGS__) : (s)->classic == 1 ? F<N, false, 1>(__VA_ARGS__) : (s)->classic == 3 ? F<N, false, 3>(__VA_ARGS__) : F<N, false, 0>(__VA_ARGS__))
 #define DISPATCH(s, F, ...) ((s)->JW == 1 ? DISPATCH1(s, F, 1, __VA_ARGS__) : (s)->JW == 2 ? DISPATCH1(s, F, 2, __VA_ARGS__) : DISPATCH1(s, F, 4, __VA_ARGS__))
 
 extern "C" {
@@ -214,11 +214,12 @@ void* jsh_create(const jsl_instance_desc* d, const jsl_env_cfg* cfg, uint64_t se
     {
         // same rule as jsl_abi.cu
         const bool plain = !I.has_m_out && !I.has_t_out && !I.setup && !s->tobj.stochastic && I.out_buf >= 0;
-        const bool simple = plain && I.flex_pre && I.flex_post && I.caps_inf;
-        s->classic = simple ? (I.travel ? 1 : 2) : plain ? 3 : 0;
+        const bool flexbuf = I.flex_pre && I.flex_post && I.caps_inf && I.out_buf >= 0;
+        const bool simple = plain && flexbuf;
+        s->classic = simple ? (I.travel ? 1 : 2) : plain ? 3 : flexbuf ? 4 : 0;
         if (const char* lvl = std::getenv("JSL_HOSTSIM_MAX_LEVEL")) {  // force a less specialised level (tests)
             const int lv = std::atoi(lvl);
-            if (s->classic == 3) { if (lv == 0) s->classic = 0; }
+            if (s->classic >= 3) { if (lv == 0) s->classic = 0; }
             else if (s->classic > lv) s->classic = lv < 0 ? 0 : lv;
         }
     }

@@ -120,7 +120,7 @@ def test_specialisation_levels_agree_on_gpu(level, monkeypatch):
     monkeypatch.setenv("JSL_MAX_LEVEL", level)
     picks = [("classic", n) for n in SHORT["classic"][:5]] + [("transport", n) for n in _deterministic("transport")[::6]]
     if level == "0":
-        picks += [("buffers", n) for n in _deterministic("buffers")[1::3]]
+        picks += [("buffers", n) for n in _deterministic("buffers")[1::3]] + [("features", n) for n in _deterministic("features")[::3]]
     for group, name in picks:
         try:
             step_replay(G.Scenario(group, name), record=False)
@@ -197,9 +197,9 @@ def test_wide_instances_with_queues_match_oracle():
 
     eng = _engine()
     rng = np.random.default_rng(77)
-    for i in range(16):
+    for i in range(18):
         sub = np.random.default_rng(rng.integers(0, 2**63))
-        li, cfg = fuzz_engine.random_instance(sub, simple=(3, None)[i % 2], jrange=((33, 64), (65, 101))[(i // 2) % 2])
+        li, cfg = fuzz_engine.random_instance(sub, simple=(3, None, 4)[i % 3], jrange=((33, 64), (65, 101))[(i // 3) % 2])
         B, L = 6, 1500
         tape = (sub.random((B, L)) < 0.75).astype(np.uint8)
         batch = eng.Batch(li, B, record_ops=True, **cfg)

@@ -66,13 +66,14 @@ def test_specialisation_levels_agree(level, monkeypatch):
                 replay(G.Scenario(group, name))
             except AssertionError as ex:
                 raise AssertionError(f"level {level} {group}:{name}: {ex}") from ex
-    if level == "0":  # the buffers group runs at level 3 by default (the other half of what the main test replays)
-        names = [n for n in G.names("buffers") if G.Scenario("buffers", n).lowered.is_deterministic]
-        for name in names[1::2]:
-            try:
-                replay(G.Scenario("buffers", name))
-            except AssertionError as ex:
-                raise AssertionError(f"level 0 buffers:{name}: {ex}") from ex
+    if level == "0":  # buffers runs at level 3 by default (the other half of what the main test replays), features at 4
+        for group, sl in (("buffers", slice(1, None, 2)), ("features", slice(0, None, 2))):
+            names = [n for n in G.names(group) if G.Scenario(group, n).lowered.is_deterministic]
+            for name in names[sl]:
+                try:
+                    replay(G.Scenario(group, name))
+                except AssertionError as ex:
+                    raise AssertionError(f"level 0 {group}:{name}: {ex}") from ex
 
 
 def test_engine_policies():
@@ -92,7 +93,7 @@ def test_engine_source_differential_fuzz():
     oracle, step by step -- tests/fuzz_engine.py."""
     import fuzz_engine
 
-    fuzz_engine.main(400, 3)
+    fuzz_engine.main(500, 3)
     from hostsim.hostsim_py import invariants
     checks, violations = invariants()
     assert checks > 1000 and violations == 0
@@ -107,6 +108,6 @@ def test_engine_source_wide_instances():
     for i in range(24):
         sub = np.random.default_rng(rng.integers(0, 2**63))
         try:
-            fuzz_engine.run_one(sub, max_steps=600, simple=(3, None)[i % 2], jrange=((33, 64), (65, 101))[(i // 2) % 2])
+            fuzz_engine.run_one(sub, max_steps=600, simple=(3, None, 4)[i % 3], jrange=((33, 64), (65, 101))[(i // 3) % 2])
         except AssertionError as ex:
             raise AssertionError(f"wide instance {i}: {str(ex)[:2000]}") from ex
