@@ -198,7 +198,10 @@ jsl_instance_t* jsl_instance_create(const jsl_instance_desc* d);
 void jsl_instance_destroy(jsl_instance_t*);
 
 /* B envs over n_inst same-shaped instances (env b uses instance b % n_inst), on CUDA device
- * `device`.  Replaces JobShopLabEnv.__init__ wiring (env.py:388-402) for a whole batch. */
+ * `device`.  Replaces JobShopLabEnv.__init__ wiring (env.py:388-402) for a whole batch.
+ * The batch is served by the most specialised kernel set the instance allows (classic / simple / queues /
+ * features / general) -- all of them bit-exact with the reference; the environment variable
+ * JSL_MAX_LEVEL=0|1, read here, forces the less specialised ones (diagnostics, cross-level parity tests). */
 jsl_batch_t* jsl_batch_create(jsl_instance_t* const* insts, int n_inst, int64_t B, int device,
                               uint64_t seed, const jsl_env_cfg* cfg);
 /* Synthetic same-shape batches: n_inst variants of `tmpl` that differ only in
