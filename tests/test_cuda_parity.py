@@ -190,35 +190,21 @@ def test_rollout_policies_match_reference_rules():
 
 def test_wide_instances_with_queues_match_oracle():
     """Random instances with 33..100 jobs (2 and 4 lane words), FIFO / LIFO / DUMMY buffers with finite capacities,
-    with and without setup times / outages (levels 3 and 0), random action tapes: rollout mode against the CPU
+    with and without setup times / outages (levels 3, 0 and 4), random action tapes: rollout mode against the CPU
     oracle -- final digest, makespan, steps, return, status.  The golden groups of that width are classic only."""
     import fuzz_engine
-    from oracle import oracle_py as op
+    import gpu_fuzz
 
     eng = _engine()
     rng = np.random.default_rng(77)
     for i in range(18):
         sub = np.random.default_rng(rng.integers(0, 2**63))
         li, cfg = fuzz_engine.random_instance(sub, simple=(3, None, 4)[i % 3], jrange=((33, 64), (65, 101))[(i // 3) % 2])
-        B, L = 6, 1500
-        tape = (sub.random((B, L)) < 0.75).astype(np.uint8)
-        batch = eng.Batch(li, B, record_ops=True, **cfg)
-        batch.reset()
-        r = batch.rollout("tape", tape=torch.from_numpy(tape).cuda())
-        mk, ns = r.makespan.cpu().numpy(), r.n_steps.cpu().numpy()
-        ret, st = r.ret.cpu().numpy(), r.status.cpu().numpy()
-        for e in range(B):
-            o = op.OracleEnv(li, **cfg)
-            n = 0
-            while n < L and o.status == 0:
-                o.step(int(tape[e, n]))
-                n += 1
-            tag = f"wide instance {i} (J={li.n_jobs}, M={li.n_machines}, T={li.n_transports}) env {e}"
-            assert st[e] == o.status, (tag, st[e], o.status)
-            assert ns[e] == o.n_steps, (tag, ns[e], o.n_steps)
-            if o.status > 3:
-                continue  # an escaping exception: the reference has no state to compare
-            assert mk[e] == o.time, (tag, mk[e], o.time)
-            assert ret[e] == o.ret, tag
-            assert np.array_equal(batch.get_state(e), o.digest()), tag
-        batch.close()
+        gpu_fuzz.check_instance(eng, torch, li, cfg, sub, B=6, L=1500, tag=f"wide instance {i}")
+
+
+def test_gpu_differential_fuzz():
+    """Small random instances of every specialisation level on the GPU against the oracle (tests/gpu_fuzz.py)."""
+    import gpu_fuzz
+
+    gpu_fuzz.main(100, 3)
