@@ -202,6 +202,7 @@ struct alignas(16) EnvAux {
     uint32_t act_bits;
     int32_t pad;
     int32_t* leg_log;            // transport-task log of this env (see LegLog) or nullptr
+    uint32_t loop_scratch[12];   // stochastic kernels: sm_step keeps its transition masks and loop guard here (see there)
 };
 
 // per-call context: the few uniform values the hot loop keeps in registers
@@ -1364,8 +1365,19 @@ template <int JW, bool ST, int CL>
 JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int time_machine) {
     const InstDev& I = *c.I;
     c.now = s.time;
-    Mask<1> mm;
-    Mask<JW> tm, tele;
+    // transition masks of the current batch and the loop guard.  The stochastic kernels are short of registers (the
+    // samplers are inlined into the handlers): there these live in the env's shared-memory slot instead of being
+    // spilled to local memory around every handler; everywhere else they are plain registers.
+    struct LoopState { Mask<1> mm; Mask<JW> tm, tele; int guard; };
+    static_assert(sizeof(LoopState) <= sizeof(EnvAux::loop_scratch), "loop_scratch too small");
+    LoopState* const ls = reinterpret_cast<LoopState*>(c.aux->loop_scratch);
+    Mask<1> mm_r;
+    Mask<JW> tm_r, tele_r;
+    int guard_r;
+    Mask<1>& mm = ST ? ls->mm : mm_r;
+    Mask<JW>& tm = ST ? ls->tm : tm_r;
+    Mask<JW>& tele = ST ? ls->tele : tele_r;
+    int& guard = ST ? ls->guard : guard_r;
     mm.w[0] = 0;
 #pragma unroll
     for (int w = 0; w < JW; w++) { tm.w[w] = 0; tele.w[w] = 0; }
@@ -1378,7 +1390,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
     bool known_quiet = !has_action && time_machine == TM_FORCE;  // (a reset starts from the initial state instead)
     bool poss_fresh = known_quiet;  // s.c_* already describe the current state
     bool moved = CL != 2 || (!has_action && time_machine == TM_JUMP);  // a job may have reached an output buffer (reset: unknown)
-    int guard = 0;
+    guard = 0;
     if (CL == 2 && has_action && act.kind == 0 && classic_start(s, c, act)) {
         action_stage = false; first = false; known_quiet = true; poss_fresh = true;
 #ifdef JSL_HOST_SIM
