@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define JSL_ABI_VERSION 1
+#define JSL_ABI_VERSION 2
 
 /* buffer types -- jobshoplab/types/instance_config_types.py:30-36 (BufferTypeConfig) */
 #define JSL_BUF_FIFO 0
@@ -168,6 +168,21 @@ typedef struct jsl_shape {
     int32_t digest_cap;    /* upper bound on jsl_get_state digest length (int32 elements) */
 } jsl_shape;
 
+/* Per-env scalars of one env.step packed into ONE 32-byte record (two 16-byte stores per env instead of eight
+ * scattered ones): what env.step returns besides the observation (env.py:454) plus the candidate the agent sees
+ * next.  Written when jsl_step_out.record is set -- the separate arrays are then not written. */
+typedef struct jsl_step_record {
+    double reward;       /* RewardFactory.make (rewards.py:145) */
+    int32_t time;        /* state.time.time */
+    int32_t makespan;    /* info["makespan"]: time if terminated else -1 (env.py:404) */
+    int16_t cand[4];     /* next possible_transitions[0]: kind(0 m/1 t), comp, job, n_remaining */
+    uint8_t terminated;  /* env.py:446 */
+    uint8_t truncated;   /* env.py:447-450 */
+    uint8_t status;      /* JSL_ST_* */
+    uint8_t reserved0;
+    int32_t reserved1;
+} jsl_step_record;
+
 /* Device output pointers of one jsl_step; any pointer may be NULL (= not wanted). */
 typedef struct jsl_step_out {
     uint8_t* obs;        /* [B][obs_bytes]   ObservationFactory.make (observations.py:515) */
@@ -178,6 +193,8 @@ typedef struct jsl_step_out {
     int32_t* time;       /* [B]              state.time.time */
     int32_t* makespan;   /* [B]              info["makespan"] (time if terminated else -1), env.py:404 */
     int16_t* cand;       /* [B][4]           next possible_transitions[0]: kind(0 m/1 t), comp, job, n_remaining */
+    jsl_step_record* record; /* [B]          all of the above scalars in one record per env (preferred: when set, the
+                                             six scalar arrays and cand are ignored) */
 } jsl_step_out;
 
 /* Device output pointers of one jsl_rollout; any may be NULL. */

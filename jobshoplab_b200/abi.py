@@ -7,7 +7,7 @@ import numpy as np
 
 from .lowered import LoweredInstance, TimeSpec
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 (ST_OK, ST_DONE, ST_TRUNCATED, ST_STEP_FAILED, ST_BUFFER_FULL, ST_UNSUCCESSFUL, ST_NO_POSSIBLE,
  ST_ENV_DONE, ST_ACTION_OUT_OF_SPACE, ST_OTHER_INVALID) = range(10)
@@ -64,7 +64,10 @@ class Shape(C.Structure):
 class StepOut(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p),
                 ("truncated", C.c_void_p), ("status", C.c_void_p), ("time", C.c_void_p),
-                ("makespan", C.c_void_p), ("cand", C.c_void_p)]
+                ("makespan", C.c_void_p), ("cand", C.c_void_p), ("record", C.c_void_p)]
+
+
+STEP_RECORD_BYTES = 32  # jsl_step_record: f64 reward | i32 time | i32 makespan | i16 cand[4] | u8 terminated, truncated, status
 
 
 class RolloutOut(C.Structure):

@@ -155,6 +155,7 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
                          const int32_t* lbs, const int32_t* mats, int64_t B, int device, uint64_t seed,
                          const jsl_env_cfg* cfg) {
     if (B <= 0 || n_inst <= 0) { set_err("B and n_inst must be positive"); return nullptr; }
+    if (B >= (1ll << 31) || n_inst >= (1ll << 31)) { set_err("unsupported: 2^31 or more envs / variants in one batch"); return nullptr; }
     if (t->M > 32) { set_err("unsupported: more than 32 machines"); return nullptr; }
     if (t->S > 32) { set_err("unsupported: more than 32 standalone buffers"); return nullptr; }
     int jt = t->J > t->T ? t->J : t->T;
@@ -274,7 +275,8 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     C.truncation_active = cfg->truncation_active; C.obs_kind = cfg->obs_kind; C.record_ops = cfg->record_ops;
     C.sparse_bias = cfg->sparse_bias; C.dense_bias = cfg->dense_bias; C.truncation_bias = cfg->truncation_bias;
     b->bd.B = B; b->bd.seed = seed; b->bd.env_base = 0;
-    int ss = b->JW == 1 ? state_bytes_jw1() : b->JW == 2 ? state_bytes_jw2() : state_bytes_jw4();
+    const int lvl = b->bd.classic;
+    int ss = b->JW == 1 ? state_bytes_jw1(lvl) : b->JW == 2 ? state_bytes_jw2(lvl) : state_bytes_jw4(lvl);
     int os = b->JW == 1 ? outs_bytes_jw1() : b->JW == 2 ? outs_bytes_jw2() : outs_bytes_jw4();
     b->bd.state_stride = ss;
     b->bd.outs_stride = (I.has_m_out || I.has_t_out) ? os : 0;

@@ -33,6 +33,7 @@
 //   state_machine/middleware/middleware.py:264-443, env/factories/{actions,observations,rewards}.py,
 //   env/env.py:427-454, utils/dipatching_benchmark.py:17-67, types/stochasticy_models.py:6-121.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/jobshoplab_b200.h"
@@ -128,7 +129,10 @@ struct CfgDev {
 
 // ------------------------------------------------------------------------------------ state
 // Mutable state of one env.  JW = ceil(max(J,T)/32) lane words; machines <= 32.
-// The same struct is the HBM image (step mode) and the shared-memory working copy.
+// The shared-memory working copy.  Its first IMAGE_BYTES bytes are the HBM image (step mode): everything that
+// has to survive between launches, in one contiguous 16-byte-aligned run; behind it the TimeDependency fields
+// (part of the image only in the levels that have ordered buffers) and the per-batch scratch of sm_step, which
+// never leaves the SM.
 template <int JW, bool ST = false, int CL = false>
 struct alignas(16) EnvS {
     static constexpr int MJ = 32 * JW, MT = 32 * JW, MM = 32;
@@ -146,7 +150,11 @@ struct alignas(16) EnvS {
     uint8_t terminated, truncated, last_action_empty, obs_done;
     int32_t all_out;          // core_utils.is_done of the current state
     int32_t draw_ctr;         // StochasticTimeConfig.update() calls so far (tape position / Philox counter)
+    int32_t lower_bound;      // of this env's instance variant, copied at reset (utils.py:310-331)
     double ret;               // sum of rewards
+    double inv_mat;           // 1.0 / max_allowed_time (see obs_time_fraction)
+    int32_t max_allowed_time; // utils.py:334-352, copied at reset
+    int32_t pad_[3];
     // candidate masks of the state as of the last state-machine call (possible_transitions, unexpanded)
     uint32_t c_p1[JW], c_idle[JW], c_lr[JW], c_li[JW];
     // jobs
@@ -162,13 +170,22 @@ struct alignas(16) EnvS {
     int32_t m_occ[MM];
     uint16_t m_done[MM];             // DONE ops on this machine (observation)
     uint8_t m_state[MM], m_tool[MM], m_job[MM];
-    uint8_t x_mkind[MM], x_mjob[MM];  // scratch: timed machine transitions of this iteration
     // transports
     int32_t t_occ[MT];               // time | blocking job (TimeDependency)
-    uint16_t t_loc1[MT], t_tdbuf[MT];
+    uint16_t t_loc1[MT];
     uint8_t t_state[MT], t_job[MT], t_carry[MT], t_occkind[MT], t_lockind[MT], t_loc0[MT], t_loc2[MT];
+    // ---- end of the image of the levels without ordered buffers (no TimeDependency can arise there)
+    uint16_t t_tdbuf[MT];
     uint8_t t_tdcomp[MT], t_tdjob[MT];
-    uint8_t x_tkind[MT], x_tcomp[MT], x_tjob[MT];  // scratch: timed transport transitions
+    // ---- end of the image of the other levels; scratch: timed transitions of the current batch
+    uint8_t x_mkind[MM], x_mjob[MM];
+    uint8_t x_tkind[MT], x_tcomp[MT], x_tjob[MT];
+};
+#define JSL_LVL_BUF_(CL) ((CL) == 0 || (CL) == 3)
+template <int JW, int CL>
+struct Image {  // bytes of EnvS that travel to HBM
+    static constexpr int BYTES = JSL_LVL_BUF_(CL) ? (int)offsetof(EnvS<JW>, x_mkind) : (int)offsetof(EnvS<JW>, t_tdbuf);
+    static_assert(BYTES % 16 == 0, "the state image is copied in 16-byte units");
 };
 
 // Outage bookkeeping (types/state_types.py:178-197), only allocated for instances with outages.
@@ -197,7 +214,8 @@ struct alignas(16) EnvAux {
     uint64_t seed, env_id;       // Philox key / stream of this env
     double neg_inv_n;            // -1.0 / N: the dense reward of a penalised step (rewards.py:135-138)
     int32_t tape_len;
-    int32_t lower_bound, max_allowed_time;
+    int32_t pad0_;
+    const int32_t* lb_mat;       // {lower_bound, max_allowed_time} of this env's instance variant (read at reset)
     uint32_t act_block;          // RANDOM policy: 1 + index of the 32-step block whose actions are in act_bits (0 = none)
     uint32_t act_bits;
     int32_t pad;
@@ -1562,6 +1580,12 @@ JSL_D void env_init(EnvS<JW, ST, CL>& s, Ctx& c) {
     s.n_steps = 0; s.noop_count = 0; s.max_done_end = -1; s.status = JSL_ST_OK; s.all_out = 0;
     s.terminated = 0; s.truncated = 0; s.last_action_empty = 1; s.obs_done = 0;
     s.ret = 0.0;
+    {   // per-variant constants travel with the state: no dependent table reads on the step path
+        const int mat = c.aux->lb_mat[1];
+        s.lower_bound = c.aux->lb_mat[0]; s.max_allowed_time = mat;
+        s.inv_mat = 1.0 / (double)mat;
+        s.pad_[0] = 0; s.pad_[1] = 0; s.pad_[2] = 0;
+    }
     JSL_SYNCWARP();
     wp_for<JW>(EnvS<JW, ST, CL>::MJ, [&](int j) {
         bool live = j < I.J;
@@ -1603,7 +1627,7 @@ JSL_D double make_reward(EnvS<JW, ST, CL>& s, const Ctx& c) {
     double sr;
     if (s.truncated) sr = (c.C->truncation_bias * 1.0) / c.C->sparse_bias;
     else if (!s.terminated) sr = 0.0;
-    else sr = (double)(c.aux->max_allowed_time - s.time) / (double)(c.aux->max_allowed_time - c.aux->lower_bound);
+    else sr = (double)(s.max_allowed_time - s.time) / (double)(s.max_allowed_time - s.lower_bound);
     if (s.last_action_empty) s.reward_noop = s.reward_noop + 1;
     else s.reward_noop = 0;
     const double dr = s.reward_noop >= c.I->J ? c.aux->neg_inv_n : 0.0;  // -int(flag) / N
@@ -1789,6 +1813,25 @@ JSL_HD int obs_bytes_binary(int J, int M) { return (16 + 4 * J + 4 * M + 2 * J +
 JSL_HD int obs_bytes_oparray(int J, int N) { return (16 + 4 * N + 4 * J + 15) & ~15; }
 JSL_HD int obs_bytes_tassel(int J) { return (7 * 4 * J + 15) & ~15; }
 
+// np.float32(time / max_allowed_time) (observations.py:470-471): the float64 quotient rounded to float32.  A
+// float64 division is a ~20-instruction sequence on the SM; t * (1/m) is within 2 ulp(f64) of t / m, while the
+// quotient of two integers with m < 2^22 is either a float32 value itself or at least 2^-47 (relative) away from the
+// nearest float32 rounding boundary, so both round to the same float32 (checked exhaustively for m < 3000 and on
+// 8e7 random pairs, tests/test_host_api.py).  Larger / degenerate m take the division.
+template <int JW, bool ST, int CL>
+JSL_D float time_fraction(const EnvS<JW, ST, CL>& s) {
+    const int m = s.max_allowed_time;
+    if (m > 0 && m < (1 << 22)) {
+#if defined(__CUDACC__) && !defined(JSL_HOST_SIM)
+        return (float)__dmul_rn((double)s.time, s.inv_mat);
+#else
+        volatile double q = (double)s.time * s.inv_mat;
+        return (float)q;
+#endif
+    }
+    return (float)((double)s.time / (double)m);
+}
+
 template <int JW, bool ST, int CL>
 JSL_D void cand_floats(const EnvS<JW, ST, CL>& s, const Ctx& c, float* tr, const Trans* known = nullptr) {
     const InstDev& I = *c.I;
@@ -1801,6 +1844,12 @@ JSL_D void cand_floats(const EnvS<JW, ST, CL>& s, const Ctx& c, float* tr, const
     } else {
         tr[0] = tr[1] = tr[2] = 1.0f;
     }
+}
+
+template <int Q>
+JSL_D void exec_row_words(uint32_t* rw, uint32_t mask) {
+#pragma unroll
+    for (int q = 0; q < Q; q++) rw[q] = (((mask >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
 }
 
 template <int JW, bool ST, int CL>
@@ -1818,7 +1867,7 @@ JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* ou
     int8_t* exec = mrun + M;
     const int total = obs_bytes_binary(J, M);
     wp_for_dyn(1, [&](int) {
-        f[0] = (float)((double)s.time / (double)c.aux->max_allowed_time);
+        f[0] = time_fraction(s);
         f[1] = tr[0]; f[2] = tr[1]; f[3] = tr[2];
         for (int i = 16 + 4 * J + 4 * M + 2 * J + M + J * M; i < total; i++) out[i] = 0;
     });
@@ -1835,7 +1884,13 @@ JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* ou
         int8_t* row = exec + r * M;
         if (word_rows) {
             uint32_t* rw = (uint32_t*)row;
-            for (int q = 0; q < M / 4; q++) rw[q] = (((mask >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
+            // 4 mask bits -> 4 bytes per word; the common row lengths are unrolled (a counted loop costs twice
+            // the instructions of its body here)
+            if (M == 20) exec_row_words<5>(rw, mask);
+            else if (M == 16) exec_row_words<4>(rw, mask);
+            else if (M == 12) exec_row_words<3>(rw, mask);
+            else if (M == 8) exec_row_words<2>(rw, mask);
+            else for (int q = 0; q < M / 4; q++) rw[q] = (((mask >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
         } else {
             for (int m = 0; m < M; m++) row[m] = (int8_t)((mask >> m) & 1u);
         }
@@ -1890,7 +1945,7 @@ JSL_D void write_obs_tassel(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* ou
     const InstDev& I = *c.I;
     const int J = I.J;
     float* f = (float*)out;
-    const double mat = (double)c.aux->max_allowed_time;
+    const double mat = (double)s.max_allowed_time;
     const int32_t* log = c.aux->op_log;
     const int now = s.time;
     const int total_bytes = obs_bytes_tassel(J);

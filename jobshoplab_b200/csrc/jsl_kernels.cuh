@@ -98,10 +98,14 @@ __device__ __forceinline__ int slot_stride(const BatchDev& bd) {
     return (!JSL_LVL_OUT(CL) || !bd.outs) ? Slot<JW>::BYTES : Slot<JW>::BYTES_OUTS;
 }
 
-template <int JW, bool ST, int CL>
-__device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env, uint8_t* slot) {
+// Per-env context.  STEP = the one-step kernels (k_reset / k_step / k_digest): the fields only the fused rollout
+// reads (policy streams, action tape, step limit) are not set up.  `env` is 32-bit (B < 2^31, checked at batch
+// creation) so that every address is one IMAD.WIDE.
+template <int JW, bool ST, int CL, bool STEP>
+__device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, uint32_t env, uint8_t* slot) {
     const InstDev& I = bd.inst;
-    const int64_t v = I.n_inst == 1 ? 0 : (env < I.n_inst ? env : (int64_t)((uint64_t)env % (uint32_t)I.n_inst));
+    const uint32_t ni = (uint32_t)I.n_inst;
+    const uint32_t v = ni == 1u ? 0u : (env < ni ? env : env % ni);
     EnvAux* aux = (EnvAux*)(slot + Slot<JW>::AUX);
     c.I = &bd.inst;
     c.C = &bd.cfg;
@@ -111,41 +115,71 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, int64_t env
     c.log = LEG_LOG_BUILD && bd.leg_log != nullptr;
     __syncwarp();
     // every lane stores the same (warp-uniform) values: no divergent single-lane section
-    aux->op_mt = I.op_mt + v * I.N;
-    aux->op_dur = I.op_dur + v * I.N;
-    aux->job_work = I.job_work + v * I.J;
-    aux->op_log = bd.op_log ? bd.op_log + env * 2 * (int64_t)I.N : nullptr;
-    aux->leg_log = bd.leg_log ? bd.leg_log + env * (int64_t)bd.leg_stride : nullptr;
+    const size_t vo = (size_t)v * (uint32_t)I.N;
+    aux->op_mt = I.op_mt + vo;
+    aux->op_dur = I.op_dur + vo;
+    aux->job_work = I.job_work + (size_t)v * (uint32_t)I.J;
+    aux->lb_mat = I.lb_mat + 2 * (size_t)v;
+    aux->op_log = bd.op_log ? bd.op_log + (size_t)env * (2u * (uint32_t)I.N) : nullptr;
+    aux->leg_log = (LEG_LOG_BUILD && bd.leg_log) ? bd.leg_log + (size_t)env * (uint32_t)bd.leg_stride : nullptr;
     aux->outs = (JSL_LVL_OUT(CL) && bd.outs) ? (void*)(slot + Slot<JW>::OUTS) : nullptr;
     if (ST) {
-        aux->tcur = bd.tcur + env * (int64_t)I.n_tobj;
-        aux->tseed = bd.tseed ? bd.tseed + env * (int64_t)I.n_tobj : nullptr;
-        aux->start_seeds = bd.start_seeds ? bd.start_seeds + env * (int64_t)I.n_tobj : nullptr;
-        aux->tape = bd.tape ? bd.tape + env * bd.tape_stride : nullptr;
+        aux->tcur = bd.tcur + (size_t)env * (uint32_t)I.n_tobj;
+        aux->tseed = bd.tseed ? bd.tseed + (size_t)env * (uint32_t)I.n_tobj : nullptr;
+        aux->start_seeds = bd.start_seeds ? bd.start_seeds + (size_t)env * (uint32_t)I.n_tobj : nullptr;
+        aux->tape = bd.tape ? bd.tape + (size_t)env * bd.tape_stride : nullptr;
         aux->tape_len = (int)bd.tape_stride;
-    } else {
-        aux->tcur = nullptr; aux->tseed = nullptr; aux->start_seeds = nullptr; aux->tape = nullptr; aux->tape_len = 0;
     }
-    aux->seed = bd.seed;
-    aux->env_id = (uint64_t)(bd.env_base + env);
-    aux->lower_bound = I.lb_mat[2 * v];
-    aux->max_allowed_time = I.lb_mat[2 * v + 1];
+    if (ST || !STEP) {  // Philox key / stream: stochastic draws and the RANDOM policy
+        aux->seed = bd.seed;
+        aux->env_id = (uint64_t)(bd.env_base + env);
+    }
     aux->neg_inv_n = I.neg_inv_n;
-    aux->act_block = 0;
+    if (!STEP) aux->act_block = 0;
     __syncwarp();
 }
 
+// per-env scalars of a step: one 32-byte jsl_step_record (two 16-byte stores) or, for callers that did not ask for
+// it, the separate arrays
 template <int JW, bool ST, int CL>
-__device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c, const jsl_step_out& out, int64_t env,
+__device__ __forceinline__ void write_scalars(const EnvS<JW, ST, CL>& s, const jsl_step_out& out, uint32_t env,
+                                              double reward, int status, const int16_t (&cd)[4]) {
+    if (JSL_LANE != 0) return;
+    if (out.record) {
+        int4 a, b;
+        a.x = __double2loint(reward); a.y = __double2hiint(reward);
+        a.z = s.time; a.w = s.terminated ? s.time : -1;
+        b.x = (int)((uint32_t)(uint16_t)cd[0] | ((uint32_t)(uint16_t)cd[1] << 16));
+        b.y = (int)((uint32_t)(uint16_t)cd[2] | ((uint32_t)(uint16_t)cd[3] << 16));
+        b.z = (int)((uint32_t)s.terminated | ((uint32_t)s.truncated << 8) | ((uint32_t)status << 16));
+        b.w = 0;
+        int4* q = (int4*)(out.record + env);
+        q[0] = a; q[1] = b;
+        return;
+    }
+    if (out.reward) out.reward[env] = reward;
+    if (out.terminated) out.terminated[env] = s.terminated;
+    if (out.truncated) out.truncated[env] = s.truncated;
+    if (out.status) out.status[env] = (uint8_t)status;
+    if (out.time) out.time[env] = s.time;
+    if (out.makespan) out.makespan[env] = s.terminated ? s.time : -1;
+    if (out.cand) {
+        int16_t* q = out.cand + (size_t)env * 4;
+        q[0] = cd[0]; q[1] = cd[1]; q[2] = cd[2]; q[3] = cd[3];
+    }
+}
+
+template <int JW, bool ST, int CL>
+__device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c, const jsl_step_out& out, uint32_t env,
                                                double reward, int obs_bytes) {
     const int remaining = s.n_possible - s.skip;
-    // the candidate the agent sees next: needed by the observation (current_transition) and by out.cand
+    // the candidate the agent sees next: needed by the observation (current_transition) and by the record
     Trans cand;
     cand.kind = -1; cand.comp = -1; cand.new_state = 0; cand.job = -1;
     const bool have_cand = remaining > 0 && s.status <= JSL_ST_STEP_FAILED;
     if (have_cand) cand = current_candidate(s, c);
     if (out.obs && s.status <= JSL_ST_STEP_FAILED) {
-        uint8_t* o = out.obs + env * (int64_t)obs_bytes;
+        uint8_t* o = out.obs + (size_t)env * (uint32_t)obs_bytes;
         if (c.C->obs_kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o, have_cand ? &cand : nullptr);
         else if (c.C->obs_kind == JSL_OBS_OPERATION_ARRAY) write_obs_oparray(s, c, o, have_cand ? &cand : nullptr);
         else if (c.C->obs_kind == JSL_OBS_TASSEL) write_obs_tassel(s, c, o);
@@ -153,22 +187,11 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c
     int status = s.status;
     if (c.raise && status <= JSL_ST_STEP_FAILED) status = c.raise;  // observation factory raised
     int16_t cd[4] = {-1, -1, -1, 0};
-    if (out.cand && remaining > 0 && status <= JSL_ST_TRUNCATED) {
+    if (remaining > 0 && status <= JSL_ST_TRUNCATED) {
         cd[0] = (int16_t)cand.kind; cd[1] = (int16_t)cand.comp; cd[2] = (int16_t)cand.job;
         cd[3] = (int16_t)(remaining > 32767 ? 32767 : remaining);
     }
-    if (JSL_LANE == 0) {
-        if (out.reward) out.reward[env] = reward;
-        if (out.terminated) out.terminated[env] = s.terminated;
-        if (out.truncated) out.truncated[env] = s.truncated;
-        if (out.status) out.status[env] = (uint8_t)status;
-        if (out.time) out.time[env] = s.time;
-        if (out.makespan) out.makespan[env] = s.terminated ? s.time : -1;
-        if (out.cand) {
-            int16_t* q = out.cand + env * 4;
-            q[0] = cd[0]; q[1] = cd[1]; q[2] = cd[2]; q[3] = cd[3];
-        }
-    }
+    write_scalars(s, out, env, reward, status, cd);
 }
 
 template <int JW, bool ST, int CL>
@@ -176,20 +199,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = WARPS_PER_CTA == 1 ? 0 : warp_index();
-    const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
-    if (env >= bd.B) return;
+    const uint32_t env = blockIdx.x * WARPS_PER_CTA + warp;
+    if (env >= (uint32_t)bd.B) return;
     if (mask && !mask[env]) return;
     uint8_t* slot = smem + warp * slot_stride<JW, CL>(bd);
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
     void* outs_sm = bd.outs ? (void*)(slot + Slot<JW>::OUTS) : nullptr;
     Ctx c;
-    make_ctx<JW, ST, CL>(c, bd, env, slot);
+    make_ctx<JW, ST, CL, true>(c, bd, env, slot);
     run_env_op(s, c, OP_RESET);
     __syncwarp();
     write_step_out(s, c, out, env, 0.0, obs_bytes);
     __syncwarp();
-    copy_in(bd.state + env * (int64_t)bd.state_stride, &s, bd.state_stride);
-    if (bd.outs) copy_in(bd.outs + env * (int64_t)bd.outs_stride, outs_sm, bd.outs_stride);
+    copy_fixed<Image<JW, CL>::BYTES>(bd.state + (size_t)env * Image<JW, CL>::BYTES, &s);
+    if (bd.outs) copy_in(bd.outs + (size_t)env * (uint32_t)bd.outs_stride, outs_sm, bd.outs_stride);
 }
 
 template <int JW, bool ST, int CL>
@@ -197,18 +220,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_STEP_MIN_CTAS)
 k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = WARPS_PER_CTA == 1 ? 0 : warp_index();
-    const int64_t env = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
-    if (env >= bd.B) return;
+    const uint32_t env = blockIdx.x * WARPS_PER_CTA + warp;
+    if (env >= (uint32_t)bd.B) return;
+    const int action = actions[env];  // issued ahead of the image copy, whose latency covers it
     uint8_t* slot = smem + warp * slot_stride<JW, CL>(bd);
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
-    void* outs_sm = bd.outs ? (void*)(slot + Slot<JW>::OUTS) : nullptr;
-    uint8_t* g_state = bd.state + env * (int64_t)bd.state_stride;
-    uint8_t* g_outs = bd.outs ? bd.outs + env * (int64_t)bd.outs_stride : nullptr;
-    copy_fixed<(int)sizeof(EnvS<JW, ST, CL>)>(&s, g_state);
-    if (g_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
+    constexpr int IMG = Image<JW, CL>::BYTES;
+    const bool has_outs = JSL_LVL_OUT(CL) && bd.outs != nullptr;
+    void* outs_sm = (void*)(slot + Slot<JW>::OUTS);
+    uint8_t* g_state = bd.state + (size_t)env * IMG;
+    uint8_t* g_outs = has_outs ? bd.outs + (size_t)env * (uint32_t)bd.outs_stride : nullptr;
+    copy_fixed<IMG>(&s, g_state);
+    if (has_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
     Ctx c;
-    make_ctx<JW, ST, CL>(c, bd, env, slot);
-    const int action = actions[env];
+    make_ctx<JW, ST, CL, true>(c, bd, env, slot);
     double r = run_env_op(s, c, action);
     __syncwarp();
     if (s.status >= JSL_ST_STEP_FAILED) {
@@ -218,8 +243,8 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
             step_noop = s.step_noop;
         double ret = s.ret;
         __syncwarp();
-        copy_in(&s, g_state, bd.state_stride);
-        if (g_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
+        copy_in(&s, g_state, IMG);
+        if (has_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
         s.status = status;
         if (status == JSL_ST_STEP_FAILED) {
             s.truncated = 1; s.terminated = 0; s.obs_done = 1;
@@ -230,8 +255,8 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     }
     write_step_out(s, c, out, env, r, obs_bytes);
     __syncwarp();
-    copy_fixed<(int)sizeof(EnvS<JW, ST, CL>)>(g_state, &s);
-    if (g_outs) copy_in(g_outs, outs_sm, bd.outs_stride);
+    copy_fixed<IMG>(g_state, &s);
+    if (has_outs) copy_in(g_outs, outs_sm, bd.outs_stride);
 }
 
 template <int JW, bool ST, int CL>
@@ -253,10 +278,10 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
         const int64_t env = (int64_t)__shfl_sync(0xffffffffu, next, 0);
         if (env >= bd.B) break;
         Ctx c;
-        make_ctx<JW, ST, CL>(c, bd, env, slot);
+        make_ctx<JW, ST, CL, false>(c, bd, (uint32_t)env, slot);
         bool pending_reset = (flags & JSL_RO_RESET_FIRST) != 0;
         if (!pending_reset) {
-            copy_in(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
+            copy_in(&s, bd.state + env * (int64_t)Image<JW, CL>::BYTES, Image<JW, CL>::BYTES);
             if (bd.outs) copy_in(outs_sm, bd.outs + env * (int64_t)bd.outs_stride, bd.outs_stride);
         }
         if (JSL_LANE == 0) {  // per-env loop constants live in the aux block, not in registers
@@ -294,7 +319,7 @@ k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __rest
         }
         __syncwarp();
         if (!(flags & JSL_RO_NO_WRITEBACK)) {
-            copy_in(bd.state + e * (int64_t)bd.state_stride, &s, bd.state_stride);
+            copy_in(bd.state + e * (int64_t)Image<JW, CL>::BYTES, &s, Image<JW, CL>::BYTES);
             if (bd.outs) copy_in(bd.outs + e * (int64_t)bd.outs_stride, outs_sm, bd.outs_stride);
         }
         __syncwarp();
@@ -308,10 +333,10 @@ k_digest(const __grid_constant__ BatchDev bd, int64_t env, int32_t* out, int cap
     uint8_t* slot = smem;
     EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)smem;
     void* outs_sm = bd.outs ? (void*)(smem + Slot<JW>::OUTS) : nullptr;
-    copy_in(&s, bd.state + env * (int64_t)bd.state_stride, bd.state_stride);
+    copy_in(&s, bd.state + env * (int64_t)Image<JW, CL>::BYTES, Image<JW, CL>::BYTES);
     if (bd.outs) copy_in(outs_sm, bd.outs + env * (int64_t)bd.outs_stride, bd.outs_stride);
     Ctx c;
-    make_ctx<JW, ST, CL>(c, bd, env, slot);
+    make_ctx<JW, ST, CL, true>(c, bd, (uint32_t)env, slot);
     int n = write_digest(s, c, out, cap);
     if (JSL_LANE == 0) *n_out = n;
 }
@@ -362,7 +387,7 @@ int rollout_occupancy(int smem) {  // resident CTAs per SM for the persistent ro
                                      jsl_rollout_out);                                                                \
     cudaError_t launch_digest_jw##N(const BatchDev&, const LaunchCfg&, int64_t, int32_t*, int, int32_t*);            \
     int rollout_occupancy_jw##N(const BatchDev& bd, int smem);                                                                            \
-    int state_bytes_jw##N();                                                                                          \
+    int state_bytes_jw##N(int level);                                                                                 \
     int outs_bytes_jw##N();
 JSL_DECLARE_JW(1)
 JSL_DECLARE_JW(2)
@@ -392,7 +417,7 @@ JSL_DECLARE_JW(4)
         return JSL_BY_KIND(bd, launch_digest, N, bd, lc, e, o, c, n);                                                 \
     }                                                                                                                 \
     int rollout_occupancy_jw##N(const BatchDev& bd, int smem) { return JSL_BY_KIND(bd, rollout_occupancy, N, smem); } \
-    int state_bytes_jw##N() { return (int)sizeof(EnvS<N, false, 0>); }                                                \
+    int state_bytes_jw##N(int level) { return JSL_LVL_BUF(level) ? Image<N, 0>::BYTES : Image<N, 1>::BYTES; }          \
     int outs_bytes_jw##N() { return (int)sizeof(OutS<N>); }
 
 }  // namespace jsl

@@ -155,15 +155,16 @@ class Batch:
         self.L.jsl_batch_shape(self.h, C.byref(self.shape))
         dev = torch.device("cuda", self.device)
         ob = max(self.shape.obs_bytes, 16)
+        # per-env scalars of a step arrive as one 32-byte jsl_step_record per env; the named fields are strided views
+        self.record = torch.zeros((self.B, abi.STEP_RECORD_BYTES), dtype=torch.uint8, device=dev)
+        rec = self.record
+        i32 = rec[:, 8:16].view(torch.int32)
         self.out = StepResult(
             obs=torch.zeros((self.B, ob), dtype=torch.uint8, device=dev),
-            reward=torch.zeros(self.B, dtype=torch.float64, device=dev),
-            terminated=torch.zeros(self.B, dtype=torch.uint8, device=dev),
-            truncated=torch.zeros(self.B, dtype=torch.uint8, device=dev),
-            status=torch.zeros(self.B, dtype=torch.uint8, device=dev),
-            time=torch.zeros(self.B, dtype=torch.int32, device=dev),
-            makespan=torch.zeros(self.B, dtype=torch.int32, device=dev),
-            cand=torch.zeros((self.B, 4), dtype=torch.int16, device=dev),
+            reward=rec[:, 0:8].view(torch.float64)[:, 0],
+            terminated=rec[:, 24], truncated=rec[:, 25], status=rec[:, 26],
+            time=i32[:, 0], makespan=i32[:, 1],
+            cand=rec[:, 16:24].view(torch.int16),
         )
         self.rout = RolloutResult(
             makespan=torch.zeros(self.B, dtype=torch.int32, device=dev),
@@ -172,10 +173,8 @@ class Batch:
             status=torch.zeros(self.B, dtype=torch.uint8, device=dev),
             no_op_count=torch.zeros(self.B, dtype=torch.int32, device=dev),
         )
-        o = self.out
-        self._step_out = abi.StepOut(o.obs.data_ptr() if self.shape.obs_bytes else None, o.reward.data_ptr(),
-                                     o.terminated.data_ptr(), o.truncated.data_ptr(), o.status.data_ptr(),
-                                     o.time.data_ptr(), o.makespan.data_ptr(), o.cand.data_ptr())
+        self._step_out = abi.StepOut(self.out.obs.data_ptr() if self.shape.obs_bytes else None, None, None, None, None,
+                                     None, None, None, rec.data_ptr())
         r = self.rout
         self._roll_out = abi.RolloutOut(r.makespan.data_ptr(), r.n_steps.data_ptr(), r.ret.data_ptr(),
                                         r.status.data_ptr(), r.no_op_count.data_ptr())

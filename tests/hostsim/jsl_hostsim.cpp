@@ -75,14 +75,20 @@ void make_ctx(Sim* s, Ctx& c) {
     a.start_seeds = s->start_seeds.empty() ? nullptr : s->start_seeds.data();
     a.tape = s->tape.empty() ? nullptr : s->tape.data(); a.tape_len = (int)s->tape.size();
     a.seed = s->seed; a.env_id = s->env_id; a.act_block = 0;
-    a.lower_bound = s->lb_mat[0]; a.max_allowed_time = s->lb_mat[1]; a.neg_inv_n = -1.0 / (double)s->I.N;
+    a.lb_mat = s->lb_mat.data(); a.neg_inv_n = -1.0 / (double)s->I.N;
 }
 
+// Only the first Image<JW, CL>::BYTES of the state travel to HBM between the launches of step mode: poison the rest
+// after every operation, so that any dependence of the engine on scratch surviving a launch shows up here.
+template <int JW, bool ST, int CL> void scrub(Sim* s) {
+    std::memset(s->state.data() + Image<JW, CL>::BYTES, 0xA5, sizeof(EnvS<JW, ST, CL>) - Image<JW, CL>::BYTES);
+}
 template <int JW, bool ST, int CL> int do_reset(Sim* s) {
     EnvS<JW, ST, CL>& st = *(EnvS<JW, ST, CL>*)s->state.data();
     Ctx c; make_ctx(s, c);
     run_env_op(st, c, OP_RESET);
     s->last_reward = 0.0;
+    scrub<JW, ST, CL>(s);
     return st.status;
 }
 template <int JW, bool ST, int CL> int do_step(Sim* s, int action) {
@@ -99,6 +105,7 @@ template <int JW, bool ST, int CL> int do_step(Sim* s, int action) {
         if (status == JSL_ST_STEP_FAILED) { o.truncated = 1; o.terminated = 0; o.obs_done = 1; o.n_steps = n_steps; o.reward_noop = rn; o.step_action = sa; o.step_noop = sn; o.ret = ret; }
     }
     s->last_reward = r;
+    scrub<JW, ST, CL>(s);
     return ((EnvS<JW, ST, CL>*)s->state.data())->status;
 }
 template <int JW, bool ST, int CL> int do_digest(Sim* s, int32_t* out, int cap) {
@@ -125,6 +132,7 @@ template <int JW, bool ST, int CL> int do_rollout(Sim* s, int policy, const uint
         run_env_op(st, c, a);
         n++;
     }
+    scrub<JW, ST, CL>(s);
     return n;
 }
 template <int JW, bool ST, int CL> void get_scalars(Sim* s, int32_t* o) {

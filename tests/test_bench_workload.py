@@ -38,4 +38,35 @@ def test_reference_arm_line():
                          capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
     d = json.loads(out)
     assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    from oracle import ref_bench
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_bench.available() else "port")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"] == bench.WORKLOAD
+    assert d["config"]["envs"] > 0 and "envs_per_gpu" not in d["config"]  # the line prints what it ran
+
+
+def test_torch_bounds_equal_numpy():
+    import torch
+
+    om, od = bench.make_instances(3000, first=500)
+    lb, mat = bench.taillard_bounds(om, od)
+    lt, mt = bench.taillard_bounds_torch(torch.from_numpy(om), torch.from_numpy(od), chunk=1024)
+    assert np.array_equal(lb, lt.numpy()) and np.array_equal(mat, mt.numpy())
+    a, b = bench.make_instances(2 * bench.BLOCK + 7, first=11, threads=1)
+    c, d = bench.make_instances(2 * bench.BLOCK + 7, first=11, threads=4)
+    assert np.array_equal(a, c) and np.array_equal(b, d)
+
+
+def test_reference_pool_matches_oracle():
+    """The bench's CPU baseline steps the UNMODIFIED reference on the bench's own instances and Philox action
+    streams; its finished episodes must be the oracle's (and, in bench.py, the GPU's)."""
+    import pytest
+    from oracle import ref_bench
+
+    if not ref_bench.available():
+        pytest.skip("reference not installed (oracle/make_ref.py)")
+    pool = bench.reference_pool(2, episodes_per_worker=1)
+    r = pool.run(0)
+    pool.close()
+    ora, _ = bench.cpu_run(2, 2)
+    got = {i: (mk, ns) for i, mk, ns, term in r["episodes"]}
+    assert got == {i: (int(ora["makespan"][i]), int(ora["n_steps"][i])) for i in range(2)}

@@ -9,6 +9,7 @@ from pathlib import Path
 import pytest
 
 import _golden as G
+from jobshoplab_b200 import abi
 
 ROOT = Path(__file__).resolve().parent.parent
 
@@ -66,7 +67,7 @@ def test_abi_library_exports_every_declared_symbol():
         lib = ctypes.CDLL(str(path))
         for sym in declared:
             getattr(lib, sym)
-        assert lib.jsl_abi_version() == 1
+        assert lib.jsl_abi_version() == abi.ABI_VERSION == 2
 
 
 def test_no_cpu_fallback():
@@ -83,3 +84,17 @@ def test_no_cpu_fallback():
     for p in (ROOT / "jobshoplab_b200").glob("*.py"):
         text = p.read_text()
         assert "import oracle" not in text and "from oracle" not in text and "hostsim" not in text, p
+
+
+def test_time_fraction_shortcut_is_exact():
+    """jsl_engine.cuh time_fraction(): float32(t * (1/m)) == float32(t / m) for every integer pair the engine feeds it
+    (m < 2^22): exhaustive for small m, random for large."""
+    import numpy as np
+
+    for m in range(1, 1500):
+        t = np.arange(0, 3 * m + 5, dtype=np.float64)
+        assert np.array_equal((t / m).astype(np.float32), (t * (1.0 / m)).astype(np.float32)), m
+    rng = np.random.default_rng(1)
+    m = rng.integers(1, 1 << 22, size=4_000_000).astype(np.float64)
+    t = np.floor(rng.random(4_000_000) * m * 1.5)
+    assert np.array_equal((t / m).astype(np.float32), (t * (1.0 / m)).astype(np.float32))
