@@ -240,6 +240,13 @@ int jsl_batch_load_variants(jsl_batch_t*, const int32_t* op_machine, const int32
 int jsl_batch_stage_variants(jsl_batch_t*, const int32_t* op_machine, const int32_t* op_duration,
                              const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream);
 int jsl_batch_commit_variants(jsl_batch_t*, void* stream);
+/* Uploaded tables are validated on the device while they are packed (the host arrays of the staged path are never
+ * walked on the CPU): an operation machine outside [0, n_machines) or a negative duration is replaced by 0 and
+ * counted.  jsl_batch_check synchronises and returns JSL_E_INVALID (+ jsl_last_error) if any such entry was seen
+ * since the batch was created, JSL_OK otherwise.  (jsl_batch_create* validate their host arrays directly.)
+ * A jsl_rollout that ends on a validation error or an escaping exception leaves the env with that status; its state
+ * image is then unspecified (jsl_step restores the pre-step state instead, as the reference does, state.py:202-210). */
+int jsl_batch_check(jsl_batch_t*);
 /* compiler/manipulators.py:99-150 InstanceRandomizer.manipulate for every variant of the batch, on the device:
  * per job a uniformly random permutation of its operations (machine and tool travel together) and durations
  * uniform in [min_duration, max_duration) (random.randrange); per-job work, the lower bound and

@@ -508,10 +508,12 @@ class Compiler:
                 raise InvalidValue("compiler.manipulators", m)  # the reference: AttributeError from getattr
         self.manipulators = tuple(MANIPULATORS[m] for m in names)
 
-    def compile(self) -> L.LoweredInstance:
+    def compile(self, manipulate: bool = True) -> L.LoweredInstance:
+        """manipulate=False: the instance as loaded, before compiler.manipulators run (what the reference's
+        InstanceRandomizer is handed on every reset: it takes its duration range from THAT instance)."""
         li = lower_dict(self.repo.load_as_dict())
-        for manipulate in self.manipulators:  # compiler.py:98-99
-            li = manipulate(li)
+        for fn in (self.manipulators if manipulate else ()):  # compiler.py:98-99
+            li = fn(li)
         return li
 
 

@@ -64,6 +64,7 @@ struct jsl_batch {
     int sm_count = 148;
     int smem_per_warp = 0;
     int rollout_ctas_per_sm = 0;
+    int32_t* d_bad = nullptr;     // number of out-of-range table entries seen by k_pack_variants (jsl_batch_check)
     int32_t* d_stage = nullptr;   // [2][n_inst*N] + [2][n_inst] staging for jsl_batch_load_variants
     int32_t* d_op_tool = nullptr; // [N]
 };
@@ -71,7 +72,9 @@ struct jsl_batch {
 namespace {
 
 // packs staged (machine, duration) tables into the engine layout and recomputes the per-job work sums
-__global__ void k_pack_variants(int64_t n_inst, int N, int J, const int32_t* __restrict__ job_op_start,
+// (uploaded tables are untrusted input: an operation machine outside [0, M) would index the per-machine state out
+// of bounds inside the engine, so it is replaced by machine 0 and counted; jsl_batch_check reports it)
+__global__ void k_pack_variants(int64_t n_inst, int N, int J, int M, int32_t* bad, const int32_t* __restrict__ job_op_start,
                                 const int32_t* __restrict__ op_tool, const int32_t* __restrict__ st_m,
                                 const int32_t* __restrict__ st_d, const int32_t* __restrict__ st_lb,
                                 const int32_t* __restrict__ st_mat, int32_t* op_mt, int32_t* op_dur,
@@ -80,15 +83,17 @@ __global__ void k_pack_variants(int64_t n_inst, int N, int J, const int32_t* __r
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         int o = (int)(i % N);
-        op_mt[i] = st_m[i] | (op_tool[o] << 16);
-        op_dur[i] = st_d[i];
+        int m = st_m[i], d = st_d[i];
+        if (m < 0 || m >= M || d < 0) { atomicAdd(bad, 1); m = m < 0 || m >= M ? 0 : m; d = d < 0 ? 0 : d; }
+        op_mt[i] = m | (op_tool[o] << 16);
+        op_dur[i] = d;
     }
     const int64_t nj = n_inst * J;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nj; i += stride) {
         int64_t v = i / J;
         int j = (int)(i % J);
         int w = 0;
-        for (int o = job_op_start[j]; o < job_op_start[j + 1]; o++) w += st_d[v * N + o];
+        for (int o = job_op_start[j]; o < job_op_start[j + 1]; o++) w += st_d[v * N + o] < 0 ? 0 : st_d[v * N + o];
         job_work[i] = w;
     }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_inst; i += stride) {
@@ -314,8 +319,10 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
                     3 * ((int)t->m_outage_freq.size() + t->T * I.n_t_out) + 4 * (t->J + t->T * t->J);
     if (cudaMalloc(&p, (size_t)(b->digest_cap + 4) * sizeof(int32_t)) != cudaSuccess) { set_err("cudaMalloc(digest) failed"); jsl_batch_destroy(b); return nullptr; }
     b->allocs.push_back(p); b->d_digest = (int32_t*)p; b->d_digest_n = b->d_digest + b->digest_cap;
-    if (cudaMalloc(&p, sizeof(unsigned long long)) != cudaSuccess) { set_err("cudaMalloc(counter) failed"); jsl_batch_destroy(b); return nullptr; }
+    if (cudaMalloc(&p, 2 * sizeof(unsigned long long)) != cudaSuccess) { set_err("cudaMalloc(counter) failed"); jsl_batch_destroy(b); return nullptr; }
     b->allocs.push_back(p); b->bd.work_counter = (unsigned long long*)p;
+    b->d_bad = (int32_t*)((unsigned long long*)p + 1);
+    cudaMemset(p, 0, 2 * sizeof(unsigned long long));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) b->sm_count = prop.multiProcessorCount;
     return b;
@@ -428,11 +435,25 @@ int jsl_batch_commit_variants(jsl_batch_t* b, void* stream) {
     const InstDev& I = b->bd.inst;
     const size_t n = (size_t)I.n_inst * I.N, ni = (size_t)I.n_inst;
     int32_t *sm = b->d_stage, *sd = sm + n, *sl = sd + n, *sa = sl + ni;
-    k_pack_variants<<<b->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(I.n_inst, I.N, I.J, I.job_op_start, b->d_op_tool, sm, sd, sl, sa,
+    k_pack_variants<<<b->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(I.n_inst, I.N, I.J, I.M, b->d_bad, I.job_op_start, b->d_op_tool, sm, sd, sl, sa,
                                                                       (int32_t*)I.op_mt, (int32_t*)I.op_dur, (int32_t*)I.job_work,
                                                                       (int32_t*)I.lb_mat);
     b->launches++;
     CK(cudaGetLastError());
+    return JSL_OK;
+}
+
+int jsl_batch_check(jsl_batch_t* b) {
+    if (!b) return JSL_E_INVALID;
+    CK(cudaSetDevice(b->device));
+    CK(cudaDeviceSynchronize());
+    int32_t bad = 0;
+    CK(cudaMemcpy(&bad, b->d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+    if (bad) {
+        set_err(std::to_string(bad) + " uploaded table entries were out of range (operation machine outside [0, n_machines) "
+                "or negative duration) and were replaced by 0");
+        return JSL_E_INVALID;
+    }
     return JSL_OK;
 }
 

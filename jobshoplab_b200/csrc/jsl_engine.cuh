@@ -278,7 +278,16 @@ struct Mask {
         for (int i = 0; i < W; i++) c += JSL_POPC(w[i]);
         return c;
     }
-    JSL_M bool test(int i) const { return (w[i >> 5] >> (i & 31)) & 1u; }
+    // (a single-word mask is never indexed dynamically: that would put it into local memory)
+    JSL_M bool test(int i) const { return W == 1 ? ((w[0] >> (i & 31)) & 1u) : ((w[i >> 5] >> (i & 31)) & 1u); }
+    JSL_M void set(int i) { if (W == 1) w[0] |= 1u << (i & 31); else w[i >> 5] |= 1u << (i & 31); }
+    JSL_M void clear(int i) { if (W == 1) w[0] &= ~(1u << (i & 31)); else w[i >> 5] &= ~(1u << (i & 31)); }
+    JSL_M void assign_only(int i) {
+#pragma unroll
+        for (int k = 0; k < W; k++) w[k] = 0;
+        set(i);
+    }
+    JSL_M uint32_t word_of(int i) const { return W == 1 ? w[0] : w[i >> 5]; }
     JSL_M int first() const {  // -1 if empty
 #pragma unroll
         for (int i = 0; i < W; i++)
@@ -754,7 +763,7 @@ JSL_DN void stoch_init(const InstDev* I, int32_t* tcur, uint16_t* tseed, const i
                 if (sd < 0) sd = 0;
                 if (sd >= I->sample_depth) sd = I->sample_depth - 1;
                 tseed[i] = (uint16_t)sd;
-                if (!start_seeds) v = I->sample_table[row * I->sample_depth + sd];
+                v = I->sample_table[row * I->sample_depth + sd];  // the construction-time sample of that seed (:15)
             }
         }
         tcur[i] = v;
@@ -1285,9 +1294,9 @@ JSL_D bool classic_start(EnvS<JW, ST, CL>& s, Ctx& c, const Trans& act) {
             s.t_job[a] = (uint8_t)j;
             s.j_agv[j] = (uint8_t)a;
             leg_open(s, c, a, j, now, end);
-            p.idle.w[a >> 5] &= ~(1u << (a & 31));
+            p.idle.clear(a);
         } else {
-            p.lr.w[j >> 5] |= 1u << (j & 31);
+            p.lr.set(j);
         }
     }
     // machine m is busy now: nobody waiting in front of it can start
@@ -1348,7 +1357,7 @@ JSL_D bool classic_complete(EnvS<JW, ST, CL>& s, Ctx& c, const Mask<1>& mm, cons
     // agv_to_waitingpickup (x2) + agv_to_transit + agv_transit_to_outage + OUTAGE->IDLE
     wp_for<JW>(I.T, [&](int t) {
         if (!tm.test(t)) return;
-        int rank = JSL_POPC(tm.w[t >> 5] & ((1u << (t & 31)) - 1u));
+        int rank = JSL_POPC(tm.word_of(t) & ((1u << (t & 31)) - 1u));
 #pragma unroll
         for (int w = 0; w < JW; w++)
             if (w < (t >> 5)) rank += JSL_POPC(tm.w[w]);
@@ -1425,7 +1434,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                 s.x_tkind[act.comp] = (uint8_t)act.new_state;
                 if (JSL_LVL_BUF(CL)) s.x_tcomp[act.comp] = (uint8_t)act.comp;
                 s.x_tjob[act.comp] = (uint8_t)act.job;
-                tm.w[act.comp >> 5] = 1u << (act.comp & 31);
+                tm.set(act.comp);
             }
         } else {
             bool time_due = false;
@@ -1512,7 +1521,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
                     int j = zr.any() ? zr.pop_first() : zi.pop_first();
                     s.x_tkind[t] = JSL_T_WORKING; s.x_tjob[t] = (uint8_t)j;
                     if (JSL_LVL_BUF(CL)) s.x_tcomp[t] = (uint8_t)t;
-                    tele.w[t >> 5] |= 1u << (t & 31);
+                    tele.set(t);
                 }
             }
             if (!have && !tele.any()) break;
@@ -1833,10 +1842,10 @@ JSL_D float time_fraction(const EnvS<JW, ST, CL>& s) {
 }
 
 template <int JW, bool ST, int CL>
-JSL_D void cand_floats(const EnvS<JW, ST, CL>& s, const Ctx& c, float* tr, const Trans* known = nullptr) {
+JSL_D void cand_floats(const EnvS<JW, ST, CL>& s, const Ctx& c, float (&tr)[3], bool known, const Trans& kc) {
     const InstDev& I = *c.I;
     if (!s.obs_done && s.n_possible - s.skip > 0) {
-        Trans cand = known ? *known : current_candidate(s, c);
+        const Trans cand = known ? kc : current_candidate(s, c);
         int comp_idx = cand.kind == 0 ? cand.comp : I.M + cand.comp;
         tr[0] = I.tr_comp[comp_idx];  // float32 of the float64 quotient, tabulated on the host
         tr[1] = I.tr_job[cand.job];
@@ -1853,11 +1862,11 @@ JSL_D void exec_row_words(uint32_t* rw, uint32_t mask) {
 }
 
 template <int JW, bool ST, int CL>
-JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* out, const Trans* cand = nullptr) {
+JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* out, bool have_cand, const Trans& cand) {
     const InstDev& I = *c.I;
     const int J = I.J, M = I.M;
     float tr[3];
-    cand_floats(s, c, tr, cand);
+    cand_floats(s, c, tr, have_cand, cand);
     float* f = (float*)out;
     int32_t* jprog = (int32_t*)(out + 16);
     int32_t* mprog = jprog + J;
@@ -1905,10 +1914,10 @@ JSL_D void write_obs_binary(const EnvS<JW, ST, CL>& s, const Ctx& c, uint8_t* ou
 // BinaryOperationArrayObservation.make (observations.py:631-693 over :588-618):
 //   f32 current_transition[3] | f32 0 | f32 operation_state[N] | f32 job_locations[J]
 template <int JW, bool ST, int CL>
-JSL_D void write_obs_oparray(const EnvS<JW, ST, CL>& s, Ctx& c, uint8_t* out, const Trans* cand = nullptr) {
+JSL_D void write_obs_oparray(const EnvS<JW, ST, CL>& s, Ctx& c, uint8_t* out, bool have_cand, const Trans& cand) {
     const InstDev& I = *c.I;
     float tr[3];
-    cand_floats(s, c, tr, cand);
+    cand_floats(s, c, tr, have_cand, cand);
     float* f = (float*)out;
     float* ops = f + 4;
     float* loc = ops + I.N;

@@ -143,14 +143,14 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, uint32_t en
 // it, the separate arrays
 template <int JW, bool ST, int CL>
 __device__ __forceinline__ void write_scalars(const EnvS<JW, ST, CL>& s, const jsl_step_out& out, uint32_t env,
-                                              double reward, int status, const int16_t (&cd)[4]) {
+                                              double reward, int status, int cd0, int cd1, int cd2, int cd3) {
     if (JSL_LANE != 0) return;
     if (out.record) {
         int4 a, b;
         a.x = __double2loint(reward); a.y = __double2hiint(reward);
         a.z = s.time; a.w = s.terminated ? s.time : -1;
-        b.x = (int)((uint32_t)(uint16_t)cd[0] | ((uint32_t)(uint16_t)cd[1] << 16));
-        b.y = (int)((uint32_t)(uint16_t)cd[2] | ((uint32_t)(uint16_t)cd[3] << 16));
+        b.x = (int)(((uint32_t)cd0 & 0xffffu) | ((uint32_t)cd1 << 16));
+        b.y = (int)(((uint32_t)cd2 & 0xffffu) | ((uint32_t)cd3 << 16));
         b.z = (int)((uint32_t)s.terminated | ((uint32_t)s.truncated << 8) | ((uint32_t)status << 16));
         b.w = 0;
         int4* q = (int4*)(out.record + env);
@@ -165,7 +165,7 @@ __device__ __forceinline__ void write_scalars(const EnvS<JW, ST, CL>& s, const j
     if (out.makespan) out.makespan[env] = s.terminated ? s.time : -1;
     if (out.cand) {
         int16_t* q = out.cand + (size_t)env * 4;
-        q[0] = cd[0]; q[1] = cd[1]; q[2] = cd[2]; q[3] = cd[3];
+        q[0] = (int16_t)cd0; q[1] = (int16_t)cd1; q[2] = (int16_t)cd2; q[3] = (int16_t)cd3;
     }
 }
 
@@ -180,18 +180,15 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c
     if (have_cand) cand = current_candidate(s, c);
     if (out.obs && s.status <= JSL_ST_STEP_FAILED) {
         uint8_t* o = out.obs + (size_t)env * (uint32_t)obs_bytes;
-        if (c.C->obs_kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o, have_cand ? &cand : nullptr);
-        else if (c.C->obs_kind == JSL_OBS_OPERATION_ARRAY) write_obs_oparray(s, c, o, have_cand ? &cand : nullptr);
+        if (c.C->obs_kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o, have_cand, cand);
+        else if (c.C->obs_kind == JSL_OBS_OPERATION_ARRAY) write_obs_oparray(s, c, o, have_cand, cand);
         else if (c.C->obs_kind == JSL_OBS_TASSEL) write_obs_tassel(s, c, o);
     }
     int status = s.status;
     if (c.raise && status <= JSL_ST_STEP_FAILED) status = c.raise;  // observation factory raised
-    int16_t cd[4] = {-1, -1, -1, 0};
-    if (remaining > 0 && status <= JSL_ST_TRUNCATED) {
-        cd[0] = (int16_t)cand.kind; cd[1] = (int16_t)cand.comp; cd[2] = (int16_t)cand.job;
-        cd[3] = (int16_t)(remaining > 32767 ? 32767 : remaining);
-    }
-    write_scalars(s, out, env, reward, status, cd);
+    const bool show = remaining > 0 && status <= JSL_ST_TRUNCATED;
+    write_scalars(s, out, env, reward, status, show ? cand.kind : -1, show ? cand.comp : -1, show ? cand.job : -1,
+                  show ? (remaining > 32767 ? 32767 : remaining) : 0);
 }
 
 template <int JW, bool ST, int CL>
@@ -356,6 +353,12 @@ cudaError_t launch_reset(const BatchDev& bd, const LaunchCfg& lc, const uint8_t*
 template <int JW, bool ST, int CL>
 cudaError_t launch_step(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* actions, jsl_step_out out, int obs_bytes) {
     if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_step<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+    static bool carved = false;  // per instantiation: room for JSL_STEP_MIN_CTAS resident CTAs' slots, the rest stays L1
+    if (!carved) {
+        int pct = (int)(((long long)lc.smem + 1024) * JSL_STEP_MIN_CTAS * 100 / (228 * 1024)) + 1;
+        cudaFuncSetAttribute(k_step<JW, ST, CL>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+        carved = true;
+    }
     k_step<JW, ST, CL><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, actions, out, obs_bytes);
     return cudaGetLastError();
 }

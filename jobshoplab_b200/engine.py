@@ -23,7 +23,7 @@ LOG_LIB_PATH = Path(os.environ.get("JSL_LOG_LIB", Path(__file__).resolve().paren
 _libs: dict = {}
 
 ABI_SYMBOLS = ("jsl_last_error", "jsl_abi_version", "jsl_instance_create", "jsl_instance_destroy", "jsl_batch_create",
-               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_stage_variants", "jsl_batch_commit_variants", "jsl_batch_randomize", "jsl_batch_get_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
+               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_stage_variants", "jsl_batch_commit_variants", "jsl_batch_check", "jsl_batch_randomize", "jsl_batch_get_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
                "jsl_reset", "jsl_step", "jsl_rollout", "jsl_get_state", "jsl_get_op_log", "jsl_get_leg_log", "jsl_launch_count")
 
 RO_RESET_FIRST, RO_NO_WRITEBACK = 1, 2
@@ -53,6 +53,7 @@ def load_library(log: bool = False):
     L.jsl_batch_load_variants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.jsl_batch_stage_variants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.jsl_batch_commit_variants.argtypes = [C.c_void_p, C.c_void_p]
+    L.jsl_batch_check.argtypes = [C.c_void_p]
     L.jsl_batch_randomize.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.jsl_batch_get_variants.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 5
     L.jsl_batch_destroy.argtypes = [C.c_void_p]
@@ -141,6 +142,10 @@ class Batch:
         if variants is not None:
             om, od, lb, mat = (np.ascontiguousarray(a, dtype=np.int32) for a in variants)
             n_inst = om.shape[0]
+            n_ops = self.lowered[0].n_ops
+            if om.ndim != 2 or om.shape != (n_inst, n_ops) or od.shape != om.shape or lb.shape != (n_inst,) or mat.shape != (n_inst,):
+                raise InvalidValue("variants", (om.shape, od.shape, lb.shape, mat.shape),
+                                   f"expected op tables [n][{n_ops}] and bounds [n]")
             self.n_variants = int(n_inst)
             self.h = self.L.jsl_batch_create_variants(self.instances[0].h, n_inst, om.ctypes.data, od.ctypes.data,
                                                       lb.ctypes.data, mat.ctypes.data, self.B, self.device, seed,
@@ -198,7 +203,10 @@ class Batch:
 
     def _host_ptrs(self, arrays):
         ptrs = []
-        for a in arrays:
+        n, N = int(self.n_variants), self.shape.n_ops
+        for a, want in zip(arrays, (n * N, n * N, n, n)):
+            if int(a.numel() if hasattr(a, "numel") else a.size) != want:
+                raise InvalidValue("variant tables", tuple(a.shape), f"expected {want} int32 elements")
             if hasattr(a, "data_ptr"):
                 assert not a.is_cuda and a.dtype == self.torch.int32 and a.is_contiguous()
                 ptrs.append(a.data_ptr())
@@ -218,6 +226,10 @@ class Batch:
         rollout still runs on the tables in use)."""
         ptrs = self._host_ptrs((op_machine, op_duration, lower_bound, max_allowed_time))
         self._check(self.L.jsl_batch_stage_variants(self.h, *ptrs, self._stream()))
+
+    def check(self):
+        """Raises if any uploaded table entry was out of range (validated on the device while packing; synchronises)."""
+        self._check(self.L.jsl_batch_check(self.h))
 
     def commit_variants(self):
         """Second half: staged tables -> live tables on the current stream."""

@@ -16,7 +16,7 @@ from pathlib import Path
 
 import numpy as np
 
-from . import abi, compiler as _compiler
+from . import abi, compiler as _compiler, spaces as _spaces
 from .config import Config
 from .engine import Batch
 from .exceptions import (STATUS_TO_EXCEPTION, ConfigurationError, EnvDone, InvalidValue)
@@ -59,16 +59,38 @@ def _cfg_kwargs(config: Config) -> dict:
                 dense_bias=rw.dense_bias, truncation_bias=rw.truncation_bias)
 
 
-def _lower(config: Config, compiler) -> LoweredInstance:
+def _lower(config: Config, compiler, manipulate: bool = True) -> LoweredInstance:
     if isinstance(compiler, LoweredInstance):
         return compiler
     if compiler is None:
         compiler = _compiler.Compiler(config)
-    out = compiler.compile()
+    try:
+        out = compiler.compile(manipulate=manipulate) if not manipulate else compiler.compile()
+    except TypeError:  # a user compiler without the keyword
+        out = compiler.compile()
     if not isinstance(out, LoweredInstance):
         raise InvalidValue("compiler", type(out), "compile() must return a LoweredInstance "
                            "(use jobshoplab_b200.compiler.Compiler)")
     return out
+
+
+def _same_instance(a: LoweredInstance, b: LoweredInstance) -> bool:
+    """Equal lowered tables: the device batch built for `a` serves `b` (reset then costs one kernel, no allocation)."""
+    import dataclasses
+
+    for f in dataclasses.fields(a):
+        x, y = getattr(a, f.name), getattr(b, f.name)
+        if f.name.endswith("_spec"):
+            for k in ("kind", "base", "param"):
+                xx, yy = getattr(x, k), getattr(y, k)
+                if (xx is None) != (yy is None) or (xx is not None and not np.array_equal(xx, yy)):
+                    return False
+        elif isinstance(x, np.ndarray):
+            if not np.array_equal(x, y):
+                return False
+        elif f.name != "description" and x != y:
+            return False
+    return True
 
 
 class BatchedJobShopLabEnv:
@@ -77,11 +99,12 @@ class BatchedJobShopLabEnv:
     def __init__(self, config: Config | None = None, num_envs: int = 1, compiler=None, device: int = 0, seed: int = 0,
                  instances=None, variants=None, record_ops: bool = False, auto_reset: bool = False):
         self.config = config or Config()
-        lowered = instances if instances is not None else _lower(self.config, compiler)
         # compiler.manipulators = [InstanceRandomizer]: the reference recompiles -- and so re-randomises -- the
         # instance on every env.reset (env.py:491).  Batched: every env owns a variant of the operation
-        # tables, redrawn on the device whenever that env is reset (engine.Batch.randomize).
+        # tables, redrawn on the device whenever that env is reset (engine.Batch.randomize).  The manipulator takes
+        # its duration range from the instance it is handed, i.e. the UN-manipulated one (manipulators.py:122-125).
         self.randomize = "InstanceRandomizer" in [m for m in self.config.compiler.manipulators if m]
+        lowered = instances if instances is not None else _lower(self.config, compiler, manipulate=not self.randomize)
         if self.randomize and variants is None and instances is None:
             li = lowered
             tile = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.int32), (num_envs, len(a))))
@@ -89,13 +112,21 @@ class BatchedJobShopLabEnv:
                         np.full(num_envs, li.max_allowed_time, np.int32))
         self.batch = Batch(lowered, num_envs, device=device, seed=seed, variants=variants, record_ops=record_ops,
                            **_cfg_kwargs(self.config))
+        if self.randomize and self.batch.n_variants != num_envs:
+            # the redraw mask is per env: with shared variants, resetting one env would rewrite tables under others
+            raise ConfigurationError("compiler.manipulators", "InstanceRandomizer",
+                                     f"needs one variant per env (got {self.batch.n_variants} variants for {num_envs} envs)")
         self.instance = self.batch.lowered[0]
         self.num_envs = num_envs
         self.auto_reset = auto_reset
-        self.action_space = Discrete(2)
+        self.action_space = _spaces.action_space()
+        self.observation_space = _spaces.observation_space(self.batch.cfg.obs_kind, self.instance.n_jobs,
+                                                           self.instance.n_machines, self.instance.n_ops)
         self._seed, self._epoch = int(seed), 0
         d = np.asarray(self.instance.op_duration)
         self._dur_range = (int(d.min()), int(d.max()))  # of the instance handed to the manipulator
+        if self.randomize:
+            self._redraw()  # the reference's constructor compiles (and randomises) once as well
 
     def _redraw(self, mask=None):
         self._epoch += 1
@@ -109,18 +140,21 @@ class BatchedJobShopLabEnv:
         return self.batch.unpack_obs(out.obs), out
 
     def step(self, actions):
-        """actions: uint8 CUDA tensor [B].  Returns (obs dict of views, reward, terminated, truncated, out)."""
+        """actions: uint8 CUDA tensor [B].  Returns (obs dict of views, reward, terminated, truncated, out).
+        With auto_reset, every env that ended -- terminated, truncated, or dead with an escaped exception
+        (status >= JSL_ST_STEP_FAILED, reported in out.status) -- is reset at once."""
         out = self.batch.step(actions)
         if self.auto_reset:
-            done = (out.terminated | out.truncated)
+            done = (out.terminated | out.truncated | (out.status >= abi.ST_STEP_FAILED).to(out.terminated.dtype)).contiguous()
             if bool(done.any()):
-                final = {k: v.clone() for k, v in (("reward", out.reward), ("terminated", out.terminated),
-                                                   ("truncated", out.truncated), ("makespan", out.makespan))}
+                final = self.batch.record.clone()
                 if self.randomize:
                     self._redraw(done)
                 self.batch.reset(done)
-                out.reward.copy_(final["reward"]); out.terminated.copy_(final["terminated"])
-                out.truncated.copy_(final["truncated"]); out.makespan.copy_(final["makespan"])
+                # reward / makespan / flags of the finished step survive the reset; observation, time, status and
+                # candidate are the fresh episode's
+                rec = self.batch.record
+                rec[:, 0:8] = final[:, 0:8]; rec[:, 12:16] = final[:, 12:16]; rec[:, 24:26] = final[:, 24:26]
         return self.batch.unpack_obs(out.obs), out.reward, out.terminated, out.truncated, out
 
     # gymnasium.vector / SB3 VecEnv style split step (SURVEY 8(f)2): the launch is asynchronous on the
@@ -146,23 +180,61 @@ class BatchedJobShopLabEnv:
         self.batch.close()
 
 
+class _ActionView:
+    """`.transitions` of the Action a history entry was made with (types/action_types.py:36-46)."""
+
+    __slots__ = ("transitions",)
+
+    def __init__(self, transitions):
+        self.transitions = transitions
+
+
+class HistoryEntry:
+    """What user code reads of a ``StateMachineResult`` in ``env.history`` (env.py:404-411, :446): the action's
+    transitions (empty = no-op), success, message and the time after the step.  States are not kept per step --
+    ``env.state`` rebuilds the current one, ``env.gantt_data()`` / ``render()`` work from the engine's logs."""
+
+    __slots__ = ("action", "success", "message", "time")
+
+    def __init__(self, transitions, success, message, time):
+        self.action, self.success, self.message, self.time = _ActionView(transitions), success, message, time
+
+
+def _factory_name(arg, default):
+    if arg is None:
+        return default
+    if isinstance(arg, str):
+        return arg
+    return getattr(arg, "__name__", None) or type(arg).__name__
+
+
 class JobShopLabEnv:
     """Single-env drop-in (env.py:293-618).  `compiler` may be a jobshoplab_b200.compiler.Compiler, a
-    LoweredInstance, or None (built from config.compiler like the reference)."""
+    LoweredInstance, or None (built from config.compiler like the reference).  The factory / middleware arguments
+    take what the reference takes -- a class, an instance or (as in the config) a name -- as long as it names one of
+    the stock classes the engine implements; for user-defined factories plug the engine into the reference's own env
+    instead (jobshoplab_b200.middleware.CudaEventBasedBinaryActionMiddleware, INTEGRATION.md)."""
 
     metadata = {"render_modes": ["normal", "dashboard", "debug"]}
 
     def __init__(self, config: Config | None = None, seed=None, compiler=None, observation_factory=None,
                  reward_factory=None, middleware=None, action_factory=None, render_backend=None, loglevel=None,
                  device: int = 0):
+        self.config = config or Config()
+        stock = {"observation_factory": tuple(_OBS_KINDS), "reward_factory": ("BinaryActionJsspReward",),
+                 "middleware": ("EventBasedBinaryActionMiddleware", "CudaEventBasedBinaryActionMiddleware"),
+                 "action_factory": ("BinaryJobActionFactory",)}
         for name, arg in (("observation_factory", observation_factory), ("reward_factory", reward_factory),
                           ("middleware", middleware), ("action_factory", action_factory)):
-            if arg is not None and not isinstance(arg, str):
-                raise ConfigurationError(name, arg, "the CUDA engine implements the reference's stock classes; "
-                                         "select them by name through the config")
-        self.config = config or Config()
-        if isinstance(observation_factory, str):
-            self.config.env.observation_factory = observation_factory
+            if arg is None:
+                continue
+            cls = _factory_name(arg, None)
+            if cls not in stock[name]:
+                raise ConfigurationError(name, cls, "the CUDA engine implements the reference's stock classes "
+                                         f"{stock[name]}; for a user-defined one use the reference env with "
+                                         "jobshoplab_b200.middleware.CudaEventBasedBinaryActionMiddleware")
+            if name == "observation_factory":
+                self.config.env.observation_factory = cls
         self._compiler = compiler
         self._device = device
         self.seed = seed
@@ -181,40 +253,53 @@ class JobShopLabEnv:
         return self.instance.n_ops
 
     def _obs_host(self):
-        views = self._batch.unpack_obs(self._batch.out.obs)
-        host = {k: v[0].cpu().numpy() for k, v in views.items()}
-        if self._batch.cfg.obs_kind == abi.OBS_BINARY_ACTION:
-            for k in ("job_running", "machine_running", "available_jobs"):
-                host[k] = tuple(bool(x) for x in host[k])
-            host["job_executed_on_machine"] = tuple(tuple(bool(x) for x in row) for row in host["job_executed_on_machine"])
-            host["job_progression"] = tuple(int(x) for x in host["job_progression"])
-            host["machine_progression"] = tuple(int(x) for x in host["machine_progression"])
-        return host
+        from .middleware import host_observation
+        return host_observation(self._batch, 0)
+
+    def _record(self):
+        """The 32-byte jsl_step_record of the env: one device->host copy per step."""
+        raw = self._batch.record[0].cpu().numpy().tobytes()
+        reward = float(np.frombuffer(raw, np.float64, 1, 0)[0])
+        time, makespan = (int(x) for x in np.frombuffer(raw, np.int32, 2, 8))
+        cand = tuple(int(x) for x in np.frombuffer(raw, np.int16, 4, 16))
+        return reward, time, makespan, cand, bool(raw[24]), bool(raw[25]), raw[26]
 
     def _get_info(self, no_op: bool) -> dict:
         return {"no_op": no_op, "terminated": self.terminated, "truncated": self.truncated,
-                "makespan": int(self._batch.out.time[0]) if self.terminated else None,
-                "no_op_count": self._no_op_count}
+                "makespan": self._time if self.terminated else None, "no_op_count": self._no_op_count}
+
+    def _cand_transition(self, cand):
+        from .state_view import ComponentTransition, M_STATES, T_STATES
+        kind, comp, job, n = cand
+        if n <= 0:
+            return None
+        return ComponentTransition(f"m-{comp}" if kind == 0 else f"t-{comp}", M_STATES[1] if kind == 0 else T_STATES[1],
+                                   f"j-{job}")
 
     def reset(self, seed=None):
         self.episode_counter += 1
         if seed is None:
             seed = self.seed
         self.seed = seed + self.episode_counter if seed is not None else None
-        self.instance = _lower(self.config, self._compiler)  # the reference recompiles on every reset (env.py:491)
-        if self._batch is not None:
-            self._batch.close()
-        self._batch = Batch(self.instance, 1, device=self._device, seed=self.seed or 0, record_ops=True,
-                            **_cfg_kwargs(self.config))
+        instance = _lower(self.config, self._compiler)  # the reference recompiles on every reset (env.py:491)
+        if self._batch is None or not _same_instance(instance, self.instance):
+            if self._batch is not None:
+                self._batch.close()
+            self._batch = Batch(instance, 1, device=self._device, seed=self.seed or 0, record_ops=True,
+                                **_cfg_kwargs(self.config))
+            self._acts = self._batch.torch.zeros(1, dtype=self._batch.torch.uint8, device=f"cuda:{self._device}")
+        self.instance = instance
         self.lower_bound = self.instance.lower_bound
         self.max_allowed_time = self.instance.max_allowed_time
         self.action_space = Discrete(2)
-        self.observation_space = None
-        out = self._batch.reset()
-        self._raise_for(int(out.status[0]))
+        self.observation_space = _spaces.observation_space(self._batch.cfg.obs_kind, instance.n_jobs, instance.n_machines,
+                                                           instance.n_ops)
+        self._batch.reset()
+        _, self._time, _, self._cand, _, _, status = self._record()
+        self._raise_for(status)
         self.terminated = self.truncated = self.done = False
         self._no_op_count = 0
-        self._acts = self._batch.torch.zeros(1, dtype=self._batch.torch.uint8, device=f"cuda:{self._device}")
+        self.history: tuple = tuple()
         return self._obs_host(), {"env_seed": self.seed}
 
     def _raise_for(self, status: int):
@@ -231,18 +316,17 @@ class JobShopLabEnv:
         if self.done:
             raise EnvDone()
         if not self.action_space.contains(action):
-            status = abi.ST_ACTION_OUT_OF_SPACE if self._batch.out.cand[0, 3] > 0 else abi.ST_NO_POSSIBLE
-            self._raise_for(status)
+            self._raise_for(abi.ST_ACTION_OUT_OF_SPACE if self._cand[3] > 0 else abi.ST_NO_POSSIBLE)
         self._acts.fill_(int(action))
-        out = self._batch.step(self._acts)
-        status = int(out.status[0])
+        self._batch.step(self._acts)
+        applied = (self._cand_transition(self._cand),) if int(action) == 1 else tuple()
+        reward, self._time, _, self._cand, self.terminated, self.truncated, status = self._record()
         self._raise_for(status)
-        self.terminated = bool(out.terminated[0])
-        self.truncated = bool(out.truncated[0])
         self.done = self.terminated or self.truncated
-        if status != abi.ST_STEP_FAILED:
+        if status != abi.ST_STEP_FAILED:  # env.py:444-446: only successful results enter the history
             self._no_op_count += int(action == 0)
-        return self._obs_host(), float(out.reward[0]), self.terminated, self.truncated, self._get_info(action == 0)
+            self.history += (HistoryEntry(applied, True, "Success" if action == 1 else "NO OPERATION", self._time),)
+        return self._obs_host(), reward, self.terminated, self.truncated, self._get_info(action == 0)
 
     def op_log(self) -> np.ndarray:
         """Per-op (start, end) times so far -- what render() / the Gantt dashboard consume (8(f)1)."""

@@ -49,7 +49,7 @@ def local_stats(makespan, n_steps, ret, status, bins: int = 64, lo: int = 0, hi:
     hist = torch.histc(mk, bins=bins, min=lo, max=hi) if mk.numel() else torch.zeros(bins, dtype=torch.float64, device=makespan.device)
     sums = torch.stack([
         torch.tensor(float(status.numel()), dtype=torch.float64, device=makespan.device),
-        ok.sum().to(torch.float64), (status == 2).sum().to(torch.float64), (status > 2).sum().to(torch.float64),
+        ok.sum().to(torch.float64), ((status == 2) | (status == 3)).sum().to(torch.float64), (status > 3).sum().to(torch.float64),
         n_steps.sum().to(torch.float64), mk.sum(), (mk * mk).sum(), ret.sum().to(torch.float64)])
     sums = torch.cat([sums, hist.to(torch.float64)])
     big = torch.iinfo(torch.int64).max

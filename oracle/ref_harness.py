@@ -30,7 +30,17 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-REF_ROOT = Path(os.environ.get("JSL_REFERENCE_ROOT", "/root/reference"))
+def _ref_root() -> Path:
+    """/root/reference where it exists (the build container), else the installed copy oracle/_ref (oracle/make_ref.py;
+    it travels to the GPU box with the repo snapshot)."""
+    env = os.environ.get("JSL_REFERENCE_ROOT")
+    for p in ([Path(env)] if env else []) + [Path("/root/reference"), _HERE / "_ref"]:
+        if (p / "jobshoplab" / "__init__.py").exists():
+            return p
+    return Path("/root/reference")
+
+
+REF_ROOT = _ref_root()
 
 
 def _activate():

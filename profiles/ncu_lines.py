@@ -66,3 +66,34 @@ for f, ls in files:
             if r[i].isdigit():
                 agg[n] += int(r[i])
 print("\nstall samples:", ", ".join(f"{n[6:]}={v}" for n, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v))
+
+# ---- per-function totals (optional 4th argument: the source file the capture was compiled from)
+if len(sys.argv) > 4:
+    import re
+    src = open(sys.argv[4]).read().splitlines()
+    starts = []
+    pat = re.compile(r"^(?:JSL_DN?|JSL_M|JSL_HD|template|static|__device__|__global__|inline)?.*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;]*$")
+    depth = 0
+    for n, line in enumerate(src, 1):
+        if depth <= 1 and line and not line.startswith((" ", "\t", "//", "#", "}", "template", "struct", "constexpr", "namespace")) and "(" in line:
+            m = pat.match(line)
+            if m:
+                starts.append((n, m.group(1)))
+        depth += line.count("{") - line.count("}")
+    fn_tot = defaultdict(lambda: [0, 0])
+    target = [ls for f, ls in files if f.endswith(sys.argv[4].split("/")[-1].replace("engine_r01", "jsl_engine"))]
+    for ls in target[:1]:
+        for r in ls:
+            if not r[I_EXEC].isdigit():
+                continue
+            ln = int(r[0])
+            name = "?"
+            for n, nm in starts:
+                if n <= ln:
+                    name = nm
+                else:
+                    break
+            fn_tot[name][0] += int(r[I_EXEC]); fn_tot[name][1] += int(r[I_SAMP])
+    print("\nper function (instr/unit, % of all, samples):")
+    for nm, (a, b) in sorted(fn_tot.items(), key=lambda kv: -kv[1][0])[:40]:
+        print(f"  {nm:<28} {a / units:10.1f} {100 * a / total:6.1f} %  {b:7d} smp")

@@ -116,9 +116,9 @@ template <int JW, bool ST, int CL> int do_digest(Sim* s, int32_t* out, int cap) 
 template <int JW, bool ST, int CL> int do_obs(Sim* s, uint8_t* out) {
     EnvS<JW, ST, CL>& st = *(EnvS<JW, ST, CL>*)s->state.data();
     Ctx c; make_ctx(s, c);
-    if (s->C.obs_kind == JSL_OBS_OPERATION_ARRAY) { write_obs_oparray(st, c, out); return c.raise ? -c.raise : obs_bytes_oparray(s->I.J, s->I.N); }
+    if (s->C.obs_kind == JSL_OBS_OPERATION_ARRAY) { { Trans none = {-1, -1, 0, -1}; write_obs_oparray(st, c, out, false, none); } return c.raise ? -c.raise : obs_bytes_oparray(s->I.J, s->I.N); }
     if (s->C.obs_kind == JSL_OBS_TASSEL) { write_obs_tassel(st, c, out); return obs_bytes_tassel(s->I.J); }
-    write_obs_binary(st, c, out);
+    { Trans none = {-1, -1, 0, -1}; write_obs_binary(st, c, out, false, none); }
     return obs_bytes_binary(s->I.J, s->I.M);
 }
 template <int JW, bool ST, int CL> int do_rollout(Sim* s, int policy, const uint8_t* tape, int n_tape, int max_steps, uint64_t env_idx) {

@@ -208,3 +208,60 @@ def test_gpu_differential_fuzz():
     import gpu_fuzz
 
     gpu_fuzz.main(100, 3)
+
+
+def test_packed_record_equals_separate_arrays():
+    """jsl_step_out.record (one 32-byte jsl_step_record per env, what engine.Batch uses) carries exactly what the
+    separate per-field arrays of the ABI carry."""
+    import ctypes as C
+
+    eng = _engine()
+    sc = G.Scenario("transport", "ft10-t/random0")
+    B = 9
+    a, b = eng.Batch(sc.lowered, B, **sc.cfg), eng.Batch(sc.lowered, B, **sc.cfg)
+    dev = "cuda"
+    leg = dict(reward=torch.zeros(B, dtype=torch.float64, device=dev), terminated=torch.zeros(B, dtype=torch.uint8, device=dev),
+               truncated=torch.zeros(B, dtype=torch.uint8, device=dev), status=torch.zeros(B, dtype=torch.uint8, device=dev),
+               time=torch.zeros(B, dtype=torch.int32, device=dev), makespan=torch.zeros(B, dtype=torch.int32, device=dev),
+               cand=torch.zeros((B, 4), dtype=torch.int16, device=dev))
+    obs2 = torch.zeros_like(b.out.obs)
+    legacy = abi.StepOut(obs2.data_ptr(), leg["reward"].data_ptr(), leg["terminated"].data_ptr(), leg["truncated"].data_ptr(),
+                         leg["status"].data_ptr(), leg["time"].data_ptr(), leg["makespan"].data_ptr(), leg["cand"].data_ptr(), None)
+    a.reset()
+    assert b.L.jsl_reset(b.h, None, legacy, b._stream()) == 0
+    rng = np.random.default_rng(5)
+    for i in range(len(sc.actions) + 2):
+        acts = torch.from_numpy(rng.integers(0, 2, B).astype(np.uint8)).cuda()
+        out = a.step(acts)
+        assert b.L.jsl_step(b.h, acts.data_ptr(), legacy, b._stream()) == 0
+        torch.cuda.synchronize()
+        for k, v in leg.items():
+            assert torch.equal(getattr(out, k).contiguous(), v), (i, k)
+        assert torch.equal(out.obs, obs2), (i, "obs")
+    a.close(); b.close()
+
+
+def test_uploaded_tables_are_validated_on_the_device():
+    """jsl_batch_stage/commit_variants used to pack whatever machine ids they were handed; a machine outside
+    [0, M) is now neutralised while packing and reported by jsl_batch_check; wrong shapes never reach the library."""
+    import bench
+    from jobshoplab_b200.exceptions import InvalidValue
+
+    eng = _engine()
+    tmpl = bench.template_instance()
+    om, od = bench.make_instances(8)
+    lb, mat = bench.taillard_bounds(om, od)
+    batch = eng.Batch(tmpl, 8, variants=(om, od, lb, mat))
+    batch.check()
+    with pytest.raises(InvalidValue):
+        batch.load_variants(om[:4], od, lb, mat)
+    with pytest.raises(InvalidValue):
+        eng.Batch(tmpl, 8, variants=(om[:, :-1], od[:, :-1], lb, mat))
+    bad = om.copy(); bad[3, 17] = 77
+    batch.load_variants(bad, od, lb, mat)
+    r = batch.rollout("random", reset_first=True)
+    torch.cuda.synchronize()
+    assert (r.status.cpu().numpy() == abi.ST_DONE).all()  # ran on the sanitised table instead of indexing out of bounds
+    with pytest.raises(InvalidValue):
+        batch.check()
+    batch.close()

@@ -182,3 +182,48 @@ def test_sb3_style_vec_env_matches_single_env():
     assert episodes >= 3
     assert venv.env_is_wrapped(object) == [False] * B and len(venv.get_attr("num_envs")) == B
     venv.close(); single.close()
+
+
+def test_gym_surface_of_the_single_env():
+    """env.py:347-358, :404-411, :533-536 of the reference: factories passed as classes / instances / names,
+    observation_space, history, and no device allocation on reset when the instance is unchanged."""
+    from jobshoplab_b200 import Config, JobShopLabEnv
+    from jobshoplab_b200 import compiler as C
+    from jobshoplab_b200.exceptions import ConfigurationError
+
+    sc = G.Scenario("classic", "ft06/random0")
+    li = C.compile_spec_text(sc.source_text)
+
+    class BinaryActionObservationFactory:  # stands for the reference's class of that name
+        pass
+
+    class Mine:
+        pass
+
+    env = JobShopLabEnv(config=Config(), compiler=li, observation_factory=BinaryActionObservationFactory,
+                        middleware="EventBasedBinaryActionMiddleware", seed=3)
+    with pytest.raises(ConfigurationError):
+        JobShopLabEnv(config=Config(), compiler=li, observation_factory=Mine)
+    sp = env.observation_space
+    assert set(sp.keys()) == {"job_running", "job_executed_on_machine", "job_progression", "machine_running",
+                              "machine_progression", "available_jobs", "current_time", "current_transition"}
+    assert sp["job_executed_on_machine"].shape == (6, 6) and sp["current_transition"].dtype == np.float32
+    assert env.action_space.contains(1) and not env.action_space.contains(2)
+    b0 = env._batch
+    for ep in range(2):
+        assert env.history == tuple()
+        n_noop = 0
+        for i, a in enumerate(sc.actions.tolist()):
+            cand = env.state.possible_transitions[0]
+            obs, r, term, trunc, info = env.step(int(a))
+            assert r == float(sc.reward[i]) and info["no_op"] == (a == 0)
+            n_noop += a == 0
+            h = env.history[-1]
+            assert len(env.history) == i + 1 and (len(h.action.transitions) == 0) == (a == 0)
+            if a == 1:
+                assert h.action.transitions[0].component_id == cand.component_id and h.action.transitions[0].job_id == cand.job_id
+            assert info["no_op_count"] == n_noop == sum(len(h.action.transitions) == 0 for h in env.history)
+        assert term and info["makespan"] == sc.meta["makespan"]
+        env.reset()
+        assert env._batch is b0  # same instance: the device batch is reused, reset is one kernel
+    env.close()
