@@ -85,6 +85,9 @@ extern "C" {
 #define JSL_OBS_BINARY_ACTION 1 /* BinaryActionObservationFactory :488-551 (default) */
 #define JSL_OBS_OPERATION_ARRAY 2 /* BinaryOperationArrayObservation :631-693 */
 #define JSL_OBS_TASSEL 3          /* TasselJsspObservation :696-918 (implies record_ops) */
+#define JSL_OBS_STATE 4           /* the env's raw state image (jsl_batch_state_layout names its fields): the input of
+                                     user-defined observation / reward factories (observations.py:31-76,
+                                     rewards.py:11-58 ABCs) written on the torch side */
 
 /*
  * Lowered instance: what jobshoplab.compiler (compiler.py:84, mapper.py:1201,1387) produces,
@@ -183,6 +186,16 @@ typedef struct jsl_step_record {
     int32_t reserved1;
 } jsl_step_record;
 
+/* One field of the state image an env keeps in HBM (= the JSL_OBS_STATE observation record). */
+typedef struct jsl_state_field {
+    char name[24];
+    int32_t offset;     /* bytes from the start of the record */
+    int32_t elem_bytes; /* 1, 2, 4 or 8 */
+    int32_t count;      /* elements (arrays are padded to 32 per lane word; only the first n_jobs / n_machines /
+                           n_transports entries are meaningful) */
+    int32_t is_float;   /* 1: IEEE floating point (f64), 0: integer */
+} jsl_state_field;
+
 /* Device output pointers of one jsl_step; any pointer may be NULL (= not wanted). */
 typedef struct jsl_step_out {
     uint8_t* obs;        /* [B][obs_bytes]   ObservationFactory.make (observations.py:515) */
@@ -264,6 +277,9 @@ int jsl_batch_get_variants(jsl_batch_t*, int64_t first, int64_t count, int32_t* 
                            int32_t* op_duration, int32_t* lower_bound, int32_t* max_allowed_time);
 void jsl_batch_destroy(jsl_batch_t*);
 int jsl_batch_shape(const jsl_batch_t*, jsl_shape* out);
+/* Field table of the state image of this batch (layout of the JSL_OBS_STATE record and of jsl_shape.state_bytes):
+ * writes up to `cap` entries, returns the number of fields. */
+int jsl_batch_state_layout(const jsl_batch_t*, jsl_state_field* out, int cap);
 /* Stochastic instances (stochasticy_models.py): by default every StochasticTimeConfig.update() draws from
  * the reference's own sample function (first variate of numpy default_rng(start seed + n), tabulated).  For bit-exact replay against
  * the reference, hand in the recorded update() results instead: dev int32 [B][stride], consumed in call

@@ -16,7 +16,9 @@ STATUS_NAMES = ("OK", "DONE", "TRUNCATED", "STEP_FAILED", "BUFFER_FULL", "UNSUCC
 POLICY_FIFO, POLICY_SPT, POLICY_MWKR, POLICY_RANDOM, POLICY_TAPE = range(5)
 POLICIES = {"fifo": POLICY_FIFO, "spt": POLICY_SPT, "mwkr": POLICY_MWKR, "random": POLICY_RANDOM,
             "tape": POLICY_TAPE}
-OBS_NONE, OBS_BINARY_ACTION, OBS_OPERATION_ARRAY, OBS_TASSEL = 0, 1, 2, 3
+M_IDLE, M_SETUP, M_WORKING, M_OUTAGE = range(4)                                  # JSL_M_*
+T_IDLE, T_WORKING, T_PICKUP, T_TRANSIT, T_OUTAGE, T_WAITINGPICKUP = range(6)        # JSL_T_*
+OBS_NONE, OBS_BINARY_ACTION, OBS_OPERATION_ARRAY, OBS_TASSEL, OBS_STATE = 0, 1, 2, 3, 4
 
 _i32p = C.POINTER(C.c_int32)
 _f32p = C.POINTER(C.c_float)
@@ -68,6 +70,11 @@ class StepOut(C.Structure):
 
 
 STEP_RECORD_BYTES = 32  # jsl_step_record: f64 reward | i32 time | i32 makespan | i16 cand[4] | u8 terminated, truncated, status
+
+
+class StateField(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("offset", C.c_int32), ("elem_bytes", C.c_int32), ("count", C.c_int32),
+                ("is_float", C.c_int32)]
 
 
 class RolloutOut(C.Structure):

@@ -64,5 +64,25 @@ def build(force: bool = False) -> Path:
     return LIB
 
 
+def build_variant(tag: str, extra_flags, lib: Path, force: bool = False) -> Path:
+    """The same sources with extra nvcc flags into their own library, e.g. a user reward hook:
+    build_variant("_user", ['-DJSL_USER_HEADER="examples/jsl_user_example.cuh"'], CSRC / "libjsl_b200_user.so")."""
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        objs = list(ex.map(lambda u: _compile(u, force, tag, tuple(extra_flags)), UNITS))
+    _link(lib, objs, force)
+    return lib
+
+
+USER_EXAMPLE_LIB = CSRC / "libjsl_b200_user.so"
+
+
+def build_user_example(force: bool = False) -> Path:
+    """libjsl_b200_user.so: the throughput build with csrc/examples/jsl_user_example.cuh as reward hook (tests)."""
+    hdr = CSRC / "examples" / "jsl_user_example.cuh"
+    if hdr not in HEADERS:
+        HEADERS.append(hdr)
+    return build_variant("_user", ['-DJSL_USER_HEADER="examples/jsl_user_example.cuh"'], USER_EXAMPLE_LIB, force)
+
+
 if __name__ == "__main__":
     print(build("--force" in sys.argv))

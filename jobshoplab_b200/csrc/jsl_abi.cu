@@ -314,7 +314,8 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     }
     b->obs_bytes = cfg->obs_kind == JSL_OBS_BINARY_ACTION ? obs_bytes_binary(t->J, t->M)
                    : cfg->obs_kind == JSL_OBS_OPERATION_ARRAY ? obs_bytes_oparray(t->J, t->N)
-                   : cfg->obs_kind == JSL_OBS_TASSEL ? obs_bytes_tassel(t->J) : 0;
+                   : cfg->obs_kind == JSL_OBS_TASSEL ? obs_bytes_tassel(t->J)
+                   : cfg->obs_kind == JSL_OBS_STATE ? ss : 0;
     b->digest_cap = 64 + 3 * t->J + 3 * N + t->M * 6 + 2 * t->J + 11 * t->T + t->S +
                     3 * ((int)t->m_outage_freq.size() + t->T * I.n_t_out) + 4 * (t->J + t->T * t->J);
     if (cudaMalloc(&p, (size_t)(b->digest_cap + 4) * sizeof(int32_t)) != cudaSuccess) { set_err("cudaMalloc(digest) failed"); jsl_batch_destroy(b); return nullptr; }
@@ -523,6 +524,12 @@ int jsl_batch_shape(const jsl_batch_t* b, jsl_shape* out) {
     out->n_tools = I.NT; out->obs_bytes = b->obs_bytes; out->state_bytes = b->bd.state_stride + b->bd.outs_stride;
     out->digest_cap = b->digest_cap;
     return JSL_OK;
+}
+
+int jsl_batch_state_layout(const jsl_batch_t* b, jsl_state_field* out, int cap) {
+    if (!b || (!out && cap > 0)) return JSL_E_INVALID;
+    return b->JW == 1 ? state_layout_jw1(b->bd.classic, out, cap) : b->JW == 2 ? state_layout_jw2(b->bd.classic, out, cap)
+                                                                               : state_layout_jw4(b->bd.classic, out, cap);
 }
 
 int jsl_batch_set_sample_tape(jsl_batch_t* b, const int32_t* dev_tape, int64_t stride) {

@@ -1649,6 +1649,20 @@ JSL_D double make_reward(EnvS<JW, ST, CL>& s, const Ctx& c) {
 #endif
 }
 
+// User hook (the reference's RewardFactory ABC, rewards.py:11-58): a library built with
+// -DJSL_USER_HEADER='"my_hooks.cuh"' includes that header here; it must define
+//     template <int JW, bool ST, int CL>
+//     JSL_D double jsl_user_reward(const EnvS<JW, ST, CL>& s, const Ctx& c, double stock_reward);
+// whose result replaces the reward of every env.step (the stock BinaryActionJsspReward value is handed in).  The
+// state fields it may read are the ones jsl_batch_state_layout lists.  Example: csrc/examples/jsl_user_example.cuh;
+// build: JSL_NVCC_EXTRA='-DJSL_USER_HEADER="\"examples/jsl_user_example.cuh\""' JSL_LIB_OUT=... python -m jobshoplab_b200.build
+#ifdef JSL_USER_HEADER
+#include JSL_USER_HEADER
+#else
+template <int JW, bool ST, int CL>
+JSL_D double jsl_user_reward(const EnvS<JW, ST, CL>&, const Ctx&, double stock_reward) { return stock_reward; }
+#endif
+
 // env.py:427-454 step + middleware.py:384-431 step + :304-368 _get_no_op_result, split around the single
 // sm_step call site of run_env_op().
 struct StepPlan {
@@ -1704,7 +1718,7 @@ JSL_D double env_step_post(EnvS<JW, ST, CL>& s, Ctx& c, int action, const StepPl
         s.obs_done = 1;
         s.truncated = 1; s.terminated = 0;
     }
-    double r = make_reward(s, c);
+    double r = jsl_user_reward(s, c, make_reward(s, c));
     s.ret = s.ret + r;
     s.n_steps = s.n_steps + 1;
     s.status = !success ? JSL_ST_STEP_FAILED : s.terminated ? JSL_ST_DONE : s.truncated ? JSL_ST_TRUNCATED : JSL_ST_OK;

@@ -183,6 +183,7 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c
         if (c.C->obs_kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o, have_cand, cand);
         else if (c.C->obs_kind == JSL_OBS_OPERATION_ARRAY) write_obs_oparray(s, c, o, have_cand, cand);
         else if (c.C->obs_kind == JSL_OBS_TASSEL) write_obs_tassel(s, c, o);
+        else if (c.C->obs_kind == JSL_OBS_STATE) copy_fixed<Image<JW, CL>::BYTES>(o, &s);  // raw state for torch-side factories
     }
     int status = s.status;
     if (c.raise && status <= JSL_ST_STEP_FAILED) status = c.raise;  // observation factory raised
@@ -382,6 +383,39 @@ int rollout_occupancy(int smem) {  // resident CTAs per SM for the persistent ro
     return n > 0 ? n : 1;
 }
 
+// field table of the state image (jsl_batch_state_layout)
+template <int JW>
+int state_layout(int level, jsl_state_field* out, int cap) {
+    using S = EnvS<JW>;
+    const int limit = JSL_LVL_BUF(level) ? Image<JW, 0>::BYTES : Image<JW, 1>::BYTES;
+    int n = 0;
+    auto put = [&](const char* name, size_t off, int eb, int cnt, int flt) {
+        if ((int)off >= limit) return;
+        if (n < cap) {
+            jsl_state_field& f = out[n];
+            int k = 0;
+            for (; name[k] && k < 23; k++) f.name[k] = name[k];
+            for (; k < 24; k++) f.name[k] = 0;
+            f.offset = (int32_t)off; f.elem_bytes = eb; f.count = cnt; f.is_float = flt;
+        }
+        n++;
+    };
+#define JSL_F(field, flt) put(#field, offsetof(S, field), (int)sizeof(((S*)0)->field), 1, flt)
+#define JSL_A(field) put(#field, offsetof(S, field), (int)sizeof(((S*)0)->field[0]), (int)(sizeof(((S*)0)->field) / sizeof(((S*)0)->field[0])), 0)
+    JSL_F(time, 0); JSL_F(seq_ctr, 0); JSL_F(n_possible, 0); JSL_F(skip, 0); JSL_F(joker, 0); JSL_F(step_noop, 0);
+    JSL_F(step_action, 0); JSL_F(reward_noop, 0); JSL_F(n_steps, 0); JSL_F(noop_count, 0); JSL_F(max_done_end, 0);
+    JSL_F(status, 0); JSL_F(terminated, 0); JSL_F(truncated, 0); JSL_F(last_action_empty, 0); JSL_F(obs_done, 0);
+    JSL_F(all_out, 0); JSL_F(draw_ctr, 0); JSL_F(lower_bound, 0); JSL_F(ret, 1); JSL_F(inv_mat, 1); JSL_F(max_allowed_time, 0);
+    JSL_A(c_p1); JSL_A(c_idle); JSL_A(c_lr); JSL_A(c_li);
+    JSL_A(j_start); JSL_A(j_end); JSL_A(j_seq); JSL_A(j_loc); JSL_A(j_k); JSL_A(j_proc); JSL_A(j_agv); JSL_A(j_mach); JSL_A(j_exec);
+    JSL_A(m_occ); JSL_A(m_done); JSL_A(m_state); JSL_A(m_tool); JSL_A(m_job);
+    JSL_A(t_occ); JSL_A(t_loc1); JSL_A(t_state); JSL_A(t_job); JSL_A(t_carry); JSL_A(t_occkind); JSL_A(t_lockind); JSL_A(t_loc0); JSL_A(t_loc2);
+    JSL_A(t_tdbuf); JSL_A(t_tdcomp); JSL_A(t_tdjob);
+#undef JSL_F
+#undef JSL_A
+    return n;
+}
+
 // entry points defined by jsl_kernels_jw<N>.cu
 #define JSL_DECLARE_JW(N)                                                                                             \
     cudaError_t launch_reset_jw##N(const BatchDev&, const LaunchCfg&, const uint8_t*, jsl_step_out, int);             \
@@ -391,6 +425,7 @@ int rollout_occupancy(int smem) {  // resident CTAs per SM for the persistent ro
     cudaError_t launch_digest_jw##N(const BatchDev&, const LaunchCfg&, int64_t, int32_t*, int, int32_t*);            \
     int rollout_occupancy_jw##N(const BatchDev& bd, int smem);                                                                            \
     int state_bytes_jw##N(int level);                                                                                 \
+    int state_layout_jw##N(int level, jsl_state_field* out, int cap);                                                 \
     int outs_bytes_jw##N();
 JSL_DECLARE_JW(1)
 JSL_DECLARE_JW(2)
@@ -421,6 +456,7 @@ JSL_DECLARE_JW(4)
     }                                                                                                                 \
     int rollout_occupancy_jw##N(const BatchDev& bd, int smem) { return JSL_BY_KIND(bd, rollout_occupancy, N, smem); } \
     int state_bytes_jw##N(int level) { return JSL_LVL_BUF(level) ? Image<N, 0>::BYTES : Image<N, 1>::BYTES; }          \
+    int state_layout_jw##N(int level, jsl_state_field* out, int cap) { return state_layout<N>(level, out, cap); }      \
     int outs_bytes_jw##N() { return (int)sizeof(OutS<N>); }
 
 }  // namespace jsl

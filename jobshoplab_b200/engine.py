@@ -23,7 +23,7 @@ LOG_LIB_PATH = Path(os.environ.get("JSL_LOG_LIB", Path(__file__).resolve().paren
 _libs: dict = {}
 
 ABI_SYMBOLS = ("jsl_last_error", "jsl_abi_version", "jsl_instance_create", "jsl_instance_destroy", "jsl_batch_create",
-               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_stage_variants", "jsl_batch_commit_variants", "jsl_batch_check", "jsl_batch_randomize", "jsl_batch_get_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
+               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_stage_variants", "jsl_batch_commit_variants", "jsl_batch_check", "jsl_batch_randomize", "jsl_batch_get_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_state_layout", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
                "jsl_reset", "jsl_step", "jsl_rollout", "jsl_get_state", "jsl_get_op_log", "jsl_get_leg_log", "jsl_launch_count")
 
 RO_RESET_FIRST, RO_NO_WRITEBACK = 1, 2
@@ -58,6 +58,7 @@ def load_library(log: bool = False):
     L.jsl_batch_get_variants.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 5
     L.jsl_batch_destroy.argtypes = [C.c_void_p]
     L.jsl_batch_shape.argtypes = [C.c_void_p, C.POINTER(abi.Shape)]
+    L.jsl_batch_state_layout.argtypes = [C.c_void_p, C.POINTER(abi.StateField), C.c_int]
     L.jsl_batch_set_env_base.argtypes = [C.c_void_p, C.c_int64]
     L.jsl_batch_set_sample_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.jsl_batch_set_start_seeds.argtypes = [C.c_void_p, C.c_void_p]
@@ -335,6 +336,32 @@ class Batch:
     def launches(self) -> int:
         return int(self.L.jsl_launch_count(self.h))
 
+    def state_layout(self) -> dict:
+        """{field: (offset, numpy dtype, count)} of the state image (= the OBS_STATE observation record)."""
+        arr = (abi.StateField * 64)()
+        n = self.L.jsl_batch_state_layout(self.h, arr, 64)
+        if n < 0 or n > 64:
+            raise InvalidValue("jsl_batch_state_layout", n, _err(self.L))
+        out = {}
+        for f in arr[:n]:
+            dt = {(8, 1): np.float64, (4, 0): np.int32, (2, 0): np.uint16, (1, 0): np.uint8}[(f.elem_bytes, f.is_float)]
+            out[f.name.decode()] = (int(f.offset), np.dtype(dt), int(f.count))
+        return out
+
+    def unpack_state(self, rec=None) -> dict:
+        """Named zero-copy views into a [B, state_bytes] uint8 tensor of state images (the OBS_STATE observation):
+        scalars as [B], arrays as [B, 32 * lane words] (entries past n_jobs / n_machines / n_transports are padding).
+        j_* per job, m_* per machine, t_* per transport; meanings: csrc/jsl_engine.cuh EnvS."""
+        torch = self.torch
+        rec = self.out.obs if rec is None else rec
+        tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32, np.dtype(np.uint16): torch.int16,
+               np.dtype(np.uint8): torch.uint8}
+        views = {}
+        for name, (off, dt, cnt) in self.state_layout().items():
+            v = rec[:, off: off + dt.itemsize * cnt].view(tdt[dt])
+            views[name] = v[:, 0] if cnt == 1 else v
+        return views
+
     # ---- observation record -> named views (zero copy) -------------------------------------------------
     def unpack_obs(self, obs=None) -> dict:
         """Views into the packed observation record, keyed like the reference's observation dict
@@ -342,6 +369,8 @@ class Batch:
         torch = self.torch
         obs = self.out.obs if obs is None else obs
         J, M, N = self.shape.n_jobs, self.shape.n_machines, self.shape.n_ops
+        if self.cfg.obs_kind == abi.OBS_STATE:
+            return self.unpack_state(obs)
         if self.cfg.obs_kind == abi.OBS_TASSEL:
             f = obs[:, : 28 * J].view(torch.float32).view(-1, 7, J)
             keys = ("allocatable", "left_over_time", "percent_finished", "total_completion",

@@ -25,7 +25,9 @@ from .state_view import parse_digest
 
 _OBS_KINDS = {"BinaryActionObservationFactory": abi.OBS_BINARY_ACTION,
               "BinaryOperationArrayObservation": abi.OBS_OPERATION_ARRAY,
-              "TasselJsspObservation": abi.OBS_TASSEL}
+              "TasselJsspObservation": abi.OBS_TASSEL,
+              # extension: the raw state record, for user-defined observation / reward functions on the torch side
+              "StateObservation": abi.OBS_STATE}
 
 
 class Discrete:
@@ -97,8 +99,15 @@ class BatchedJobShopLabEnv:
     """B envs of one instance (or of same-shaped instances) on one GPU."""
 
     def __init__(self, config: Config | None = None, num_envs: int = 1, compiler=None, device: int = 0, seed: int = 0,
-                 instances=None, variants=None, record_ops: bool = False, auto_reset: bool = False):
+                 instances=None, variants=None, record_ops: bool = False, auto_reset: bool = False,
+                 observation_fn=None, reward_fn=None):
+        """observation_fn / reward_fn: user-defined factories (the reference's ObservationFactory / RewardFactory ABCs,
+        observations.py:31-76, rewards.py:11-58, in batched form): callables ``fn(views, out) -> tensor`` over the
+        views of the configured observation record (use env.observation_factory = "StateObservation" to get the
+        whole state: Batch.unpack_state) and the step scalars ``out``; their results replace the observation /
+        reward that reset() / step() return.  (A device-side reward hook: csrc/jsl_engine.cuh "User hook".)"""
         self.config = config or Config()
+        self.observation_fn, self.reward_fn = observation_fn, reward_fn
         # compiler.manipulators = [InstanceRandomizer]: the reference recompiles -- and so re-randomises -- the
         # instance on every env.reset (env.py:491).  Batched: every env owns a variant of the operation
         # tables, redrawn on the device whenever that env is reset (engine.Batch.randomize).  The manipulator takes
@@ -137,7 +146,8 @@ class BatchedJobShopLabEnv:
         if self.randomize:
             self._redraw(mask)
         out = self.batch.reset(mask)
-        return self.batch.unpack_obs(out.obs), out
+        views = self.batch.unpack_obs(out.obs)
+        return (self.observation_fn(views, out) if self.observation_fn else views), out
 
     def step(self, actions):
         """actions: uint8 CUDA tensor [B].  Returns (obs dict of views, reward, terminated, truncated, out).
@@ -155,7 +165,9 @@ class BatchedJobShopLabEnv:
                 # candidate are the fresh episode's
                 rec = self.batch.record
                 rec[:, 0:8] = final[:, 0:8]; rec[:, 12:16] = final[:, 12:16]; rec[:, 24:26] = final[:, 24:26]
-        return self.batch.unpack_obs(out.obs), out.reward, out.terminated, out.truncated, out
+        views = self.batch.unpack_obs(out.obs)
+        reward = self.reward_fn(views, out) if self.reward_fn else out.reward
+        return (self.observation_fn(views, out) if self.observation_fn else views), reward, out.terminated, out.truncated, out
 
     # gymnasium.vector / SB3 VecEnv style split step: the launch is asynchronous on the
     # current CUDA stream anyway, step_wait only hands out the views

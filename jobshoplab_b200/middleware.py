@@ -207,6 +207,11 @@ class StateBuilder:
 class CudaEventBasedBinaryActionMiddleware:
     """Drop-in for ``EventBasedBinaryActionMiddleware`` (middleware.py:211-443) running on the CUDA engine."""
 
+    # The reference env builds a NEW middleware object on every env.reset (env.py:518-524); device batches are
+    # therefore kept per lowered instance at class level, so that a reset of an unchanged instance allocates nothing.
+    _batches: dict = {}
+    _MAX_BATCHES = 4
+
     def __init__(self, loglevel, config, instance, action_factory, observation_factory, truncation_joker: int = 5,
                  truncation_active: bool = False, state_machine_step=None, device: int = 0, *args, **kwargs):
         self.loglevel, self.config, self.instance = loglevel, config, instance
@@ -261,15 +266,26 @@ class CudaEventBasedBinaryActionMiddleware:
         li = lower_reference(self.instance, init_state, self._ix)
         key = (li.op_machine.tobytes(), li.op_duration.tobytes(), li.travel_time.tobytes(), li.setup_time.tobytes(),
                li.start_seeds.tobytes(), tuple(li.job_init_buf), tuple(li.agv_init_place))
-        if self._batch is None or key != self._lowered_key:  # same tables: the batch (device memory) is reused
-            if self._batch is not None:
-                self._batch.close()
+        key = (key, tuple(sorted(self._cfg().items())), self.device)
+        cache = type(self)._batches
+        cached = cache.get(key)
+        owner = getattr(cached, "_owner", lambda: None)() if cached is not None else None
+        if cached is not None and cached.h is not None and owner in (None, self):
+            self._batch = cached  # same tables + config and its previous middleware is gone: reuse the device memory
+        else:
+            if cached is None or cached.h is None:
+                while len(cache) >= self._MAX_BATCHES:
+                    cache.pop(next(iter(cache)))
             self._batch = Batch(li, 1, device=self.device, record_ops=True, **self._cfg())
-            self._lowered_key = key
-            if not li.is_deterministic:  # the reference's own numpy start seeds: same sample streams
-                import torch
-                self._seeds = torch.from_numpy(np.ascontiguousarray(li.start_seeds.reshape(1, -1))).to(f"cuda:{self.device}")
-                self._batch.set_start_seeds(self._seeds)
+            if cached is None or cached.h is None:
+                cache[key] = self._batch
+        import weakref
+        self._batch._owner = weakref.ref(self)
+        self._lowered_key = key
+        if not li.is_deterministic:  # the reference's own numpy start seeds: same sample streams
+            import torch
+            self._seeds = torch.from_numpy(np.ascontiguousarray(li.start_seeds.reshape(1, -1))).to(f"cuda:{self.device}")
+            self._batch.set_start_seeds(self._seeds)
         self._builder = StateBuilder(self.instance, init_state, self._ix, self._ref)
         import torch
         self._acts = torch.zeros(1, dtype=torch.uint8, device=f"cuda:{self.device}")
@@ -320,6 +336,10 @@ class CudaEventBasedBinaryActionMiddleware:
         return self._truncated
 
     def close(self):
+        """Frees the device batch of this middleware's instance (and drops it from the class-level cache)."""
         if self._batch is not None:
+            for k, b in list(type(self)._batches.items()):
+                if b is self._batch:
+                    del type(self)._batches[k]
             self._batch.close()
             self._batch = None

@@ -96,7 +96,7 @@ def test_reference_env_with_cuda_middleware_equals_stock(rh, kind, rel, over):
         b0 = cuda.state_simulator._batch
         stock.reset(); cuda.reset()
         _compare(rh, stock, cuda, (rel, seed, "second reset"))
-        if kind == "spec":
+        if kind == "spec":  # (the env made a new middleware object; the device batch is the cached one)
             assert cuda.state_simulator._batch is b0
         with pytest.raises(Exception) as e1:
             stock.step(5)
