@@ -228,7 +228,9 @@ jsl_instance_t* jsl_instance_create(const jsl_instance_desc* d);
 void jsl_instance_destroy(jsl_instance_t*);
 
 /* B envs over n_inst same-shaped instances (env b uses instance b % n_inst), on CUDA device
- * `device`.  Replaces JobShopLabEnv.__init__ wiring (env.py:388-402) for a whole batch.
+ * `device`.  Replaces JobShopLabEnv.__init__ wiring (env.py:388-402) for a whole batch.  The instances share
+ * everything but the operation tables; with stochastic time objects, several instances need static operation
+ * durations (stochastic setup / travel / outage times are shared).
  * The batch is served by the most specialised kernel set the instance allows (classic / simple / queues /
  * features / general) -- all of them bit-exact with the reference; the environment variable
  * JSL_MAX_LEVEL=0|1, read here, forces the less specialised ones (diagnostics, cross-level parity tests). */
@@ -268,7 +270,8 @@ int jsl_batch_check(jsl_batch_t*);
  * so the distribution -- not sample values -- is the contract.  `mask` (dev u8 [n_inst], nullable) selects the
  * variants to redraw (the reference recompiles, hence re-randomises, on every env.reset).  Takes effect at the
  * next jsl_reset of the envs concerned.
- * JSL_E_INVALID for an empty range (the reference raises ValueError), JSL_E_UNSUPPORTED for stochastic batches. */
+ * JSL_E_INVALID for an empty range (the reference raises ValueError), JSL_E_UNSUPPORTED for batches whose operation
+ * durations are stochastic (stochastic setup / travel / outage times are fine: the manipulator makes durations static). */
 int jsl_batch_randomize(jsl_batch_t*, uint64_t seed, int min_duration, int max_duration, const uint8_t* mask,
                         void* stream);
 /* Operation tables of variants [first, first+count) copied to HOST arrays ([count][n_ops] machine, tool,

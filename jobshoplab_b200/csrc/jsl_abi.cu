@@ -2,6 +2,7 @@
 // table upload and kernel dispatch.  The kernels live in jsl_kernels.cuh (one TU per lane-word count).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -64,6 +65,7 @@ struct jsl_batch {
     int sm_count = 148;
     int smem_per_warp = 0;
     int rollout_ctas_per_sm = 0;
+    bool ops_static = true;       // every operation duration is a static time object
     int32_t* d_bad = nullptr;     // number of out-of-range table entries seen by k_pack_variants (jsl_batch_check)
     int32_t* d_stage = nullptr;   // [2][n_inst*N] + [2][n_inst] staging for jsl_batch_load_variants
     int32_t* d_op_tool = nullptr; // [N]
@@ -168,7 +170,16 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     if (3 * t->M + t->T + t->S > 65000) { set_err("unsupported: too many buffers"); return nullptr; }
     for (int j = 0; j < t->J; j++)
         if (t->job_op_start[j + 1] - t->job_op_start[j] > 250) { set_err("unsupported: more than 250 ops per job"); return nullptr; }
-    if (t->stochastic && n_inst != 1) { set_err("unsupported: stochastic instances need a single-instance batch"); return nullptr; }
+    if (t->stochastic && n_inst != 1) {
+        // several variants may share the stochastic setup / travel / outage objects as long as the operation durations
+        // themselves are static (what InstanceRandomizer produces: DeterministicTimeConfig, manipulators.py:133-137)
+        for (int o = 0; o < t->N; o++)
+            if (t->tobj.kind[o] != JSL_TIME_STATIC) {
+                set_err("unsupported: batches of several instances need static operation durations (stochastic setup / "
+                        "travel / outage times are fine)");
+                return nullptr;
+            }
+    }
     if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); return nullptr; }
     jsl_batch* b = new jsl_batch();
     b->device = device;
@@ -224,6 +235,7 @@ jsl_batch_t* build_batch(const jsl_instance* t, int64_t n_inst, const int32_t* o
     lex_order("m", t->M, ml);
     { const int32_t* tmp = nullptr; rc |= upload(b, t->op_tool, &tmp); b->d_op_tool = (int32_t*)tmp; }
     if (t->stochastic) {
+        for (int o = 0; o < t->N; o++) b->ops_static = b->ops_static && t->tobj.kind[o] == JSL_TIME_STATIC;
         rc |= upload(b, t->tobj.kind, &I.tobj_kind);
         rc |= upload(b, t->tobj.base, &I.tobj_base);
         rc |= upload(b, t->tobj.param, &I.tobj_param);
@@ -389,7 +401,12 @@ jsl_batch_t* jsl_batch_create(jsl_instance_t* const* insts, int n_inst, int64_t 
                     u->m_outage_start == t->m_outage_start && u->m_outage_freq == t->m_outage_freq &&
                     u->m_outage_dur == t->m_outage_dur && u->t_outage_freq == t->t_outage_freq &&
                     u->t_outage_dur == t->t_outage_dur && u->default_tool == t->default_tool &&
-                    u->start_time == t->start_time && !u->stochastic;
+                    u->start_time == t->start_time && u->stochastic == t->stochastic &&
+                    (!t->stochastic || (u->tobj.kind == t->tobj.kind && u->tobj.param == t->tobj.param &&
+                                        std::equal(u->tobj.base.begin() + t->N, u->tobj.base.end(), t->tobj.base.begin() + t->N) &&
+                                        u->tobj.sample_row.size() == t->tobj.sample_row.size() &&
+                                        std::equal(u->tobj.sample_row.begin() + t->N, u->tobj.sample_row.end(), t->tobj.sample_row.begin() + t->N) &&
+                                        u->tobj.sample_table == t->tobj.sample_table));
         if (!same && i > 0) { set_err("instances of one batch must share everything but the operation tables"); return nullptr; }
         std::memcpy(&om[(size_t)i * t->N], u->op_machine.data(), t->N * sizeof(int32_t));
         std::memcpy(&od[(size_t)i * t->N], u->op_duration.data(), t->N * sizeof(int32_t));
@@ -468,7 +485,7 @@ int jsl_batch_randomize(jsl_batch_t* b, uint64_t seed, int min_duration, int max
                         void* stream) {
     if (!b) return JSL_E_INVALID;
     if (max_duration <= min_duration || min_duration < 0) { set_err("empty range for randrange()"); return JSL_E_INVALID; }
-    if (b->bd.tcur) { set_err("stochastic batches cannot be randomised"); return JSL_E_UNSUPPORTED; }
+    if (b->bd.tcur && !b->ops_static) { set_err("batches with stochastic operation durations cannot be randomised"); return JSL_E_UNSUPPORTED; }
     CK(cudaSetDevice(b->device));
     const InstDev& I = b->bd.inst;
     const int threads = 128;

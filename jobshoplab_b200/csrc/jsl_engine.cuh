@@ -750,10 +750,12 @@ JSL_D int tobj_update(Ctx& c, int32_t& draw_ctr, int idx, int static_value) {
 // (recorded, or uniform 0..30 like np.random.randint(0, 31), stochasticy_models.py:12) and its
 // construction-time sample table[row][seed] (:15).  Executed by all lanes of the env's warp.
 JSL_DN void stoch_init(const InstDev* I, int32_t* tcur, uint16_t* tseed, const int32_t* start_seeds,
-                       const int32_t* tape, uint64_t seed, uint64_t env) {
+                       const int32_t* tape, uint64_t seed, uint64_t env, const int32_t* op_dur) {
     const bool table_mode = tape == nullptr && I->sample_row != nullptr;
     wp_for_dyn(I->n_tobj, [&](int i) {
-        int v = I->tobj_init[i];
+        // a static operation duration is the env's own variant's (batches of several instances share every other
+        // time object; InstanceRandomizer makes durations deterministic, manipulators.py:133-137)
+        int v = (i < I->N && I->tobj_kind[i] == JSL_TIME_STATIC) ? op_dur[i] : I->tobj_init[i];
         if (table_mode) {
             const int row = I->sample_row[i];
             if (row >= 0) {
@@ -1625,7 +1627,7 @@ JSL_D void env_init(EnvS<JW, ST, CL>& s, Ctx& c) {
     }
     s.seq_ctr = EnvS<JW, ST, CL>::MJ;
     s.draw_ctr = 0;
-    if (ST) stoch_init(c.I, c.aux->tcur, c.aux->tseed, c.aux->start_seeds, c.aux->tape, c.aux->seed, c.aux->env_id);
+    if (ST) stoch_init(c.I, c.aux->tcur, c.aux->tseed, c.aux->start_seeds, c.aux->tape, c.aux->seed, c.aux->env_id, c.aux->op_dur);
     JSL_SYNCWARP();
 }
 
