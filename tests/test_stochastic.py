@@ -229,6 +229,11 @@ def test_stochastic_batches_of_several_instances():
     assert (per_env.rollout("fifo", reset_first=True).status.cpu().numpy() == abi.ST_DONE).all()
     per_env.close(); mixed.close()
     # stochastic operation durations still need one instance per batch
-    sc = next(G.Scenario("features", n) for n in G.names("features") if G.Scenario("features", n).lowered.op_spec.kind is not None)
+    N = li.n_ops
+    noisy = dataclasses.replace(li, op_spec=L.TimeSpec(np.full(N, L.TIME_GAUSSIAN, np.int32), np.asarray(li.op_duration, np.int32),
+                                                       np.full(N, 2.0, np.float32)))
+    one = engine.Batch(noisy, 4, seed=1)
+    assert (one.rollout("fifo", reset_first=True).status.cpu().numpy() == abi.ST_DONE).all()
+    one.close()
     with pytest.raises(InvalidValue):
-        engine.Batch([sc.lowered, sc.lowered], 4)
+        engine.Batch([noisy, noisy], 4)
