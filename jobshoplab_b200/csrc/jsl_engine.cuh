@@ -220,7 +220,7 @@ struct alignas(16) EnvAux {
     uint32_t act_bits;
     int32_t pad;
     int32_t* leg_log;            // transport-task log of this env (see LegLog) or nullptr
-    uint32_t loop_scratch[12];   // stochastic kernels: sm_step keeps its transition masks and loop guard here (see there)
+    uint32_t loop_scratch[14];   // stochastic kernels: sm_step keeps its transition masks and loop guard here (see there)
 };
 
 // per-call context: the few uniform values the hot loop keeps in registers
@@ -1397,7 +1397,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
     // transition masks of the current batch and the loop guard.  The stochastic kernels are short of registers (the
     // samplers are inlined into the handlers): there these live in the env's shared-memory slot instead of being
     // spilled to local memory around every handler; everywhere else they are plain registers.
-    struct LoopState { Mask<1> mm; Mask<JW> tm, tele; int guard; };
+    struct LoopState { Mask<1> mm; Mask<JW> tm, tele; int guard; bool f_action, f_first, f_eval, f_quiet, f_fresh, f_moved; };
     static_assert(sizeof(LoopState) <= sizeof(EnvAux::loop_scratch), "loop_scratch too small");
     LoopState* const ls = reinterpret_cast<LoopState*>(c.aux->loop_scratch);
     Mask<1> mm_r;
@@ -1411,14 +1411,22 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
 #pragma unroll
     for (int w = 0; w < JW; w++) { tm.w[w] = 0; tele.w[w] = 0; }
     // the candidate masks live in the state (c_p1 / c_idle / c_lr / c_li), not in registers
-    bool action_stage = has_action;
-    bool first = true;
-    bool evaluated = false;  // the time machine already ran for the current state
+    // (the loop's flags as well: in the stochastic kernels they were spilled and reloaded around every handler)
+    bool action_r, first_r, eval_r, quiet_r, fresh_r, moved_r;
+    bool& action_stage = ST ? ls->f_action : action_r;
+    bool& first = ST ? ls->f_first : first_r;
+    bool& evaluated = ST ? ls->f_eval : eval_r;      // the time machine already ran for the current state
+    bool& known_quiet = ST ? ls->f_quiet : quiet_r;
+    bool& poss_fresh = ST ? ls->f_fresh : fresh_r;   // s.c_* already describe the current state
+    bool& moved = ST ? ls->f_moved : moved_r;
+    action_stage = has_action;
+    first = true;
+    evaluated = false;
     // a step starts from the quiet state the previous call ended in (its loop only exits when nothing is due at
     // `now`), and the classic fast paths end in one: no timed transition can exist in the next batch
-    bool known_quiet = !has_action && time_machine == TM_FORCE;  // (a reset starts from the initial state instead)
-    bool poss_fresh = known_quiet;  // s.c_* already describe the current state
-    bool moved = CL != 2 || (!has_action && time_machine == TM_JUMP);  // a job may have reached an output buffer (reset: unknown)
+    known_quiet = !has_action && time_machine == TM_FORCE;  // (a reset starts from the initial state instead)
+    poss_fresh = known_quiet;
+    moved = CL != 2 || (!has_action && time_machine == TM_JUMP);  // a job may have reached an output buffer (reset: unknown)
     guard = 0;
     if (CL == 2 && has_action && act.kind == 0 && classic_start(s, c, act)) {
         action_stage = false; first = false; known_quiet = true; poss_fresh = true;
