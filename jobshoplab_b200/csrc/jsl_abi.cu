@@ -608,10 +608,14 @@ int jsl_rollout(jsl_batch_t* b, int policy, const uint8_t* action_tape, int64_t 
     if (b->rollout_ctas_per_sm == 0) {
         b->rollout_ctas_per_sm = b->JW == 1 ? rollout_occupancy_jw1(b->bd, smem)
                                  : b->JW == 2 ? rollout_occupancy_jw2(b->bd, smem) : rollout_occupancy_jw4(b->bd, smem);
+        if (const char* cap = std::getenv("JSL_ROLLOUT_CTAS_PER_SM")) {  // diagnostics: fewer resident CTAs (more L1 each)
+            const int n = std::atoi(cap);
+            if (n > 0 && n < b->rollout_ctas_per_sm) b->rollout_ctas_per_sm = n;
+        }
     }
     int64_t need = (b->bd.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     int64_t persistent = (int64_t)b->sm_count * b->rollout_ctas_per_sm;  // one full wave of resident CTAs
-    LaunchCfg lc = {(int)(need < persistent ? need : persistent), smem, (cudaStream_t)stream};
+    LaunchCfg lc = {(int)(need < persistent ? need : persistent), smem, (cudaStream_t)stream, b->rollout_ctas_per_sm};
     CK(cudaMemsetAsync(b->bd.work_counter, 0, sizeof(unsigned long long), (cudaStream_t)stream));
     JSL_DISPATCH(b, rollout, lc, policy, action_tape, tape_stride, max_steps, flags, out);
     return JSL_OK;

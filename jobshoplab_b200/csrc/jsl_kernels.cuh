@@ -343,6 +343,7 @@ k_digest(const __grid_constant__ BatchDev bd, int64_t env, int32_t* out, int cap
 struct LaunchCfg {
     int grid, smem;
     cudaStream_t stream;
+    int ctas_per_sm = 0;  // resident CTAs per SM the launch is sized for (0: unknown) -> shared-memory carve-out hint
 };
 
 template <int JW, bool ST, int CL>
@@ -367,6 +368,12 @@ template <int JW, bool ST, int CL>
 cudaError_t launch_rollout(const BatchDev& bd, const LaunchCfg& lc, int policy, const uint8_t* tape, int64_t tape_stride,
                            int max_steps, int flags, jsl_rollout_out out) {
     if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_rollout<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+    static int carved = 0;  // per instantiation: shared memory for the resident CTAs' slots, the rest stays L1 (local memory)
+    if (lc.ctas_per_sm > 0 && carved != lc.ctas_per_sm) {
+        int pct = (int)(((long long)lc.smem + 1024) * lc.ctas_per_sm * 100 / (228 * 1024)) + 1;
+        cudaFuncSetAttribute(k_rollout<JW, ST, CL>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+        carved = lc.ctas_per_sm;
+    }
     k_rollout<JW, ST, CL><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, policy, tape, tape_stride, max_steps, flags, out);
     return cudaGetLastError();
 }
