@@ -237,3 +237,31 @@ def test_stochastic_batches_of_several_instances():
     one.close()
     with pytest.raises(InvalidValue):
         engine.Batch([noisy, noisy], 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["full_feature_3x3", "ft20-t_features"])
+@pytest.mark.parametrize("policy", ["fifo", "spt", "random"])
+def test_gpu_makespan_distributions_three_policies_two_seeds(name, policy):
+    """the distribution check over 2 instances x 3 policies (always-accept, the spt rule on the
+    CURRENT duration samples, uniform-random actions) x 2 batch seeds, each against its own reference sample
+    (tests/golden/ks.npz, ks2.npz from oracle/gen_ks_more.py); two-sample KS, alpha 0.01 per comparison."""
+    pytest.importorskip("torch")
+    from jobshoplab_b200 import engine
+
+    fx = G.KsFixture(name)
+    if policy == "fifo":
+        ref = fx.makespan
+    else:
+        z = np.load(G.GOLDEN / "ks2.npz", allow_pickle=False)
+        ref = z[f"{name}/{policy}|makespan"]
+        assert z[f"{name}/{policy}|terminated"].all()
+    B = 20000
+    for seed in (5, 1234):
+        batch = engine.Batch(fx.lowered, B, seed=seed)
+        r = batch.rollout(policy, reset_first=True)
+        assert (r.status.cpu().numpy() == abi.ST_DONE).all()
+        mk = r.makespan.cpu().numpy()
+        p = stats.ks_2samp(mk, ref).pvalue
+        assert p > ALPHA, (name, policy, seed, p, mk.mean(), ref.mean(), mk.std(), ref.std())
+        batch.close()
