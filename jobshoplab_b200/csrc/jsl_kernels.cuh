@@ -178,18 +178,24 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c
     cand.kind = -1; cand.comp = -1; cand.new_state = 0; cand.job = -1;
     const bool have_cand = remaining > 0 && s.status <= JSL_ST_STEP_FAILED;
     if (have_cand) cand = current_candidate(s, c);
-    if (out.obs && s.status <= JSL_ST_STEP_FAILED) {
-        uint8_t* o = out.obs + (size_t)env * (uint32_t)obs_bytes;
-        if (c.C->obs_kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o, have_cand, cand);
-        else if (c.C->obs_kind == JSL_OBS_OPERATION_ARRAY) write_obs_oparray(s, c, o, have_cand, cand);
-        else if (c.C->obs_kind == JSL_OBS_TASSEL) write_obs_tassel(s, c, o);
-        else if (c.C->obs_kind == JSL_OBS_STATE) copy_fixed<Image<JW, CL>::BYTES>(o, &s);  // raw state for torch-side factories
-    }
+    const bool want_obs = out.obs && s.status <= JSL_ST_STEP_FAILED;
+    const int kind = c.C->obs_kind;
+    // Only the operation-array observation can raise (ZeroDivisionError, observations.py:604) and so change the
+    // status: it is written first.  For every other kind the scalars go out BEFORE the observation, so that reward
+    // and candidate are not live (= spilled) across the observation writer.
+    if (want_obs && kind == JSL_OBS_OPERATION_ARRAY)
+        write_obs_oparray(s, c, out.obs + (size_t)env * (uint32_t)obs_bytes, have_cand, cand);
     int status = s.status;
     if (c.raise && status <= JSL_ST_STEP_FAILED) status = c.raise;  // observation factory raised
     const bool show = remaining > 0 && status <= JSL_ST_TRUNCATED;
     write_scalars(s, out, env, reward, status, show ? cand.kind : -1, show ? cand.comp : -1, show ? cand.job : -1,
                   show ? (remaining > 32767 ? 32767 : remaining) : 0);
+    if (want_obs && kind != JSL_OBS_OPERATION_ARRAY) {
+        uint8_t* o = out.obs + (size_t)env * (uint32_t)obs_bytes;
+        if (kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o, have_cand, cand);
+        else if (kind == JSL_OBS_TASSEL) write_obs_tassel(s, c, o);
+        else if (kind == JSL_OBS_STATE) copy_fixed<Image<JW, CL>::BYTES>(o, &s);  // raw state for torch-side factories
+    }
 }
 
 template <int JW, bool ST, int CL>
