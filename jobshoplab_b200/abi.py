@@ -66,7 +66,11 @@ class Shape(C.Structure):
 class StepOut(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p),
                 ("truncated", C.c_void_p), ("status", C.c_void_p), ("time", C.c_void_p),
-                ("makespan", C.c_void_p), ("cand", C.c_void_p), ("record", C.c_void_p)]
+                ("makespan", C.c_void_p), ("cand", C.c_void_p), ("record", C.c_void_p), ("flags", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+STEP_OBS_PERSISTENT = 1  # JSL_STEP_OBS_PERSISTENT
 
 
 STEP_RECORD_BYTES = 32  # jsl_step_record: f64 reward | i32 time | i32 makespan | i16 cand[4] | u8 terminated, truncated, status

@@ -198,6 +198,28 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c
     }
 }
 
+// outputs of a step that left the state untouched (see k_step): the record, and of the observation only what a
+// changed candidate changes
+template <int JW, bool ST, int CL>
+__device__ __forceinline__ void write_step_delta(const EnvS<JW, ST, CL>& s, Ctx& c, const jsl_step_out& out, uint32_t env,
+                                                 double reward, int obs_bytes) {
+    const int remaining = s.n_possible - s.skip;
+    const Trans cand = current_candidate(s, c);
+    write_scalars(s, out, env, reward, s.status, cand.kind, cand.comp, cand.job, remaining > 32767 ? 32767 : remaining);
+    if (!out.obs) return;
+    uint8_t* o = out.obs + (size_t)env * (uint32_t)obs_bytes;
+    const int kind = c.C->obs_kind;
+    if (kind == JSL_OBS_BINARY_ACTION || kind == JSL_OBS_OPERATION_ARRAY) {
+        float tr[3];
+        cand_floats(s, c, tr, true, cand);
+        float* f = (float*)o + (kind == JSL_OBS_BINARY_ACTION ? 1 : 0);  // f32 current_time | current_transition[3] resp. transition first
+        if (JSL_LANE == 0) { f[0] = tr[0]; f[1] = tr[1]; f[2] = tr[2]; }
+    } else if (kind == JSL_OBS_STATE) {
+        constexpr int HDR = (int)offsetof(EnvS<JW>, j_start);
+        if (JSL_LANE < HDR / 16) ((int4*)o)[JSL_LANE] = ((const int4*)&s)[JSL_LANE];
+    }
+}
+
 template <int JW, bool ST, int CL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, jsl_step_out out, int obs_bytes) {
@@ -235,11 +257,36 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     uint8_t* g_state = bd.state + (size_t)env * IMG;
     uint8_t* g_outs = has_outs ? bd.outs + (size_t)env * (uint32_t)bd.outs_stride : nullptr;
     copy_fixed<IMG>(&s, g_state);
-    if (has_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
+    // A declined candidate with others left (middleware.py:355-368) never reaches the state machine: only bookkeeping
+    // scalars change.  When the caller guarantees that `out.obs` still holds this env's previous observation
+    // (JSL_STEP_OBS_PERSISTENT) such a step rewrites current_transition and the scalar header of the image -- no
+    // per-variant context, no observation pass, a seventh of the write-back.
+#ifdef JSL_USER_HEADER
+    const bool fast = false;  // a user reward hook may read anything
+#else
+    const bool fast = (out.flags & JSL_STEP_OBS_PERSISTENT) && action == 0 && s.status == JSL_ST_OK &&
+                      !(s.terminated | s.truncated) && s.n_possible - s.skip > 1;
+#endif
     Ctx c;
-    make_ctx<JW, ST, CL, true>(c, bd, env, slot);
+    if (fast) {
+        EnvAux* aux = (EnvAux*)(slot + Slot<JW>::AUX);
+        c.I = &bd.inst; c.C = &bd.cfg; c.aux = aux; c.raise = 0; c.now = 0; c.log = false;
+        aux->neg_inv_n = bd.inst.neg_inv_n;  // all make_reward reads of the context
+        __syncwarp();
+    } else {
+        if (has_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
+        make_ctx<JW, ST, CL, true>(c, bd, env, slot);
+    }
     double r = run_env_op(s, c, action);
     __syncwarp();
+    if (fast) {
+        write_step_delta(s, c, out, env, r, obs_bytes);
+        constexpr int HDR = (int)offsetof(EnvS<JW>, j_start);  // scalars + candidate masks: all a declined candidate touches
+        static_assert(HDR % 16 == 0 && HDR / 16 <= 32, "header is written back by one 16-byte store per lane");
+        __syncwarp();
+        if (JSL_LANE < HDR / 16) ((int4*)g_state)[JSL_LANE] = ((const int4*)&s)[JSL_LANE];
+        return;
+    }
     if (s.status >= JSL_ST_STEP_FAILED) {
         // success=False / an escaping exception: the reference keeps the OLD state (state.py:202-210);
         // re-read the HBM image and carry over only the bookkeeping scalars.
