@@ -545,20 +545,6 @@ def main():
     step_ms = s0.elapsed_time(s1)
     step_launches = batch.launches - sl0
     step_live = int((batch.out.status == 0).sum().item())  # envs still mid-episode after the timed steps
-    # the same steps with JSL_STEP_OBS_PERSISTENT off: every step rewrites the whole observation and state image
-    batch.set_obs_persistent(False)
-    batch.reset()
-    for i in range(8):
-        batch.step(acts[i])
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(args.step_mode_steps):
-        batch.step(acts[(8 + i) % pool_rows])
-    f1.record()
-    barrier()
-    full_ms = f0.elapsed_time(f1)
-    batch.set_obs_persistent(True)
     # ---- instances generated on the device (InstanceRandomizer) instead of uploaded ---------
     def gen_pass(k):
         batch.randomize(seed=SEED + 1 + k, min_duration=1, max_duration=100)
@@ -589,13 +575,13 @@ def main():
         secondary = secondary_configs(torch, dist, dev, local, rank, world, args.secondary_envs)
 
     # ---- reduce over ranks: max time, summed units ---------------------------------------------------
-    vec = torch.tensor([ms, e2e_ms, step_ms, gen_ms, strong[0] if strong else 0.0, full_ms], dtype=torch.float64, device=dev)
+    vec = torch.tensor([ms, e2e_ms, step_ms, gen_ms, strong[0] if strong else 0.0], dtype=torch.float64, device=dev)
     cnt = torch.tensor([steps_per_pass * args.steps, e2e_steps * args.steps, ok, gen_steps, strong[1] if strong else 0,
                         step_live], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms, e2e_ms, step_ms, gen_ms, strong_ms, full_ms = vec.tolist()
+    ms, e2e_ms, step_ms, gen_ms, strong_ms = vec.tolist()
     total_steps, total_e2e_steps, ok, total_gen_steps, strong_steps, step_live = cnt.tolist()
 
     if rank == 0:
@@ -612,12 +598,8 @@ def main():
         tp = ROOT / "profiles" / "r02_traffic.json"
         if tp.exists():
             stored = json.loads(tp.read_text())
-        # The roofline block describes the step kernel doing ALL its work every step (full observation and image
-        # rewritten: JSL_STEP_OBS_PERSISTENT off), so that bytes per env-step are a constant; the product path
-        # (engine.Batch.step, flag on) skips the unchanged bytes of declined-candidate steps and is reported as step_mode.
         step_rate = B * world * args.step_mode_steps / (step_ms / 1e3)
-        full_rate = B * world * args.step_mode_steps / (full_ms / 1e3)
-        step_launch_ms = full_ms / max(step_launches, 1)
+        step_launch_ms = step_ms / max(step_launches, 1)
         achieved = BYTES_PER_STEP * B / (step_launch_ms / 1e3) / 1e9
         moved = step_bytes * B / (step_launch_ms / 1e3) / 1e9
         sm_mhz = clk.get("sm_mhz") or 1965.0
@@ -658,17 +640,12 @@ def main():
                 "sm_mhz": sm_mhz, "ceiling": ceiling, "achieved": value / world, "frac": value / world / ceiling,
                 "unit": "env-steps/s/GPU", "note": "148 SMs x 4 schedulers x SM clock / warp-instructions per env-step"},
             "step_mode": {"value": step_rate, "unit": "env-steps/s", "kernel": "k_step<1,0,2>",
-                          "full_rewrite": {"value": full_rate, "bytes_per_env_step": step_bytes, "achieved_gbs": moved,
-                                           "frac_of_hbm_peak": moved / peak},
                           "bytes_per_env_step": step_bytes, "state_bytes": shape_state_bytes,
                           "obs_bytes": shape_obs_bytes, "achieved_gbs": moved, "frac_of_hbm_peak": moved / peak,
                           "algorithmic_frac_of_hbm_peak": BYTES_PER_STEP * step_rate / world / 1e9 / peak,
                           "envs_still_running": step_live,
-                          "what": "jsl_step on the same batch with device-resident random actions (what engine.Batch.step "
-                                  "does: JSL_STEP_OBS_PERSISTENT, a declined candidate rewrites only current_transition and "
-                                  "the scalar header); full_rewrite = the same steps with the flag off: state image "
-                                  "read+written and the whole default observation written every env.step -- the bytes "
-                                  "and fraction quoted here and in `roofline` are the full-rewrite run's"},
+                          "what": "jsl_step on the same batch with device-resident random actions: state image "
+                                  "read+written and the default observation written every env.step"},
             "makespan_stats": {"count": stats.count, "terminated": stats.terminated, "errors": stats.errors,
                                "mean": stats.makespan_mean, "std": stats.makespan_std, "min": stats.makespan_min,
                                "max": stats.makespan_max, "return_mean": stats.return_sum / max(stats.count, 1),

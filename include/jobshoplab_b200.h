@@ -208,15 +208,9 @@ typedef struct jsl_step_out {
     int16_t* cand;       /* [B][4]           next possible_transitions[0]: kind(0 m/1 t), comp, job, n_remaining */
     jsl_step_record* record; /* [B]          all of the above scalars in one record per env (preferred: when set, the
                                              six scalar arrays and cand are ignored) */
-    uint32_t flags;      /* JSL_STEP_* */
+    uint32_t flags;      /* reserved, must be 0 */
     uint32_t reserved;
 } jsl_step_out;
-/* `obs` is the buffer the previous jsl_reset / jsl_step of this batch wrote for the same envs, unmodified since.  An
- * env.step that declines a candidate while others remain (middleware.py:355-368: no state-machine call, the state
- * is untouched) then rewrites only what changed -- current_transition in the observation, the bookkeeping scalars in
- * the state image -- instead of the whole observation and image.  Results are identical; without the flag every
- * step rewrites everything. */
-#define JSL_STEP_OBS_PERSISTENT 1u
 
 /* Device output pointers of one jsl_rollout; any may be NULL. */
 typedef struct jsl_rollout_out {

@@ -70,9 +70,6 @@ class StepOut(C.Structure):
                 ("reserved", C.c_uint32)]
 
 
-STEP_OBS_PERSISTENT = 1  # JSL_STEP_OBS_PERSISTENT
-
-
 STEP_RECORD_BYTES = 32  # jsl_step_record: f64 reward | i32 time | i32 makespan | i16 cand[4] | u8 terminated, truncated, status
 
 

@@ -71,6 +71,28 @@ __device__ __forceinline__ void copy_fixed(void* dst, const void* src) {
     __syncwarp();
 }
 
+// the two halves of copy_fixed, for work that does not depend on the data to be placed between them
+template <int BYTES>
+struct Staged {
+    static constexpr int N = BYTES / 16, K = (N + 31) / 32;
+    int4 v[K];
+    __device__ __forceinline__ void load(const void* src) {
+        const int4* s = (const int4*)src;
+        const int lane = JSL_LANE;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (lane + 32 * k < N) v[k] = s[lane + 32 * k];
+    }
+    __device__ __forceinline__ void store(void* dst) {
+        int4* d = (int4*)dst;
+        const int lane = JSL_LANE;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (lane + 32 * k < N) d[lane + 32 * k] = v[k];
+        __syncwarp();
+    }
+};
+
 __device__ __forceinline__ void copy_in(void* dst, const void* src, int bytes) {
     const int4* s = (const int4*)src;
     int4* d = (int4*)dst;
@@ -178,46 +200,18 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c
     cand.kind = -1; cand.comp = -1; cand.new_state = 0; cand.job = -1;
     const bool have_cand = remaining > 0 && s.status <= JSL_ST_STEP_FAILED;
     if (have_cand) cand = current_candidate(s, c);
-    const bool want_obs = out.obs && s.status <= JSL_ST_STEP_FAILED;
-    const int kind = c.C->obs_kind;
-    // Only the operation-array observation can raise (ZeroDivisionError, observations.py:604) and so change the
-    // status: it is written first.  For every other kind the scalars go out BEFORE the observation, so that reward
-    // and candidate are not live (= spilled) across the observation writer.
-    if (want_obs && kind == JSL_OBS_OPERATION_ARRAY)
-        write_obs_oparray(s, c, out.obs + (size_t)env * (uint32_t)obs_bytes, have_cand, cand);
+    if (out.obs && s.status <= JSL_ST_STEP_FAILED) {
+        uint8_t* o = out.obs + (size_t)env * (uint32_t)obs_bytes;
+        if (c.C->obs_kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o, have_cand, cand);
+        else if (c.C->obs_kind == JSL_OBS_OPERATION_ARRAY) write_obs_oparray(s, c, o, have_cand, cand);
+        else if (c.C->obs_kind == JSL_OBS_TASSEL) write_obs_tassel(s, c, o);
+        else if (c.C->obs_kind == JSL_OBS_STATE) copy_fixed<Image<JW, CL>::BYTES>(o, &s);  // raw state for torch-side factories
+    }
     int status = s.status;
     if (c.raise && status <= JSL_ST_STEP_FAILED) status = c.raise;  // observation factory raised
     const bool show = remaining > 0 && status <= JSL_ST_TRUNCATED;
     write_scalars(s, out, env, reward, status, show ? cand.kind : -1, show ? cand.comp : -1, show ? cand.job : -1,
                   show ? (remaining > 32767 ? 32767 : remaining) : 0);
-    if (want_obs && kind != JSL_OBS_OPERATION_ARRAY) {
-        uint8_t* o = out.obs + (size_t)env * (uint32_t)obs_bytes;
-        if (kind == JSL_OBS_BINARY_ACTION) write_obs_binary(s, c, o, have_cand, cand);
-        else if (kind == JSL_OBS_TASSEL) write_obs_tassel(s, c, o);
-        else if (kind == JSL_OBS_STATE) copy_fixed<Image<JW, CL>::BYTES>(o, &s);  // raw state for torch-side factories
-    }
-}
-
-// outputs of a step that left the state untouched (see k_step): the record, and of the observation only what a
-// changed candidate changes
-template <int JW, bool ST, int CL>
-__device__ __forceinline__ void write_step_delta(const EnvS<JW, ST, CL>& s, Ctx& c, const jsl_step_out& out, uint32_t env,
-                                                 double reward, int obs_bytes) {
-    const int remaining = s.n_possible - s.skip;
-    const Trans cand = current_candidate(s, c);
-    write_scalars(s, out, env, reward, s.status, cand.kind, cand.comp, cand.job, remaining > 32767 ? 32767 : remaining);
-    if (!out.obs) return;
-    uint8_t* o = out.obs + (size_t)env * (uint32_t)obs_bytes;
-    const int kind = c.C->obs_kind;
-    if (kind == JSL_OBS_BINARY_ACTION || kind == JSL_OBS_OPERATION_ARRAY) {
-        float tr[3];
-        cand_floats(s, c, tr, true, cand);
-        float* f = (float*)o + (kind == JSL_OBS_BINARY_ACTION ? 1 : 0);  // f32 current_time | current_transition[3] resp. transition first
-        if (JSL_LANE == 0) { f[0] = tr[0]; f[1] = tr[1]; f[2] = tr[2]; }
-    } else if (kind == JSL_OBS_STATE) {
-        constexpr int HDR = (int)offsetof(EnvS<JW>, j_start);
-        if (JSL_LANE < HDR / 16) ((int4*)o)[JSL_LANE] = ((const int4*)&s)[JSL_LANE];
-    }
 }
 
 template <int JW, bool ST, int CL>
@@ -257,36 +251,11 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     uint8_t* g_state = bd.state + (size_t)env * IMG;
     uint8_t* g_outs = has_outs ? bd.outs + (size_t)env * (uint32_t)bd.outs_stride : nullptr;
     copy_fixed<IMG>(&s, g_state);
-    // A declined candidate with others left (middleware.py:355-368) never reaches the state machine: only bookkeeping
-    // scalars change.  When the caller guarantees that `out.obs` still holds this env's previous observation
-    // (JSL_STEP_OBS_PERSISTENT) such a step rewrites current_transition and the scalar header of the image -- no
-    // per-variant context, no observation pass, a seventh of the write-back.
-#ifdef JSL_USER_HEADER
-    const bool fast = false;  // a user reward hook may read anything
-#else
-    const bool fast = (out.flags & JSL_STEP_OBS_PERSISTENT) && action == 0 && s.status == JSL_ST_OK &&
-                      !(s.terminated | s.truncated) && s.n_possible - s.skip > 1;
-#endif
+    if (has_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
     Ctx c;
-    if (fast) {
-        EnvAux* aux = (EnvAux*)(slot + Slot<JW>::AUX);
-        c.I = &bd.inst; c.C = &bd.cfg; c.aux = aux; c.raise = 0; c.now = 0; c.log = false;
-        aux->neg_inv_n = bd.inst.neg_inv_n;  // all make_reward reads of the context
-        __syncwarp();
-    } else {
-        if (has_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
-        make_ctx<JW, ST, CL, true>(c, bd, env, slot);
-    }
+    make_ctx<JW, ST, CL, true>(c, bd, env, slot);
     double r = run_env_op(s, c, action);
     __syncwarp();
-    if (fast) {
-        write_step_delta(s, c, out, env, r, obs_bytes);
-        constexpr int HDR = (int)offsetof(EnvS<JW>, j_start);  // scalars + candidate masks: all a declined candidate touches
-        static_assert(HDR % 16 == 0 && HDR / 16 <= 32, "header is written back by one 16-byte store per lane");
-        __syncwarp();
-        if (JSL_LANE < HDR / 16) ((int4*)g_state)[JSL_LANE] = ((const int4*)&s)[JSL_LANE];
-        return;
-    }
     if (s.status >= JSL_ST_STEP_FAILED) {
         // success=False / an escaping exception: the reference keeps the OLD state (state.py:202-210);
         // re-read the HBM image and carry over only the bookkeeping scalars.

@@ -179,20 +179,11 @@ class Batch:
             status=torch.zeros(self.B, dtype=torch.uint8, device=dev),
             no_op_count=torch.zeros(self.B, dtype=torch.int32, device=dev),
         )
-        self.set_obs_persistent(True)
+        self._step_out = abi.StepOut(self.out.obs.data_ptr() if self.shape.obs_bytes else None, None, None, None, None,
+                                     None, None, None, rec.data_ptr(), 0, 0)
         r = self.rout
         self._roll_out = abi.RolloutOut(r.makespan.data_ptr(), r.n_steps.data_ptr(), r.ret.data_ptr(),
                                         r.status.data_ptr(), r.no_op_count.data_ptr())
-
-    def set_obs_persistent(self, on: bool = True):
-        """JSL_STEP_OBS_PERSISTENT: the batch owns its observation buffer (`out.obs`) and hands the same one to every
-        reset / step, so a step that only declines a candidate rewrites just `current_transition` and the state
-        scalars.  Treat `out.obs` (and the views of unpack_obs) as read-only -- clone before modifying in place -- or
-        switch this off to have every step rewrite the whole observation and state image."""
-        self.obs_persistent = bool(on)
-        self._step_out = abi.StepOut(self.out.obs.data_ptr() if self.shape.obs_bytes else None, None, None, None, None,
-                                     None, None, None, self.record.data_ptr(),
-                                     abi.STEP_OBS_PERSISTENT if on else 0, 0)
 
     def close(self):
         if getattr(self, "h", None):

@@ -266,35 +266,3 @@ def test_uploaded_tables_are_validated_on_the_device():
         batch.check()
     batch.close()
 
-
-def test_declined_candidate_fast_path_equals_full_rewrite():
-    """JSL_STEP_OBS_PERSISTENT (engine.Batch's default): a step that only declines a candidate rewrites
-    current_transition and the scalar header.  Observation, record and every later state must equal those of a batch
-    stepped with the flag off -- for every observation kind, under a skip-heavy random tape."""
-    eng = _engine()
-    rng = np.random.default_rng(11)
-    for group, name, kw in (("classic", "ta01/random0", {}), ("transport", "ft10-t/random0", {}),
-                            ("classic", "ft10/random0", {"obs_kind": abi.OBS_OPERATION_ARRAY}),
-                            ("classic", "ft06/random0", {"obs_kind": abi.OBS_TASSEL}),
-                            ("transport", "la01-t/random0", {"obs_kind": abi.OBS_STATE})):
-        sc = G.Scenario(group, name)
-        B = 16
-        cfg = dict(sc.cfg); cfg.update(kw)
-        a, b = eng.Batch(sc.lowered, B, **cfg), eng.Batch(sc.lowered, B, **cfg)
-        assert a.obs_persistent
-        b.set_obs_persistent(False)
-        a.reset(); b.reset()
-        steps = 0
-        while steps < 3000:
-            acts = torch.from_numpy((rng.random(B) < 0.35).astype(np.uint8)).cuda()  # mostly declines
-            oa, ob = a.step(acts), b.step(acts)
-            assert torch.equal(a.record, b.record), (name, steps)
-            assert torch.equal(oa.obs, ob.obs), (name, steps, "obs")
-            steps += 1
-            if steps % 97 == 0:
-                assert np.array_equal(a.get_state(steps % B), b.get_state(steps % B))
-                if bool((oa.status != 0).all()):
-                    break
-        r1, r2 = a.rollout("fifo"), b.rollout("fifo")  # the HBM images the two paths left behind are equivalent
-        assert torch.equal(r1.makespan, r2.makespan) and torch.equal(r1.n_steps, r2.n_steps) and torch.equal(r1.ret, r2.ret)
-        a.close(); b.close()
