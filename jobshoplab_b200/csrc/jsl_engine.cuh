@@ -57,6 +57,17 @@
 
 namespace jsl {
 
+// chain fusion (apply_machine / apply_transport): always on in the kernels; the CPU debug build can switch the
+// individual fusions off (bit mask, tests/hostsim: JSL_FUSE) to bisect against the oracle
+#ifdef JSL_HOST_SIM
+static int g_fuse = -1;
+static long g_fused[5] = {0, 0, 0, 0, 0};  // how often each fusion fired (coverage of the fuzz / golden runs)
+#define JSL_FUSE_ON(bit) ((g_fuse >> (bit)) & 1)
+#define JSL_FUSED(bit) (g_fused[bit]++)
+#else
+#define JSL_FUSE_ON(bit) true
+#define JSL_FUSED(bit) ((void)0)
+#endif
 #ifdef JSL_HOST_SIM
 static long g_invariant_checks = 0, g_invariant_violations = 0;  // CPU debug build only
 static long g_fast_start = 0, g_fast_complete = 0, g_general_batches = 0;
@@ -832,26 +843,31 @@ JSL_D bool machine_valid(const EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int j
 }
 
 // handler.py:414-457 + manipulate.py:378-444
+// Returns true when the SETUP -> WORKING transition that the next batch would create can be applied right away
+// (chain fusion, see apply_machine): a static setup time of zero.
 template <int JW, bool ST, int CL>
-JSL_D void machine_idle_to_setup(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
+JSL_D bool machine_idle_to_setup(EnvS<JW, ST, CL>& s, Ctx& c, int m, int j) {
     const InstDev& I = *c.I;
-    if (j == NONE8) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
-    if (s.j_loc[j] != 3 * m) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+    if (j == NONE8) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, false);
+    if (s.j_loc[j] != 3 * m) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, false);
     int o = I.job_op_start[j] + s.j_k[j];
     int tool = (c.aux->op_mt[o] >> 16) & 0xffff;
     int setup = 0;
+    bool drawn = false;
     if (JSL_UNLIKELY(JSL_LVL_OUT(CL) && (I.setup || ST))) {
         const int si = (m * I.NT + s.m_tool[m]) * I.NT + tool;
         setup = setup_time_cur<ST, CL>(c, si);
-        if (setup == JSL_NO_TIME && !(ST && I.tobj_kind[I.off_setup + si] != JSL_TIME_STATIC)) JSL_RAISE(c, JSL_ST_OTHER_INVALID);
+        if (ST) drawn = I.tobj_kind[I.off_setup + si] != JSL_TIME_STATIC;
+        if (setup == JSL_NO_TIME && !drawn) JSL_RAISE_V(c, JSL_ST_OTHER_INVALID, false);
         setup = tobj_update<ST>(c, s.draw_ctr, I.off_setup + si, setup);
-        if (JSL_UNLIKELY(c.raise)) return;
+        if (JSL_UNLIKELY(c.raise)) return false;
     }
-    if (s.m_job[m] != NONE8) JSL_RAISE(c, JSL_ST_BUFFER_FULL);
+    if (s.m_job[m] != NONE8) JSL_RAISE_V(c, JSL_ST_BUFFER_FULL, false);
     s.j_proc[j] = 1; s.j_start[j] = c.now; s.j_end[j] = c.now + setup;
     s.j_loc[j] = (uint16_t)(3 * m + 2);
     s.m_job[m] = (uint8_t)j;
     s.m_state[m] = JSL_M_SETUP; s.m_occ[m] = c.now + setup; s.m_tool[m] = (uint8_t)tool;
+    return setup == 0 && !drawn;
 }
 // handler.py:460-503 + manipulate.py:225-276
 template <int JW, bool ST, int CL>
@@ -911,16 +927,35 @@ JSL_D void machine_outage_to_idle(EnvS<JW, ST, CL>& s, Ctx& c, int m) {
 
 // process one machine transition (validate + handle); false = validation error
 template <int JW, bool ST, int CL>
-JSL_D bool apply_machine(EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int job) {
+JSL_D bool apply_machine(EnvS<JW, ST, CL>& s, Ctx& c, int m, int to, int job, bool fuse) {
     // every machine transition is created from that machine's own current state (timed) or from the candidate
     // masks of the unchanged state (action); only the TimeDependency hand-me-downs of non-FLEX postbuffers
     // (handler.py:632) can put two transitions of one component into a batch, so the state-graph check
     // (validate.py:30-82) can only fail there
     if (JSL_LVL_BUF(CL) && !c.I->flex_post && !machine_valid(s, c, m, to, job)) return false;
     if (JSL_UNLIKELY(c.raise)) return true;
+    // Chain fusion.  The reference applies the follow-up of a zero-duration state in the NEXT batch of the same `now`
+    // (state.py:236-267: one loop iteration per batch).  A follow-up may be applied here, in the batch that creates it,
+    // when (1) nothing that runs in between observes the intermediate state and (2) the component then has nothing more
+    // to do at this `now` -- otherwise the rest of its same-time cascade would run one batch early and could overtake
+    // another component's (the order of two drop-offs into one buffer is state).  The state every env.step ends in is
+    // then the same, the loop runs fewer batches.  For machines:
+    //   IDLE -> SETUP -> WORKING   a static setup time of zero and a static duration > 0.  In between the reference only
+    //                              has end_time = now instead of now + duration, which an AGV reads as its waiting time
+    //                              and re-reads one batch later.
+    // (WORKING -> OUTAGE -> IDLE is NOT fused: the job would reach the postbuffer, and its AGV leave, a batch early.)
+    // Never for the agent's own action (`fuse` false): the time machine and the teleports that follow it
+    // (state.py:214-232) read the intermediate occupied_till / end_time.
     int from = s.m_state[m];
-    if (from == JSL_M_IDLE) machine_idle_to_setup(s, c, m, job);
-    else if (from == JSL_M_SETUP) machine_setup_to_working(s, c, m, job);
+    if (from == JSL_M_IDLE) {
+        bool chain = machine_idle_to_setup(s, c, m, job);
+        if (!chain || !fuse || !JSL_FUSE_ON(0) || JSL_UNLIKELY(c.raise)) return true;
+        const int o = c.I->job_op_start[job] + s.j_k[job];
+        if (c.aux->op_dur[o] <= 0 || (ST && c.I->tobj_kind[o] != JSL_TIME_STATIC)) return true;
+        from = JSL_M_SETUP;
+        JSL_FUSED(0);
+    }
+    if (from == JSL_M_SETUP) machine_setup_to_working(s, c, m, job);
     else if (from == JSL_M_WORKING) machine_working_to_outage(s, c, m, job);
     else machine_outage_to_idle(s, c, m);
     return true;
@@ -1112,7 +1147,10 @@ JSL_D void agv_transit_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
                                       o.to_active + t * MAX_OUT, o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
         if (JSL_UNLIKELY(c.raise)) return;
     }
-    s.t_state[t] = JSL_T_OUTAGE;
+    // (chain fusion: without transport outages the OUTAGE state lasts zero time and OUTAGE -> IDLE, whose only effect is
+    // the state itself, would follow in the next batch of the same `now`; no handler reads the state of an AGV without a job)
+    s.t_state[t] = ((JSL_LVL_OUT(CL) && I.has_t_out) || !JSL_FUSE_ON(2)) ? JSL_T_OUTAGE : JSL_T_IDLE;
+    if (s.t_state[t] == JSL_T_IDLE) JSL_FUSED(2);
     s.t_occkind[t] = OCC_TIME; s.t_occ[t] = c.now + occupied_for;
     s.t_lockind[t] = 0; s.t_loc0[t] = (uint8_t)dest;
     s.j_agv[j] = NONE8;
@@ -1122,12 +1160,48 @@ JSL_D void agv_transit_to_outage(EnvS<JW, ST, CL>& s, Ctx& c, int t, int j) {
 
 // process one transport transition; false = validation error
 template <int JW, bool ST, int CL>
-JSL_D bool apply_transport(EnvS<JW, ST, CL>& s, Ctx& c, int t, int to, int job) {
+JSL_D bool apply_transport(EnvS<JW, ST, CL>& s, Ctx& c, int t, int to, int job, bool fuse) {
     if (JSL_LVL_BUF(CL) && !c.I->flex_post && !transport_valid(s, t, to)) return false;
+    // Chain fusion (rules: apply_machine), only with FLEX postbuffers / standalone buffers -- otherwise another AGV's
+    // waiting time is derived from this one's occupied_till and queue positions matter:
+    //   IDLE -> PICKUP -> WAITINGPICKUP   the AGV already stands at the pickup place (travel time 0) and its job is still
+    //                                     being processed beyond `now`: it ends up waiting for the future
+    //   PICKUP -> WAITINGPICKUP -> TRANSIT  the job is ready on arrival (in a postbuffer / standalone buffer) and the
+    //                                     trip takes a static time > 0; needs unbounded capacities (the job leaves its
+    //                                     buffer one batch early)
+    //   TRANSIT -> OUTAGE -> IDLE         no transport outages (in agv_transit_to_outage)
+    const InstDev& I = *c.I;
+    const bool flex = fuse && (!JSL_LVL_BUF(CL) || I.flex_post != 0);
     int from = s.t_state[t];
-    if (from == JSL_T_IDLE && to == JSL_T_WORKING) agv_idle_to_working(s, c, t, job);
-    else if (from == JSL_T_PICKUP && to == JSL_T_WAITINGPICKUP) agv_to_waitingpickup(s, c, t, job);
-    else if ((from == JSL_T_WAITINGPICKUP || from == JSL_T_PICKUP) && to == JSL_T_TRANSIT) agv_to_transit(s, c, t, job);
+    if (from == JSL_T_IDLE && to == JSL_T_WORKING) {
+        agv_idle_to_working(s, c, t, job);
+        if (!flex || !JSL_FUSE_ON(3) || JSL_UNLIKELY(c.raise) || s.t_occ[t] != c.now) return true;
+        const int b = s.j_loc[job];
+        const bool in_machine = b < 3 * I.M && (b % 3) != 1;  // prebuffer or machine buffer: waits for the op's end
+        if (!(in_machine && s.j_proc[job] && s.j_end[job] > c.now)) return true;
+        from = JSL_T_PICKUP; to = JSL_T_WAITINGPICKUP;
+        JSL_FUSED(3);
+    }
+    if ((from == JSL_T_PICKUP || from == JSL_T_WAITINGPICKUP) && to == JSL_T_WAITINGPICKUP) {  // handler.py:642-702, :989-1030
+        const bool arriving = from == JSL_T_PICKUP;
+        agv_to_waitingpickup(s, c, t, job);
+        if (!flex || !arriving || !JSL_FUSE_ON(4) || JSL_UNLIKELY(c.raise)) return true;
+        if (JSL_LVL_BUF(CL) && !I.caps_inf) return true;
+        if (s.t_occkind[t] != OCC_TIME || s.t_occ[t] != c.now) return true;
+        const int b = s.j_loc[job];
+        if (!(is_standalone(I, b) || (b < 3 * I.M && (b % 3) == 1))) return true;  // not ready: keeps waiting
+        {   // the trip must end strictly later, by a time that is not redrawn (agv_to_transit resamples stochastic ones)
+            const int src = place_of_buf(I, b);
+            const int nip = next_idle_place(s, c, job);
+            const int dst = nip < 0 ? (I.out_buf < 0 ? -1 : I.M + (I.out_buf - 3 * I.M - I.T)) : (int)s.j_mach[job];
+            if (src < 0 || dst < 0) return true;
+            if (ST && I.tobj_kind[I.off_travel + src * I.NP + dst] != JSL_TIME_STATIC) return true;
+            if (travel_time_cur<ST, CL>(c, src, dst) <= 0) return true;
+        }
+        from = JSL_T_WAITINGPICKUP; to = JSL_T_TRANSIT;
+        JSL_FUSED(4);
+    }
+    if ((from == JSL_T_WAITINGPICKUP || from == JSL_T_PICKUP) && to == JSL_T_TRANSIT) agv_to_transit(s, c, t, job);
     else if ((from == JSL_T_WORKING || from == JSL_T_TRANSIT) && to == JSL_T_OUTAGE) agv_transit_to_outage(s, c, t, job);
     else if (from == JSL_T_OUTAGE && to == JSL_T_IDLE) {  // handler.py:961-986
         if (JSL_LVL_OUT(CL) && c.I->has_t_out) {
@@ -1135,8 +1209,7 @@ JSL_D bool apply_transport(EnvS<JW, ST, CL>& s, Ctx& c, int t, int to, int job) 
             release_outages(c.I->n_t_out, o.to_active + t * MAX_OUT, o.to_a + t * MAX_OUT, o.to_b + t * MAX_OUT);
         }
         s.t_state[t] = JSL_T_IDLE;
-    } else if (from == JSL_T_WAITINGPICKUP && to == JSL_T_WAITINGPICKUP) agv_to_waitingpickup(s, c, t, job);
-    else { if (!c.raise) c.raise = JSL_ST_OTHER_INVALID; }  // NotImplementedError, handler.py:1125
+    } else { if (!c.raise) c.raise = JSL_ST_OTHER_INVALID; }  // NotImplementedError, handler.py:1125
     return true;
 }
 
@@ -1553,7 +1626,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
         moved = true;
         while (mm.any()) {
             int m = mm.pop_first();
-            bool ok = apply_machine(s, c, m, s.x_mkind[m], s.x_mjob[m]);
+            bool ok = apply_machine(s, c, m, s.x_mkind[m], s.x_mjob[m], !action_stage);
             if (JSL_UNLIKELY(c.raise)) return true;
             if (JSL_UNLIKELY(!ok)) return false;
         }
@@ -1562,7 +1635,7 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
             Mask<JW> cur = ph == 0 ? tm : tele;
             while (cur.any()) {
                 int t = cur.pop_first();
-                bool ok = apply_transport(s, c, JSL_LVL_BUF(CL) ? (int)s.x_tcomp[t] : t, s.x_tkind[t], s.x_tjob[t]);
+                bool ok = apply_transport(s, c, JSL_LVL_BUF(CL) ? (int)s.x_tcomp[t] : t, s.x_tkind[t], s.x_tjob[t], !action_stage);
                 if (JSL_UNLIKELY(c.raise)) return true;
                 if (JSL_UNLIKELY(!ok)) return false;
             }

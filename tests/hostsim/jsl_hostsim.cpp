@@ -234,6 +234,8 @@ void* jsh_create(const jsl_instance_desc* d, const jsl_env_cfg* cfg, uint64_t se
     return s;
 }
 void jsh_destroy(void* h) { delete (Sim*)h; }
+void jsh_set_fuse(int mask) { g_fuse = mask; }
+void jsh_fused(long* o) { for (int i = 0; i < 5; i++) o[i] = g_fused[i]; }
 void jsh_set_tape(void* h, const int32_t* t, int n) { Sim* s = (Sim*)h; s->tape.assign(t, t + n); }
 void jsh_invariants(long* o) { o[0] = g_invariant_checks; o[1] = g_invariant_violations; }
 void jsh_randomize_variant(uint64_t seed, uint64_t variant, int J, const int32_t* job_op_start, int min_d, int max_d,
