@@ -75,6 +75,21 @@ def randomize_variant(seed, variant, job_op_start, op_machine, op_tool, min_d, m
     return mt & 0xffff, mt >> 16, dur, work, int(lm[0]), int(lm[1])
 
 
+def fused():
+    """How often each chain fusion of the general event loop fired so far (jsl_engine.cuh apply_machine /
+    apply_transport): [IDLE->SETUP->WORKING, (unused), TRANSIT->OUTAGE->IDLE, IDLE->PICKUP->WAITING,
+    PICKUP->WAITING->TRANSIT]."""
+    o = (C.c_long * 5)()
+    lib().jsh_fused(o)
+    return list(o)
+
+
+def set_fuse(mask: int):
+    """Debug switch of the CPU build: bit i enables fusion i (-1: all, the kernels' behaviour; 0: one reference batch per
+    loop iteration)."""
+    lib().jsh_set_fuse(int(mask))
+
+
 def fast_paths():
     """(classic_start hits, classic_complete hits, batches of classic instances that took the general loop)."""
     o = (C.c_long * 3)()

@@ -93,10 +93,20 @@ def test_engine_source_differential_fuzz():
     oracle, step by step -- tests/fuzz_engine.py."""
     import fuzz_engine
 
+    from hostsim.hostsim_py import fused, invariants, set_fuse
+    before = fused()
     fuzz_engine.main(500, 3)
-    from hostsim.hostsim_py import invariants
     checks, violations = invariants()
     assert checks > 1000 and violations == 0
+    # the chain fusions of the general event loop all fired in this run (they are what the kernels execute) ...
+    fired = [b - a for a, b in zip(before, fused())]
+    assert fired[0] > 100 and fired[2] > 1000 and fired[3] > 100 and fired[4] > 100, fired
+    # ... and with every fusion off (one reference batch per loop iteration) the engine agrees with the oracle as well
+    set_fuse(0)
+    try:
+        fuzz_engine.main(150, 4)
+    finally:
+        set_fuse(-1)
 
 
 def test_engine_source_wide_instances():
