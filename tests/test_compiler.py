@@ -82,3 +82,53 @@ def test_repositories(tmp_path):
     assert np.array_equal(a.travel_time, b.travel_time) and a.travel_time.max() == 9
     with pytest.raises(FileNotFoundError):
         C.SpecRepository(tmp_path / "missing")
+
+
+def test_lowering_of_reference_objects():
+    """jobshoplab_b200.ref_lowering (what the seam-2 middleware does with the `(InstanceConfig, State)` the reference
+    env hands it) == the lowering stored in the goldens, for every distinct golden source incl. stochastic ones
+    (time behaviours, numpy start seeds).  Needs the reference (oracle/_ref or /root/reference)."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
+    from oracle import ref_bench
+    if not ref_bench.available():
+        pytest.skip("the reference is not installed (python oracle/make_ref.py)")
+    import ref_harness as rh
+    from jobshoplab_b200 import ref_lowering as RL
+    import dataclasses
+
+    seen, n = set(), 0
+    for group in ("classic", "transport", "buffers", "features"):
+        for name in G.names(group)[::4]:
+            sc = G.Scenario(group, name)
+            if hash(sc.source_text) in seen:
+                continue
+            seen.add(hash(sc.source_text))
+            env = rh.make_env("spec" if sc.kind == "spec" else "dslstr", _as_file(sc) if sc.kind == "spec" else sc.source_text)
+            inst, init = env.jsl_rc.inner.compile()
+            a, b = rh.lower_reference(inst, init), RL.lower_reference(inst, init)
+            for f in dataclasses.fields(a):
+                x, y = getattr(a, f.name), getattr(b, f.name)
+                if f.name.endswith("_spec"):
+                    for k in ("kind", "base", "param"):
+                        xx, yy = getattr(x, k), getattr(y, k)
+                        assert (xx is None) == (yy is None) and (xx is None or np.array_equal(xx, yy)), (name, f.name, k)
+                elif isinstance(x, (np.ndarray, list)):
+                    assert np.array_equal(np.asarray(x), np.asarray(y)), (name, f.name)
+                else:
+                    assert x == y, (name, f.name)
+            assert np.array_equal(a.start_seeds, b.start_seeds), name
+            n += 1
+    assert n >= 20
+
+
+def _as_file(sc):
+    import tempfile
+    from pathlib import Path
+
+    d = Path(tempfile.mkdtemp())
+    p = d / "inst"
+    p.write_text(sc.source_text)
+    return p
