@@ -29,4 +29,22 @@ for group, name in (("classic", "ft06/random0"), ("buffers", "la01-t/lifo2/noear
     torch.cuda.synchronize()
     print(group, name, "steps", n, "digest len", len(d), "rollout steps", r.n_steps.cpu().tolist()[:3], "status", r.status.cpu().tolist()[:3])
     batch.close()
+    # the throughput build as well, with the raw-state observation (image-sized observation copies) and, for the
+    # classic instance, uploaded / device-randomised variant tables
+    fast = engine.Batch(sc.lowered, B, obs_kind=4, **{k: v for k, v in sc.cfg.items() if k != "obs_kind"})
+    fast.reset()
+    for i in range(min(n, 30)):
+        fast.step(acts[:, i].contiguous())
+    fast.rollout("fifo", max_steps=200)
+    if sc.lowered.is_deterministic and group == "classic":
+        om = np.tile(sc.lowered.op_machine, (B, 1)).astype(np.int32); od = np.tile(sc.lowered.op_duration, (B, 1)).astype(np.int32)
+        lb = np.full(B, sc.lowered.lower_bound, np.int32); mat = np.full(B, sc.lowered.max_allowed_time, np.int32)
+        vb = engine.Batch(sc.lowered, B, variants=(om, od, lb, mat))
+        vb.load_variants(om, od, lb, mat)
+        vb.randomize(seed=3)
+        vb.rollout("random", reset_first=True)
+        vb.check()
+        vb.close()
+    torch.cuda.synchronize()
+    fast.close()
 print("sanitize workload done")
