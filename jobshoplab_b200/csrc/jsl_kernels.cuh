@@ -25,6 +25,9 @@ constexpr int WARPS_PER_CTA = JSL_WARPS_PER_CTA;
 #ifndef JSL_STEP_MIN_CTAS
 #define JSL_STEP_MIN_CTAS 24
 #endif
+#ifndef JSL_ROLLOUT_MIN_CTAS_ST
+#define JSL_ROLLOUT_MIN_CTAS_ST 32  // the stochastic rollout kernels (24 / 20 = 40 / 48 registers were measured slower)
+#endif
 #ifndef JSL_ROLLOUT_MIN_CTAS_GENERAL
 #define JSL_ROLLOUT_MIN_CTAS_GENERAL 32  // same budget for the general (non-classic) rollout kernels
 #endif
@@ -280,7 +283,7 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
 }
 
 template <int JW, bool ST, int CL>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CL ? JSL_ROLLOUT_MIN_CTAS : JSL_ROLLOUT_MIN_CTAS_GENERAL)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, ST ? JSL_ROLLOUT_MIN_CTAS_ST : CL ? JSL_ROLLOUT_MIN_CTAS : JSL_ROLLOUT_MIN_CTAS_GENERAL)
 k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __restrict__ tape, int64_t tape_stride,
           int max_steps, int flags, jsl_rollout_out out) {
     extern __shared__ __align__(16) uint8_t smem[];

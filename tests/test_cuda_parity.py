@@ -266,3 +266,41 @@ def test_uploaded_tables_are_validated_on_the_device():
         batch.check()
     batch.close()
 
+
+
+def test_maximum_sizes_and_limits():
+    """The engine's limits: 128 jobs x 32 machines (4 lane words, every machine bit of the masks in
+    use), 128 AGVs, and a ragged variant with 1..32 operations per job run bit-exactly against the oracle under three policies;
+    one machine more is refused with an error, not a crash."""
+    from jobshoplab_b200 import compiler as C
+    from jobshoplab_b200.exceptions import InvalidValue
+    from oracle import oracle_py as op
+
+    eng = _engine()
+    rng = np.random.default_rng(4)
+    J, M = 128, 32
+    lines = [f"{J} {M}"]
+    for j in range(J):
+        lines.append(" ".join(f"{m} {int(rng.integers(1, 50))}" for m in rng.permutation(M)))
+    li = C.compile_spec_text("\n".join(lines) + "\n")
+    assert (li.n_jobs, li.n_machines, li.n_transports) == (128, 32, 128)
+    # ragged variant: job j keeps its first 1 + (7 j mod 32) operations
+    import dataclasses
+    keep = [1 + (7 * j) % 32 for j in range(J)]
+    jos = np.concatenate([[0], np.cumsum(keep)]).astype(np.int32)
+    sel = np.concatenate([np.arange(j * M, j * M + keep[j]) for j in range(J)])
+    ragged = dataclasses.replace(li, job_op_start=jos, op_machine=li.op_machine[sel], op_tool=li.op_tool[sel],
+                                 op_duration=li.op_duration[sel], lower_bound=1, max_allowed_time=int(li.op_duration[sel].sum()))
+    for inst in (li, ragged):
+        batch = eng.Batch(inst, 3, seed=9)
+        for pol, code in (("fifo", abi.POLICY_FIFO), ("spt", abi.POLICY_SPT), ("random", abi.POLICY_RANDOM)):
+            r = batch.rollout(pol, reset_first=True)
+            o = op.OracleEnv(inst)
+            o.rollout(code, seed=9, env_idx=1)
+            assert int(r.status[1]) == abi.ST_DONE and o.terminated
+            assert (int(r.makespan[1]), int(r.n_steps[1]), float(r.ret[1])) == (o.time, o.n_steps, o.ret), pol
+        batch.close()
+    lines = [f"4 33"] + [" ".join(f"{m} 3" for m in range(33)) for _ in range(4)]
+    with pytest.raises(InvalidValue) as e:
+        eng.Batch(C.compile_spec_text("\n".join(lines) + "\n"), 2)
+    assert "32 machines" in str(e.value)
