@@ -256,6 +256,10 @@ int jsl_batch_load_variants(jsl_batch_t*, const int32_t* op_machine, const int32
  * after the staging copies).  One staging area per batch: stage again only after the commit has run. */
 int jsl_batch_stage_variants(jsl_batch_t*, const int32_t* op_machine, const int32_t* op_duration,
                              const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream);
+/* `stage` with narrow host tables -- uint8 machines, uint16 durations (3 instead of 8 bytes per operation over PCIe);
+ * the caller guarantees that the values fit.  Committed by the same jsl_batch_commit_variants. */
+int jsl_batch_stage_variants_packed(jsl_batch_t*, const uint8_t* op_machine, const uint16_t* op_duration,
+                                    const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream);
 int jsl_batch_commit_variants(jsl_batch_t*, void* stream);
 /* Uploaded tables are validated on the device while they are packed (the host arrays of the staged path are never
  * walked on the CPU): an operation machine outside [0, n_machines) or a negative duration is replaced by 0 and

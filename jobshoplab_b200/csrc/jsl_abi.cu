@@ -68,6 +68,7 @@ struct jsl_batch {
     bool ops_static = true;       // every operation duration is a static time object
     int32_t* d_bad = nullptr;     // number of out-of-range table entries seen by k_pack_variants (jsl_batch_check)
     int32_t* d_stage = nullptr;   // [2][n_inst*N] + [2][n_inst] staging for jsl_batch_load_variants
+    bool stage_packed = false;    // the staged tables are u8 machines / u16 durations (jsl_batch_stage_variants_packed)
     int32_t* d_op_tool = nullptr; // [N]
 };
 
@@ -76,16 +77,17 @@ namespace {
 // packs staged (machine, duration) tables into the engine layout and recomputes the per-job work sums
 // (uploaded tables are untrusted input: an operation machine outside [0, M) would index the per-machine state out
 // of bounds inside the engine, so it is replaced by machine 0 and counted; jsl_batch_check reports it)
+template <class TM, class TD>
 __global__ void k_pack_variants(int64_t n_inst, int N, int J, int M, int32_t* bad, const int32_t* __restrict__ job_op_start,
-                                const int32_t* __restrict__ op_tool, const int32_t* __restrict__ st_m,
-                                const int32_t* __restrict__ st_d, const int32_t* __restrict__ st_lb,
+                                const int32_t* __restrict__ op_tool, const TM* __restrict__ st_m,
+                                const TD* __restrict__ st_d, const int32_t* __restrict__ st_lb,
                                 const int32_t* __restrict__ st_mat, int32_t* op_mt, int32_t* op_dur,
                                 int32_t* job_work, int32_t* lb_mat) {
     const int64_t total = n_inst * N;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         int o = (int)(i % N);
-        int m = st_m[i], d = st_d[i];
+        int m = (int)st_m[i], d = (int)st_d[i];
         if (m < 0 || m >= M || d < 0) { atomicAdd(bad, 1); m = m < 0 || m >= M ? 0 : m; d = d < 0 ? 0 : d; }
         op_mt[i] = m | (op_tool[o] << 16);
         op_dur[i] = d;
@@ -95,7 +97,7 @@ __global__ void k_pack_variants(int64_t n_inst, int N, int J, int M, int32_t* ba
         int64_t v = i / J;
         int j = (int)(i % J);
         int w = 0;
-        for (int o = job_op_start[j]; o < job_op_start[j + 1]; o++) w += st_d[v * N + o] < 0 ? 0 : st_d[v * N + o];
+        for (int o = job_op_start[j]; o < job_op_start[j + 1]; o++) w += (int)st_d[v * N + o] < 0 ? 0 : (int)st_d[v * N + o];
         job_work[i] = w;
     }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_inst; i += stride) {
@@ -442,6 +444,30 @@ int jsl_batch_stage_variants(jsl_batch_t* b, const int32_t* op_machine, const in
     CK(cudaMemcpyAsync(sd, op_duration, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(sl, lower_bound, ni * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(sa, max_allowed_time, ni * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    b->stage_packed = false;
+    return JSL_OK;
+}
+
+// the same with narrow host tables (machines < 256, durations < 65536): 3 instead of 8 bytes per operation over PCIe
+int jsl_batch_stage_variants_packed(jsl_batch_t* b, const uint8_t* op_machine, const uint16_t* op_duration,
+                                    const int32_t* lower_bound, const int32_t* max_allowed_time, void* stream) {
+    if (!b || !op_machine || !op_duration || !lower_bound || !max_allowed_time) return JSL_E_INVALID;
+    CK(cudaSetDevice(b->device));
+    const InstDev& I = b->bd.inst;
+    const size_t n = (size_t)I.n_inst * I.N, ni = (size_t)I.n_inst;
+    if (!b->d_stage) {
+        void* p = nullptr;
+        CK(cudaMalloc(&p, (2 * n + 2 * ni) * sizeof(int32_t)));
+        b->allocs.push_back(p);
+        b->d_stage = (int32_t*)p;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *sm = b->d_stage, *sd = sm + n, *sl = sd + n, *sa = sl + ni;  // (same staging area, narrower use)
+    CK(cudaMemcpyAsync(sm, op_machine, n * sizeof(uint8_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sd, op_duration, n * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sl, lower_bound, ni * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sa, max_allowed_time, ni * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    b->stage_packed = true;
     return JSL_OK;
 }
 
@@ -453,9 +479,14 @@ int jsl_batch_commit_variants(jsl_batch_t* b, void* stream) {
     const InstDev& I = b->bd.inst;
     const size_t n = (size_t)I.n_inst * I.N, ni = (size_t)I.n_inst;
     int32_t *sm = b->d_stage, *sd = sm + n, *sl = sd + n, *sa = sl + ni;
-    k_pack_variants<<<b->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(I.n_inst, I.N, I.J, I.M, b->d_bad, I.job_op_start, b->d_op_tool, sm, sd, sl, sa,
-                                                                      (int32_t*)I.op_mt, (int32_t*)I.op_dur, (int32_t*)I.job_work,
-                                                                      (int32_t*)I.lb_mat);
+    if (b->stage_packed)
+        k_pack_variants<uint8_t, uint16_t><<<b->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(
+            I.n_inst, I.N, I.J, I.M, b->d_bad, I.job_op_start, b->d_op_tool, (const uint8_t*)sm, (const uint16_t*)sd, sl, sa,
+            (int32_t*)I.op_mt, (int32_t*)I.op_dur, (int32_t*)I.job_work, (int32_t*)I.lb_mat);
+    else
+        k_pack_variants<int32_t, int32_t><<<b->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(
+            I.n_inst, I.N, I.J, I.M, b->d_bad, I.job_op_start, b->d_op_tool, sm, sd, sl, sa,
+            (int32_t*)I.op_mt, (int32_t*)I.op_dur, (int32_t*)I.job_work, (int32_t*)I.lb_mat);
     b->launches++;
     CK(cudaGetLastError());
     return JSL_OK;

@@ -23,7 +23,7 @@ LOG_LIB_PATH = Path(os.environ.get("JSL_LOG_LIB", Path(__file__).resolve().paren
 _libs: dict = {}
 
 ABI_SYMBOLS = ("jsl_last_error", "jsl_abi_version", "jsl_instance_create", "jsl_instance_destroy", "jsl_batch_create",
-               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_stage_variants", "jsl_batch_commit_variants", "jsl_batch_check", "jsl_batch_randomize", "jsl_batch_get_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_state_layout", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
+               "jsl_batch_create_variants", "jsl_batch_load_variants", "jsl_batch_stage_variants", "jsl_batch_stage_variants_packed", "jsl_batch_commit_variants", "jsl_batch_check", "jsl_batch_randomize", "jsl_batch_get_variants", "jsl_batch_destroy", "jsl_batch_shape", "jsl_batch_state_layout", "jsl_batch_set_env_base", "jsl_batch_set_sample_tape", "jsl_batch_set_start_seeds",
                "jsl_reset", "jsl_step", "jsl_rollout", "jsl_get_state", "jsl_get_op_log", "jsl_get_leg_log", "jsl_launch_count")
 
 RO_RESET_FIRST, RO_NO_WRITEBACK = 1, 2
@@ -52,6 +52,7 @@ def load_library(log: bool = False):
                                             C.c_int64, C.c_int, C.c_uint64, C.POINTER(abi.EnvCfg)]
     L.jsl_batch_load_variants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.jsl_batch_stage_variants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.jsl_batch_stage_variants_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.jsl_batch_commit_variants.argtypes = [C.c_void_p, C.c_void_p]
     L.jsl_batch_check.argtypes = [C.c_void_p]
     L.jsl_batch_randomize.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -227,6 +228,27 @@ class Batch:
         rollout still runs on the tables in use)."""
         ptrs = self._host_ptrs((op_machine, op_duration, lower_bound, max_allowed_time))
         self._check(self.L.jsl_batch_stage_variants(self.h, *ptrs, self._stream()))
+
+    def stage_variants_packed(self, op_machine_u8, op_duration_u16, lower_bound, max_allowed_time):
+        """stage_variants with narrow HOST tables: uint8 machines, uint16 durations (3 instead of 8 bytes per operation
+        over PCIe).  The caller guarantees the values fit (pack_variants checks)."""
+        torch = self.torch
+        n, N = int(self.n_variants), self.shape.n_ops
+        for a, dt, want in ((op_machine_u8, torch.uint8, n * N), (op_duration_u16, torch.uint16, n * N),
+                            (lower_bound, torch.int32, n), (max_allowed_time, torch.int32, n)):
+            if a.is_cuda or a.dtype != dt or not a.is_contiguous() or a.numel() != want:
+                raise InvalidValue("packed variant tables", (tuple(a.shape), a.dtype), f"expected {want} host elements of {dt}")
+        self._check(self.L.jsl_batch_stage_variants_packed(self.h, op_machine_u8.data_ptr(), op_duration_u16.data_ptr(),
+                                                           lower_bound.data_ptr(), max_allowed_time.data_ptr(), self._stream()))
+
+    @staticmethod
+    def pack_variants(op_machine, op_duration):
+        """int32 tables -> (uint8 machines, uint16 durations) pinned host tensors for stage_variants_packed."""
+        import torch
+        om, od = torch.as_tensor(op_machine), torch.as_tensor(op_duration)
+        if int(om.min()) < 0 or int(om.max()) > 255 or int(od.min()) < 0 or int(od.max()) > 65535:
+            raise InvalidValue("variant tables", (int(om.max()), int(od.max())), "do not fit uint8 machines / uint16 durations")
+        return om.to(torch.uint8).contiguous().pin_memory(), od.to(torch.uint16).contiguous().pin_memory()
 
     def check(self):
         """Raises if any uploaded table entry was out of range (validated on the device while packing; synchronises)."""

@@ -304,3 +304,29 @@ def test_maximum_sizes_and_limits():
     with pytest.raises(InvalidValue) as e:
         eng.Batch(C.compile_spec_text("\n".join(lines) + "\n"), 2)
     assert "32 machines" in str(e.value)
+
+
+def test_packed_variant_upload_equals_int32_upload():
+    """jsl_batch_stage_variants_packed (uint8 machines / uint16 durations, what bench.py's e2e path uploads) leaves the
+    same tables on the device as the int32 path; values that do not fit are refused on the host."""
+    import bench
+    from jobshoplab_b200.exceptions import InvalidValue
+
+    eng = _engine()
+    tmpl = bench.template_instance()
+    om, od = bench.make_instances(64, first=128)
+    lb, mat = bench.taillard_bounds(om, od)
+    a = eng.Batch(tmpl, 64, variants=(om, od, lb, mat))
+    zeros = np.zeros_like(om)
+    b = eng.Batch(tmpl, 64, variants=(zeros, zeros + 1, lb * 0 + 1, mat * 0 + 600))
+    pm, pd = eng.Batch.pack_variants(om, od)
+    b.stage_variants_packed(pm, pd, torch.from_numpy(lb).pin_memory(), torch.from_numpy(mat).pin_memory())
+    b.commit_variants()
+    b.check()
+    for x, y in zip(a.get_variants(), b.get_variants()):
+        assert np.array_equal(x, y)
+    ra, rb = a.rollout("spt", reset_first=True), b.rollout("spt", reset_first=True)
+    assert torch.equal(ra.makespan, rb.makespan) and torch.equal(ra.ret, rb.ret)
+    with pytest.raises(InvalidValue):
+        eng.Batch.pack_variants(om, od * 1000)
+    a.close(); b.close()
