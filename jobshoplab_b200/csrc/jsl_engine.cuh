@@ -1630,18 +1630,31 @@ JSL_D bool sm_step(EnvS<JW, ST, CL>& s, Ctx& c, bool has_action, Trans act, int 
             if (JSL_UNLIKELY(c.raise)) return true;
             if (JSL_UNLIKELY(!ok)) return false;
         }
+        if (CL == 2) {  // (the classic kernel keeps the loop it was tuned with: its layout is worth 2 % of the headline)
 #pragma unroll 1
-        for (int ph = 0; ph < 2; ph++) {
-            Mask<JW> cur = ph == 0 ? tm : tele;
-            while (cur.any()) {
-                int t = cur.pop_first();
+            for (int ph = 0; ph < 2; ph++) {
+                Mask<JW> cur = ph == 0 ? tm : tele;
+                while (cur.any()) {
+                    int t = cur.pop_first();
+                    bool ok = apply_transport(s, c, t, s.x_tkind[t], s.x_tjob[t], !action_stage);
+                    if (JSL_UNLIKELY(c.raise)) return true;
+                    if (JSL_UNLIKELY(!ok)) return false;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < JW; w++) { tm.w[w] = 0; tele.w[w] = 0; }
+        } else {
+            // timed transports first, then the teleports: one loop, one call site, the masks consumed in place (no
+            // copy of the current mask to keep live -- or, in the stochastic kernels, to spill -- across the handlers)
+            for (;;) {
+                int t = tm.pop_first();
+                if (t < 0) t = tele.pop_first();
+                if (t < 0) break;
                 bool ok = apply_transport(s, c, JSL_LVL_BUF(CL) ? (int)s.x_tcomp[t] : t, s.x_tkind[t], s.x_tjob[t], !action_stage);
                 if (JSL_UNLIKELY(c.raise)) return true;
                 if (JSL_UNLIKELY(!ok)) return false;
             }
         }
-#pragma unroll
-        for (int w = 0; w < JW; w++) { tm.w[w] = 0; tele.w[w] = 0; }
         JSL_SYNCWARP();
         if (action_stage) { action_stage = false; leg_stamp(s, c); }
         else first = false;
