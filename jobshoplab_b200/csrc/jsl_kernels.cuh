@@ -282,6 +282,76 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     if (has_outs) copy_in(g_outs, outs_sm, bd.outs_stride);
 }
 
+#ifdef JSL_STEP_PERSISTENT
+// EXPERIMENT (not in the shipped library): persistent step kernel.  One resident wave of CTAs, every warp
+// walks envs gw, gw + W, ...; the image of the NEXT env is fetched with cp.async (LDGSTS, no registers) into the warp's
+// second slot while the current env is stepped.
+template <int JW, bool ST, int CL>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_STEP_MIN_CTAS)
+k_step_p(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions, jsl_step_out out, int obs_bytes) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = WARPS_PER_CTA == 1 ? 0 : warp_index();
+    const uint32_t B = (uint32_t)bd.B, nw = gridDim.x * WARPS_PER_CTA;
+    uint32_t env = blockIdx.x * WARPS_PER_CTA + warp;
+    if (env >= B) return;
+    constexpr int IMG = Image<JW, CL>::BYTES;
+    const int stride = slot_stride<JW, CL>(bd);
+    uint8_t* base = smem + warp * 2 * stride;
+    const bool has_outs = JSL_LVL_OUT(CL) && bd.outs != nullptr;
+    auto prefetch = [&](uint8_t* dst, uint32_t e) {
+        const uint8_t* src = bd.state + (size_t)e * IMG;
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+#pragma unroll
+        for (int k = 0; k < (IMG / 16 + 31) / 32; k++) {
+            const int i = JSL_LANE + 32 * k;
+            if (i < IMG / 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16 * i), "l"(src + 16 * i));
+        }
+    };
+    int cur = 0;
+    prefetch(base, env);
+    asm volatile("cp.async.commit_group;");
+    for (;;) {
+        const uint32_t nxt = env + nw;
+        if (nxt < B) prefetch(base + (1 - cur) * stride, nxt);
+        asm volatile("cp.async.commit_group;");
+        const int action = actions[env];
+        uint8_t* slot = base + cur * stride;
+        EnvS<JW, ST, CL>& s = *(EnvS<JW, ST, CL>*)slot;
+        void* outs_sm = (void*)(slot + Slot<JW>::OUTS);
+        uint8_t* g_state = bd.state + (size_t)env * IMG;
+        uint8_t* g_outs = has_outs ? bd.outs + (size_t)env * (uint32_t)bd.outs_stride : nullptr;
+        Ctx c;
+        make_ctx<JW, ST, CL, true>(c, bd, env, slot);
+        if (has_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        double r = run_env_op(s, c, action);
+        __syncwarp();
+        if (s.status >= JSL_ST_STEP_FAILED) {
+            int status = s.status, n_steps = s.n_steps, reward_noop = s.reward_noop, step_action = s.step_action,
+                step_noop = s.step_noop;
+            double ret = s.ret;
+            __syncwarp();
+            copy_in(&s, g_state, IMG);
+            if (has_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
+            s.status = status;
+            if (status == JSL_ST_STEP_FAILED) {
+                s.truncated = 1; s.terminated = 0; s.obs_done = 1;
+                s.n_steps = n_steps; s.reward_noop = reward_noop; s.step_action = step_action; s.step_noop = step_noop;
+                s.ret = ret;
+            }
+            __syncwarp();
+        }
+        write_step_out(s, c, out, env, r, obs_bytes);
+        __syncwarp();
+        copy_fixed<IMG>(g_state, &s);
+        if (has_outs) copy_in(g_outs, outs_sm, bd.outs_stride);
+        if (nxt >= B) break;
+        env = nxt; cur ^= 1;
+    }
+}
+#endif
+
 template <int JW, bool ST, int CL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, ST ? JSL_ROLLOUT_MIN_CTAS_ST : CL ? JSL_ROLLOUT_MIN_CTAS : JSL_ROLLOUT_MIN_CTAS_GENERAL)
 k_rollout(const __grid_constant__ BatchDev bd, int policy, const uint8_t* __restrict__ tape, int64_t tape_stride,
@@ -380,6 +450,24 @@ cudaError_t launch_reset(const BatchDev& bd, const LaunchCfg& lc, const uint8_t*
 template <int JW, bool ST, int CL>
 cudaError_t launch_step(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* actions, jsl_step_out out, int obs_bytes) {
     if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_step<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+#ifdef JSL_STEP_PERSISTENT
+    {
+        static int sms = 0;
+        if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        const int smem2 = 2 * lc.smem;
+        static bool once = false;
+        if (!once) {
+            cudaFuncSetAttribute(k_step_p<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+            cudaFuncSetAttribute(k_step_p<JW, ST, CL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            once = true;
+        }
+        int ctas = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_step_p<JW, ST, CL>, WARPS_PER_CTA * 32, smem2);
+        const long long wave = (long long)sms * (ctas > 0 ? ctas : 1);
+        k_step_p<JW, ST, CL><<<(int)(lc.grid < wave ? lc.grid : wave), WARPS_PER_CTA * 32, smem2, lc.stream>>>(bd, actions, out, obs_bytes);
+        return cudaGetLastError();
+    }
+#endif
     static bool carved = false;  // per instantiation: room for JSL_STEP_MIN_CTAS resident CTAs' slots, the rest stays L1
     if (!carved) {
         int pct = (int)(((long long)lc.smem + 1024) * JSL_STEP_MIN_CTAS * 100 / (228 * 1024)) + 1;
