@@ -163,11 +163,15 @@ class Batch:
         dev = torch.device("cuda", self.device)
         ob = max(self.shape.obs_bytes, 16)
         # per-env scalars of a step arrive as one 32-byte jsl_step_record per env; the named fields are strided views
-        self.record = torch.zeros((self.B, abi.STEP_RECORD_BYTES), dtype=torch.uint8, device=dev)
+        # (records and observations share one allocation: a single-env batch is read back with one copy, fetch_host)
+        RB = abi.STEP_RECORD_BYTES
+        self._outbuf = torch.zeros(self.B * (RB + ob), dtype=torch.uint8, device=dev)
+        self._host_out = None
+        self.record = self._outbuf[: self.B * RB].view(self.B, RB)
         rec = self.record
         i32 = rec[:, 8:16].view(torch.int32)
         self.out = StepResult(
-            obs=torch.zeros((self.B, ob), dtype=torch.uint8, device=dev),
+            obs=self._outbuf[self.B * RB:].view(self.B, ob),
             reward=rec[:, 0:8].view(torch.float64)[:, 0],
             terminated=rec[:, 24], truncated=rec[:, 25], status=rec[:, 26],
             time=i32[:, 0], makespan=i32[:, 1],
@@ -383,6 +387,51 @@ class Batch:
             v = rec[:, off: off + dt.itemsize * cnt].view(tdt[dt])
             views[name] = v[:, 0] if cnt == 1 else v
         return views
+
+    # ---- single-env read-back ---------------------------------------------------------------------------
+    def fetch_host(self, idx: int = 0):
+        """(jsl_step_record bytes, observation bytes) of env `idx` as numpy uint8 views of a pinned staging buffer:
+        one device->host copy for a single-env batch, two otherwise, one stream synchronisation.  The views are
+        overwritten by the next call."""
+        torch, RB = self.torch, abi.STEP_RECORD_BYTES
+        ob = self.out.obs.shape[1]
+        if self._host_out is None:
+            self._host_out = torch.empty(RB + ob, dtype=torch.uint8, pin_memory=True)
+            self._host_np = self._host_out.numpy()
+        if self.B == 1:
+            self._host_out.copy_(self._outbuf, non_blocking=True)
+        else:
+            self._host_out[:RB].copy_(self.record[idx], non_blocking=True)
+            self._host_out[RB:].copy_(self.out.obs[idx], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._host_np[:RB], self._host_np[RB:]
+
+    def unpack_obs_host(self, raw: np.ndarray) -> dict:
+        """unpack_obs for ONE env's observation bytes on the host (numpy views of `raw`)."""
+        J, M, N = self.shape.n_jobs, self.shape.n_machines, self.shape.n_ops
+        kind = self.cfg.obs_kind
+        if kind == abi.OBS_STATE:
+            return {k: v[0].numpy() for k, v in self.unpack_state(self.torch.from_numpy(raw)[None]).items()}
+        if kind == abi.OBS_TASSEL:
+            f = raw[: 28 * J].view(np.float32).reshape(7, J)
+            keys = ("allocatable", "left_over_time", "percent_finished", "total_completion",
+                    "time_until_next_machine_is_free", "idle_since_last_op", "cum_idle_time")
+            return {k: f[i] for i, k in enumerate(keys)}
+        if kind == abi.OBS_OPERATION_ARRAY:
+            f = raw[: 16 + 4 * N + 4 * J].view(np.float32)
+            return {"operation_state": f[None, 4: 4 + N], "job_locations": f[None, 4 + N: 4 + N + J],
+                    "current_transition": f[0:3]}
+        o = 16
+        f = raw[:16].view(np.float32)
+        jprog = raw[o: o + 4 * J].view(np.int32); o += 4 * J
+        mprog = raw[o: o + 4 * M].view(np.int32); o += 4 * M
+        jrun = raw[o: o + J].view(np.int8); o += J
+        avail = raw[o: o + J].view(np.int8); o += J
+        mrun = raw[o: o + M].view(np.int8); o += M
+        execd = raw[o: o + J * M].view(np.int8).reshape(J, M)
+        return {"job_running": jrun, "job_executed_on_machine": execd, "job_progression": jprog,
+                "machine_running": mrun, "machine_progression": mprog, "available_jobs": avail,
+                "current_time": f[0:1], "current_transition": f[1:4]}
 
     # ---- observation record -> named views (zero copy) -------------------------------------------------
     def unpack_obs(self, obs=None) -> dict:

@@ -264,17 +264,15 @@ class JobShopLabEnv:
     def num_operations(self):
         return self.instance.n_ops
 
-    def _obs_host(self):
+    def _fetch(self):
+        """One device->host copy per step: the env's 32-byte jsl_step_record and its observation record."""
         from .middleware import host_observation
-        return host_observation(self._batch, 0)
-
-    def _record(self):
-        """The 32-byte jsl_step_record of the env: one device->host copy per step."""
-        raw = self._batch.record[0].cpu().numpy().tobytes()
+        rec, obs = self._batch.fetch_host(0)
+        raw = rec.tobytes()
         reward = float(np.frombuffer(raw, np.float64, 1, 0)[0])
         time, makespan = (int(x) for x in np.frombuffer(raw, np.int32, 2, 8))
         cand = tuple(int(x) for x in np.frombuffer(raw, np.int16, 4, 16))
-        return reward, time, makespan, cand, bool(raw[24]), bool(raw[25]), raw[26]
+        return (reward, time, makespan, cand, bool(raw[24]), bool(raw[25]), raw[26]), host_observation(self._batch, 0, obs)
 
     def _get_info(self, no_op: bool) -> dict:
         return {"no_op": no_op, "terminated": self.terminated, "truncated": self.truncated,
@@ -299,7 +297,8 @@ class JobShopLabEnv:
                 self._batch.close()
             self._batch = Batch(instance, 1, device=self._device, seed=self.seed or 0, record_ops=True,
                                 **_cfg_kwargs(self.config))
-            self._acts = self._batch.torch.zeros(1, dtype=self._batch.torch.uint8, device=f"cuda:{self._device}")
+            # the two legal actions as resident device bytes: a step uploads nothing
+            self._acts = self._batch.torch.tensor([[0], [1]], dtype=self._batch.torch.uint8, device=f"cuda:{self._device}").unbind(0)
         self.instance = instance
         self.lower_bound = self.instance.lower_bound
         self.max_allowed_time = self.instance.max_allowed_time
@@ -307,12 +306,12 @@ class JobShopLabEnv:
         self.observation_space = _spaces.observation_space(self._batch.cfg.obs_kind, instance.n_jobs, instance.n_machines,
                                                            instance.n_ops)
         self._batch.reset()
-        _, self._time, _, self._cand, _, _, status = self._record()
+        (_, self._time, _, self._cand, _, _, status), obs = self._fetch()
         self._raise_for(status)
         self.terminated = self.truncated = self.done = False
         self._no_op_count = 0
         self.history: tuple = tuple()
-        return self._obs_host(), {"env_seed": self.seed}
+        return obs, {"env_seed": self.seed}
 
     def _raise_for(self, status: int):
         exc = STATUS_TO_EXCEPTION.get(status)
@@ -329,16 +328,15 @@ class JobShopLabEnv:
             raise EnvDone()
         if not self.action_space.contains(action):
             self._raise_for(abi.ST_ACTION_OUT_OF_SPACE if self._cand[3] > 0 else abi.ST_NO_POSSIBLE)
-        self._acts.fill_(int(action))
-        self._batch.step(self._acts)
+        self._batch.step(self._acts[int(action)])
         applied = (self._cand_transition(self._cand),) if int(action) == 1 else tuple()
-        reward, self._time, _, self._cand, self.terminated, self.truncated, status = self._record()
+        (reward, self._time, _, self._cand, self.terminated, self.truncated, status), obs = self._fetch()
         self._raise_for(status)
         self.done = self.terminated or self.truncated
         if status != abi.ST_STEP_FAILED:  # env.py:444-446: only successful results enter the history
             self._no_op_count += int(action == 0)
             self.history += (HistoryEntry(applied, True, "Success" if action == 1 else "NO OPERATION", self._time),)
-        return self._obs_host(), reward, self.terminated, self.truncated, self._get_info(action == 0)
+        return obs, reward, self.terminated, self.truncated, self._get_info(action == 0)
 
     def op_log(self) -> np.ndarray:
         """Per-op (start, end) times so far -- what render() / the Gantt dashboard consume (8(f)1)."""

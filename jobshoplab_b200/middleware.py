@@ -34,17 +34,19 @@ _STOCK_OBS = {"BinaryActionObservationFactory": abi.OBS_BINARY_ACTION,
               "TasselJsspObservation": abi.OBS_TASSEL}
 
 
-def host_observation(batch: Batch, idx: int = 0) -> dict:
+def host_observation(batch: Batch, idx: int = 0, raw=None) -> dict:
     """Packed observation record of env `idx` -> the dict the reference's factory returns (tuples of bool / int for
-    the default factory, observations.py:419-479; float arrays for the others)."""
-    views = batch.unpack_obs(batch.out.obs)
-    host = {k: v[idx].cpu().numpy() for k, v in views.items()}
+    the default factory, observations.py:419-479; float arrays for the others).  `raw`: the env's observation bytes
+    when the caller already fetched them (Batch.fetch_host)."""
+    if raw is None:
+        raw = batch.fetch_host(idx)[1]
+    host = {k: v.copy() for k, v in batch.unpack_obs_host(raw).items()}
     if batch.cfg.obs_kind == abi.OBS_BINARY_ACTION:
         for k in ("job_running", "machine_running", "available_jobs"):
-            host[k] = tuple(bool(x) for x in host[k])
-        host["job_executed_on_machine"] = tuple(tuple(bool(x) for x in row) for row in host["job_executed_on_machine"])
-        host["job_progression"] = tuple(int(x) for x in host["job_progression"])
-        host["machine_progression"] = tuple(int(x) for x in host["machine_progression"])
+            host[k] = tuple(host[k].astype(bool).tolist())
+        host["job_executed_on_machine"] = tuple(map(tuple, host["job_executed_on_machine"].astype(bool).tolist()))
+        host["job_progression"] = tuple(host["job_progression"].tolist())
+        host["machine_progression"] = tuple(host["machine_progression"].tolist())
     return host
 
 
@@ -252,8 +254,13 @@ class CudaEventBasedBinaryActionMiddleware:
 
     def _observation(self, result, done: bool):
         if self._engine_obs:
-            return host_observation(self._batch, 0)
+            return host_observation(self._batch, 0, self._obs_raw)
         return self.observation_factory.make(result, done)
+
+    def _fetch(self):
+        """One device->host copy per call: (status, terminated, truncated) of the record; keeps the observation bytes."""
+        rec, self._obs_raw = self._batch.fetch_host(0)
+        return int(rec[26]), bool(rec[24]), bool(rec[25])
 
     def _result(self, action, success=True, message="Success", prev=None):
         state, poss = self._builder.build(self._batch.get_state(0), prev_state=prev.state if prev is not None else None)
@@ -288,13 +295,14 @@ class CudaEventBasedBinaryActionMiddleware:
             self._batch.set_start_seeds(self._seeds)
         self._builder = StateBuilder(self.instance, init_state, self._ix, self._ref)
         import torch
-        self._acts = torch.zeros(1, dtype=torch.uint8, device=f"cuda:{self.device}")
-        out = self._batch.reset()
-        self._raise_for(int(out.status[0]))
+        self._acts = torch.tensor([[0], [1]], dtype=torch.uint8, device=f"cuda:{self.device}").unbind(0)  # resident action bytes
+        self._batch.reset()
+        status, terminated, _ = self._fetch()
+        self._raise_for(status)
         self.truncation_joker = self._init_truncation_joker
         self._truncated = False
         result = self._result(self.action_factory.get_dummy_action(), message="Success")
-        if not result.possible_transitions and bool(out.terminated[0]):
+        if not result.possible_transitions and terminated:
             result = replace(result, message="Done")
         return result, self._observation(result, False)
 
@@ -305,11 +313,10 @@ class CudaEventBasedBinaryActionMiddleware:
             raise ref.ex.InvalidValue("State must be of type StateMachineResult")
         act = self.action_factory.interpret(action, state)  # raises InvalidValue / ActionOutOfActionSpace like the stock one
         no_op = act.action_factory_info == ref.at.ActionFactoryInfo.NoOperation
-        self._acts.fill_(0 if no_op else 1)
-        out = self._batch.step(self._acts)
-        status = int(out.status[0])
+        self._batch.step(self._acts[0 if no_op else 1])
+        status, terminated, truncated = self._fetch()
         self._raise_for(status)
-        self._truncated = bool(out.truncated[0]) and status != abi.ST_STEP_FAILED
+        self._truncated = truncated and status != abi.ST_STEP_FAILED
         if status == abi.ST_STEP_FAILED:  # validation error: the old state, success=False (state.py:202-210)
             result = ref.st.StateMachineResult(state=state.state, sub_states=state.sub_states, action=act, success=False,
                                                message="Transition errors", possible_transitions=())
@@ -325,7 +332,7 @@ class CudaEventBasedBinaryActionMiddleware:
             if no_op:
                 act = replace(act, time_machine=ref.tm.force_jump_to_event)  # :336
             result = self._result(act, prev=state)
-            if not result.possible_transitions and bool(out.terminated[0]):
+            if not result.possible_transitions and terminated:
                 result = replace(result, message="Done")
         if no_op and len(state.possible_transitions) == 1 and result.possible_transitions:
             self.truncation_joker = self._init_truncation_joker  # informational; the engine holds the real counter
