@@ -98,3 +98,29 @@ def test_time_fraction_shortcut_is_exact():
     m = rng.integers(1, 1 << 22, size=4_000_000).astype(np.float64)
     t = np.floor(rng.random(4_000_000) * m * 1.5)
     assert np.array_equal((t / m).astype(np.float32), (t * (1.0 / m)).astype(np.float32))
+
+
+def test_host_unpack_matches_tensor_unpack():
+    import numpy as np
+    """Batch.unpack_obs_host (numpy views of one env's bytes, the single-env read-back) names the same bytes as
+    Batch.unpack_obs (torch views of the [B, bytes] record) for every packed observation kind."""
+    import types
+
+    import torch
+
+    from jobshoplab_b200 import abi, engine
+
+    rng = np.random.default_rng(5)
+    J, M, N = 7, 5, 31
+    for kind, nbytes in ((abi.OBS_BINARY_ACTION, (16 + 4 * J + 4 * M + 2 * J + M + J * M + 15) & ~15),
+                         (abi.OBS_OPERATION_ARRAY, 16 + 4 * N + 4 * J), (abi.OBS_TASSEL, 28 * J)):
+        stub = types.SimpleNamespace(shape=types.SimpleNamespace(n_jobs=J, n_machines=M, n_ops=N),
+                                     cfg=types.SimpleNamespace(obs_kind=kind), torch=torch, out=None)
+        raw = rng.integers(0, 256, nbytes, dtype=np.uint8)
+        host = engine.Batch.unpack_obs_host(stub, raw)
+        dev = engine.Batch.unpack_obs(stub, torch.from_numpy(raw.copy())[None])
+        assert set(host) == set(dev)
+        for k in host:
+            want = dev[k][0].numpy()
+            assert host[k].dtype == want.dtype and host[k].shape == want.shape, (kind, k)
+            assert host[k].tobytes() == want.tobytes(), (kind, k)
