@@ -232,6 +232,7 @@ struct alignas(16) EnvAux {
     int32_t pad;
     int32_t* leg_log;            // transport-task log of this env (see LegLog) or nullptr
     uint32_t loop_scratch[14];   // stochastic kernels: sm_step keeps its transition masks and loop guard here (see there)
+    uint64_t bar;                // k_step: mbarrier of the bulk copy that brings the state image in
 };
 
 // per-call context: the few uniform values the hot loop keeps in registers

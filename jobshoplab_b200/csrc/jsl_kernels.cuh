@@ -253,10 +253,30 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
     void* outs_sm = (void*)(slot + Slot<JW>::OUTS);
     uint8_t* g_state = bd.state + (size_t)env * IMG;
     uint8_t* g_outs = has_outs ? bd.outs + (size_t)env * (uint32_t)bd.outs_stride : nullptr;
-    copy_fixed<IMG>(&s, g_state);
+    // The image travels by bulk copy (UBLKCP: the TMA engine writes the 1.5 KB straight into the slot and signals the
+    // warp's mbarrier) instead of 128-bit loads and shared-memory stores of the lanes: the kernel's busiest unit is the
+    // LSU data pipe, and the two image copies were a fifth of its wavefronts.  The context is set up under the copy.
+    static_assert(IMG % 16 == 0, "bulk copies move multiples of 16 bytes");
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&((EnvAux*)(slot + Slot<JW>::AUX))->bar);
+    const uint32_t s_sm = (uint32_t)__cvta_generic_to_shared(slot);
+    if (JSL_LANE == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(IMG) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(s_sm), "l"(g_state), "r"(IMG), "r"(bar) : "memory");
+    }
+    __syncwarp();
     if (has_outs) copy_in(outs_sm, g_outs, bd.outs_stride);
     Ctx c;
     make_ctx<JW, ST, CL, true>(c, bd, env, slot);
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
+    __syncwarp();
     double r = run_env_op(s, c, action);
     __syncwarp();
     if (s.status >= JSL_ST_STEP_FAILED) {
@@ -277,9 +297,16 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
         __syncwarp();
     }
     write_step_out(s, c, out, env, r, obs_bytes);
+    // generic-proxy writes of all lanes -> visible to the async proxy, then one bulk store of the image; the slot must
+    // stay allocated until the engine has read it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    copy_fixed<IMG>(g_state, &s);
+    if (JSL_LANE == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_state), "r"(s_sm), "r"(IMG) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
     if (has_outs) copy_in(g_outs, outs_sm, bd.outs_stride);
+    if (JSL_LANE == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 #ifdef JSL_STEP_PERSISTENT
