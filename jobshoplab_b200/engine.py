@@ -406,32 +406,48 @@ class Batch:
         torch.cuda.current_stream(self.device).synchronize()
         return self._host_np[:RB], self._host_np[RB:]
 
+    def fetch_host_all(self):
+        """(jsl_step_records [B, 32], observation records [B, obs_bytes]) of EVERY env as numpy uint8 views of a pinned
+        staging buffer: one device->host copy and one stream synchronisation per call (what a host-side training loop
+        -- vec_env.SB3VecEnv -- pays per step).  The views are overwritten by the next call."""
+        torch, RB = self.torch, abi.STEP_RECORD_BYTES
+        ob = self.out.obs.shape[1]
+        if getattr(self, "_host_all", None) is None:
+            self._host_all = torch.empty(self.B * (RB + ob), dtype=torch.uint8, pin_memory=True)
+            self._host_all_np = self._host_all.numpy()
+        self._host_all.copy_(self._outbuf, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._host_all_np[: self.B * RB].reshape(self.B, RB), self._host_all_np[self.B * RB:].reshape(self.B, ob)
+
     def unpack_obs_host(self, raw: np.ndarray) -> dict:
-        """unpack_obs for ONE env's observation bytes on the host (numpy views of `raw`)."""
+        """unpack_obs on the host: numpy views of one env's observation bytes `raw` [obs_bytes], or of all of them
+        [B, obs_bytes] (then every entry has the leading batch axis of unpack_obs)."""
         J, M, N = self.shape.n_jobs, self.shape.n_machines, self.shape.n_ops
         kind = self.cfg.obs_kind
+        lead = raw.shape[:-1]
         if kind == abi.OBS_STATE:
-            return {k: v[0].numpy() for k, v in self.unpack_state(self.torch.from_numpy(raw)[None]).items()}
+            t = self.unpack_state(self.torch.from_numpy(raw if lead else raw[None]))
+            return {k: (v if lead else v[0]).numpy() for k, v in t.items()}
         if kind == abi.OBS_TASSEL:
-            f = raw[: 28 * J].view(np.float32).reshape(7, J)
+            f = raw[..., : 28 * J].view(np.float32).reshape(lead + (7, J))
             keys = ("allocatable", "left_over_time", "percent_finished", "total_completion",
                     "time_until_next_machine_is_free", "idle_since_last_op", "cum_idle_time")
-            return {k: f[i] for i, k in enumerate(keys)}
+            return {k: f[..., i, :] for i, k in enumerate(keys)}
         if kind == abi.OBS_OPERATION_ARRAY:
-            f = raw[: 16 + 4 * N + 4 * J].view(np.float32)
-            return {"operation_state": f[None, 4: 4 + N], "job_locations": f[None, 4 + N: 4 + N + J],
-                    "current_transition": f[0:3]}
+            f = raw[..., : 16 + 4 * N + 4 * J].view(np.float32)
+            return {"operation_state": f[..., None, 4: 4 + N], "job_locations": f[..., None, 4 + N: 4 + N + J],
+                    "current_transition": f[..., 0:3]}
         o = 16
-        f = raw[:16].view(np.float32)
-        jprog = raw[o: o + 4 * J].view(np.int32); o += 4 * J
-        mprog = raw[o: o + 4 * M].view(np.int32); o += 4 * M
-        jrun = raw[o: o + J].view(np.int8); o += J
-        avail = raw[o: o + J].view(np.int8); o += J
-        mrun = raw[o: o + M].view(np.int8); o += M
-        execd = raw[o: o + J * M].view(np.int8).reshape(J, M)
+        f = raw[..., :16].view(np.float32)
+        jprog = raw[..., o: o + 4 * J].view(np.int32); o += 4 * J
+        mprog = raw[..., o: o + 4 * M].view(np.int32); o += 4 * M
+        jrun = raw[..., o: o + J].view(np.int8); o += J
+        avail = raw[..., o: o + J].view(np.int8); o += J
+        mrun = raw[..., o: o + M].view(np.int8); o += M
+        execd = raw[..., o: o + J * M].view(np.int8).reshape(lead + (J, M))
         return {"job_running": jrun, "job_executed_on_machine": execd, "job_progression": jprog,
                 "machine_running": mrun, "machine_progression": mprog, "available_jobs": avail,
-                "current_time": f[0:1], "current_transition": f[1:4]}
+                "current_time": f[..., 0:1], "current_transition": f[..., 1:4]}
 
     # ---- observation record -> named views (zero copy) -------------------------------------------------
     def unpack_obs(self, obs=None) -> dict:

@@ -54,12 +54,19 @@ class SB3VecEnv(_VecEnvBase):
     def _host_obs(self, views) -> "OrderedDict[str, np.ndarray]":
         return OrderedDict((k, views[k].cpu().numpy().copy()) for k in self.observation_space.keys())
 
+    def _fetch(self):
+        """Step records and observations of all envs with ONE device->host copy (Batch.fetch_host_all):
+        (records [B, 32] uint8 view, observation dict of fresh numpy arrays)."""
+        rec, raw = self.venv.batch.fetch_host_all()
+        views = self.venv.batch.unpack_obs_host(raw)
+        return rec, OrderedDict((k, np.array(views[k])) for k in self.observation_space.keys())
+
     # ------------------------------------------------------------------ VecEnv protocol
     def reset(self):
         views, _ = self.venv.reset()
         self._episode_return[:] = 0
         self._episode_length[:] = 0
-        return self._host_obs(views)
+        return self._host_obs(views) if self.venv.observation_fn else self._fetch()[1]
 
     def step_async(self, actions):
         a = np.asarray(actions).astype(np.uint8).reshape(self.num_envs)
@@ -70,19 +77,17 @@ class SB3VecEnv(_VecEnvBase):
     def step_wait(self):
         assert self._pending, "step_wait() without step_async()"
         self._pending = False
-        out, batch = self._out, self.venv.batch
-        rewards = out.reward.cpu().numpy().astype(np.float32)
-        terminated = out.terminated.cpu().numpy().astype(bool)
-        truncated = out.truncated.cpu().numpy().astype(bool)
-        makespan = out.makespan.cpu().numpy()
-        status = out.status.cpu().numpy()
+        rec, obs = self._fetch()  # the only device->host traffic of the step (plus one more for the envs reset below)
+        rewards = rec[:, 0:8].view(np.float64)[:, 0].astype(np.float32)
+        terminated, truncated = rec[:, 24].astype(bool), rec[:, 25].astype(bool)
+        makespan = rec[:, 12:16].view(np.int32)[:, 0].copy()
+        status = rec[:, 26].copy()
         # an env that died with an escaped exception (status >= JSL_ST_STEP_FAILED: BufferFullError, ...) is over as
         # well: it is reported (infos[i]["status"], "TimeLimit.truncated" False) and reset like any finished env
         failed = status >= abi.ST_STEP_FAILED
         dones = terminated | truncated | failed
         self._episode_return += rewards
         self._episode_length += 1
-        obs = self._host_obs(batch.unpack_obs(out.obs))
         infos = [{} for _ in range(self.num_envs)]
         if dones.any():
             idx = np.nonzero(dones)[0]
@@ -92,8 +97,8 @@ class SB3VecEnv(_VecEnvBase):
                             "makespan": int(makespan[i]) if terminated[i] else None, "status": int(status[i]),
                             "episode": {"r": float(self._episode_return[i]), "l": int(self._episode_length[i])}}
             mask = self._torch.from_numpy(dones.astype(np.uint8)).to(self._actions.device)
-            views, _ = self.venv.reset(mask)  # (redraws the instances of those envs under InstanceRandomizer)
-            fresh = self._host_obs(views)
+            self.venv.reset(mask)  # (redraws the instances of those envs under InstanceRandomizer)
+            fresh = self._fetch()[1]
             for k in obs:
                 obs[k][idx] = fresh[k][idx]
             self._episode_return[idx] = 0

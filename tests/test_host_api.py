@@ -124,3 +124,11 @@ def test_host_unpack_matches_tensor_unpack():
             want = dev[k][0].numpy()
             assert host[k].dtype == want.dtype and host[k].shape == want.shape, (kind, k)
             assert host[k].tobytes() == want.tobytes(), (kind, k)
+        # all envs at once (Batch.fetch_host_all): same entries with the leading batch axis
+        raw2 = rng.integers(0, 256, (5, nbytes), dtype=np.uint8)
+        host2 = engine.Batch.unpack_obs_host(stub, raw2)
+        dev2 = engine.Batch.unpack_obs(stub, torch.from_numpy(raw2.copy()))
+        for k in host2:
+            want = dev2[k].numpy()
+            assert host2[k].dtype == want.dtype and host2[k].shape == want.shape, (kind, k, host2[k].shape, want.shape)
+            assert np.array(host2[k]).tobytes() == np.ascontiguousarray(want).tobytes(), (kind, k)
