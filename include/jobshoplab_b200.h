@@ -182,7 +182,9 @@ typedef struct jsl_step_record {
     uint8_t terminated;  /* env.py:446 */
     uint8_t truncated;   /* env.py:447-450 */
     uint8_t status;      /* JSL_ST_* */
-    uint8_t reserved0;
+    uint8_t ended;       /* JSL_STEP_AUTO_RESET: 0, or the JSL_ST_* (>= JSL_ST_DONE) the episode ended with in this call --
+                            then reward / terminated / truncated / makespan describe that finished step and time / status /
+                            cand (and the observation) the first state of the fresh episode.  Always 0 without the flag. */
     int32_t reserved1;
 } jsl_step_record;
 
@@ -208,9 +210,16 @@ typedef struct jsl_step_out {
     int16_t* cand;       /* [B][4]           next possible_transitions[0]: kind(0 m/1 t), comp, job, n_remaining */
     jsl_step_record* record; /* [B]          all of the above scalars in one record per env (preferred: when set, the
                                              six scalar arrays and cand are ignored) */
-    uint32_t flags;      /* reserved, must be 0 */
+    uint32_t flags;      /* JSL_STEP_* bits for jsl_step (other bits: reserved, must be 0; jsl_reset ignores them) */
     uint32_t reserved;
 } jsl_step_out;
+
+/* jsl_step_out.flags: reset every env whose episode ends in this step -- terminated, truncated, or dead with an escaped
+ * exception (status >= JSL_ST_STEP_FAILED) -- inside the same launch, as a vector env with auto-reset does (what the
+ * reference would do with env.reset() right after the final env.step, env.py:491).  No host round trip, no second
+ * launch.  The operation tables in force are the ones the batch holds at that moment (no per-reset jsl_batch_randomize:
+ * callers that redraw instances at every reset keep resetting explicitly). */
+#define JSL_STEP_AUTO_RESET 1u
 
 /* Device output pointers of one jsl_rollout; any may be NULL. */
 typedef struct jsl_rollout_out {

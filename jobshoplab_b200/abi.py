@@ -70,7 +70,8 @@ class StepOut(C.Structure):
                 ("reserved", C.c_uint32)]
 
 
-STEP_RECORD_BYTES = 32  # jsl_step_record: f64 reward | i32 time | i32 makespan | i16 cand[4] | u8 terminated, truncated, status
+STEP_RECORD_BYTES = 32  # jsl_step_record: f64 reward | i32 time | i32 makespan | i16 cand[4] | u8 terminated, truncated, status, ended
+STEP_AUTO_RESET = 1     # jsl_step_out.flags: JSL_STEP_AUTO_RESET
 
 
 class StateField(C.Structure):

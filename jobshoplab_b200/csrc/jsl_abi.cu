@@ -622,6 +622,7 @@ int jsl_reset(jsl_batch_t* b, const uint8_t* reset_mask, jsl_step_out out, void*
 
 int jsl_step(jsl_batch_t* b, const uint8_t* actions, jsl_step_out out, void* stream) {
     if (!b || !actions) return JSL_E_INVALID;
+    if (out.flags & ~JSL_STEP_AUTO_RESET) { set_err("jsl_step: reserved bits set in jsl_step_out.flags"); return JSL_E_INVALID; }
     CK(cudaSetDevice(b->device));
     LaunchCfg lc = {(int)((b->bd.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA), WARPS_PER_CTA * b->smem_per_warp,
                     (cudaStream_t)stream};

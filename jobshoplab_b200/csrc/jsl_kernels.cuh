@@ -166,28 +166,35 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const BatchDev& bd, uint32_t en
 
 // per-env scalars of a step: one 32-byte jsl_step_record (two 16-byte stores) or, for callers that did not ask for
 // it, the separate arrays
+// `fin` < 0: a plain step.  Otherwise the env ended in this call and was reset in the same launch (JSL_STEP_AUTO_RESET):
+// fin = terminated | truncated << 8 | status << 16 of the finished step, fin_mk its makespan; they are reported together
+// with the time, status and candidate of the fresh episode.
 template <int JW, bool ST, int CL>
 __device__ __forceinline__ void write_scalars(const EnvS<JW, ST, CL>& s, const jsl_step_out& out, uint32_t env,
-                                              double reward, int status, int cd0, int cd1, int cd2, int cd3) {
+                                              double reward, int status, int cd0, int cd1, int cd2, int cd3,
+                                              int fin = -1, int fin_mk = -1) {
     if (JSL_LANE != 0) return;
+    const int mk = fin >= 0 ? fin_mk : (s.terminated ? s.time : -1);
+    const uint32_t term = fin >= 0 ? (uint32_t)(fin & 0xff) : (uint32_t)s.terminated;
+    const uint32_t trunc = fin >= 0 ? (uint32_t)((fin >> 8) & 0xff) : (uint32_t)s.truncated;
     if (out.record) {
         int4 a, b;
         a.x = __double2loint(reward); a.y = __double2hiint(reward);
-        a.z = s.time; a.w = s.terminated ? s.time : -1;
+        a.z = s.time; a.w = mk;
         b.x = (int)(((uint32_t)cd0 & 0xffffu) | ((uint32_t)cd1 << 16));
         b.y = (int)(((uint32_t)cd2 & 0xffffu) | ((uint32_t)cd3 << 16));
-        b.z = (int)((uint32_t)s.terminated | ((uint32_t)s.truncated << 8) | ((uint32_t)status << 16));
+        b.z = (int)(term | (trunc << 8) | ((uint32_t)status << 16) | (fin >= 0 ? ((uint32_t)(fin >> 16) & 0xffu) << 24 : 0u));
         b.w = 0;
         int4* q = (int4*)(out.record + env);
         q[0] = a; q[1] = b;
         return;
     }
     if (out.reward) out.reward[env] = reward;
-    if (out.terminated) out.terminated[env] = s.terminated;
-    if (out.truncated) out.truncated[env] = s.truncated;
+    if (out.terminated) out.terminated[env] = (uint8_t)term;
+    if (out.truncated) out.truncated[env] = (uint8_t)trunc;
     if (out.status) out.status[env] = (uint8_t)status;
     if (out.time) out.time[env] = s.time;
-    if (out.makespan) out.makespan[env] = s.terminated ? s.time : -1;
+    if (out.makespan) out.makespan[env] = mk;
     if (out.cand) {
         int16_t* q = out.cand + (size_t)env * 4;
         q[0] = (int16_t)cd0; q[1] = (int16_t)cd1; q[2] = (int16_t)cd2; q[3] = (int16_t)cd3;
@@ -196,7 +203,7 @@ __device__ __forceinline__ void write_scalars(const EnvS<JW, ST, CL>& s, const j
 
 template <int JW, bool ST, int CL>
 __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c, const jsl_step_out& out, uint32_t env,
-                                               double reward, int obs_bytes) {
+                                               double reward, int obs_bytes, int fin = -1, int fin_mk = -1) {
     const int remaining = s.n_possible - s.skip;
     // the candidate the agent sees next: needed by the observation (current_transition) and by the record
     Trans cand;
@@ -214,7 +221,7 @@ __device__ __forceinline__ void write_step_out(const EnvS<JW, ST, CL>& s, Ctx& c
     if (c.raise && status <= JSL_ST_STEP_FAILED) status = c.raise;  // observation factory raised
     const bool show = remaining > 0 && status <= JSL_ST_TRUNCATED;
     write_scalars(s, out, env, reward, status, show ? cand.kind : -1, show ? cand.comp : -1, show ? cand.job : -1,
-                  show ? (remaining > 32767 ? 32767 : remaining) : 0);
+                  show ? (remaining > 32767 ? 32767 : remaining) : 0, fin, fin_mk);
 }
 
 template <int JW, bool ST, int CL>
@@ -238,7 +245,11 @@ k_reset(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ mask, j
     if (bd.outs) copy_in(bd.outs + (size_t)env * (uint32_t)bd.outs_stride, outs_sm, bd.outs_stride);
 }
 
-template <int JW, bool ST, int CL>
+// AUTO (jsl_step_out.flags & JSL_STEP_AUTO_RESET): an env whose episode ends in this step -- terminated, truncated or
+// dead with an escaped exception -- is reset in the same launch, the way a vector env auto-resets: reward, flags and
+// makespan of the finished step, observation / time / status / candidate of the fresh episode.  A separate
+// instantiation: the plain kernel's code is what it is without the flag.
+template <int JW, bool ST, int CL, bool AUTO = false>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, JSL_STEP_MIN_CTAS)
 k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions, jsl_step_out out, int obs_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -277,8 +288,14 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
                          : "=r"(done) : "r"(bar) : "memory");
     }
     __syncwarp();
-    double r = run_env_op(s, c, action);
+    double r = 0.0;
+    int op = action, fin = -1, fin_mk = -1;
+#pragma unroll 1
+    for (;;) {  // (one call site of the engine: the second pass exists only in the AUTO instantiation)
+    const double r_op = run_env_op(s, c, op);
     __syncwarp();
+    if (AUTO && op == OP_RESET) break;
+    r = r_op;
     if (s.status >= JSL_ST_STEP_FAILED) {
         // success=False / an escaping exception: the reference keeps the OLD state (state.py:202-210);
         // re-read the HBM image and carry over only the bookkeeping scalars.
@@ -296,7 +313,13 @@ k_step(const __grid_constant__ BatchDev bd, const uint8_t* __restrict__ actions,
         }
         __syncwarp();
     }
-    write_step_out(s, c, out, env, r, obs_bytes);
+    if (!AUTO || !(s.terminated || s.truncated || s.status >= JSL_ST_STEP_FAILED)) break;
+    fin = (int)s.terminated | ((int)s.truncated << 8) | (s.status << 16);
+    fin_mk = s.terminated ? s.time : -1;
+    op = OP_RESET; c.raise = 0;
+    __syncwarp();
+    }
+    write_step_out(s, c, out, env, r, obs_bytes, fin, fin_mk);
     // generic-proxy writes of all lanes -> visible to the async proxy, then one bulk store of the image; the slot must
     // stay allocated until the engine has read it
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -474,9 +497,9 @@ cudaError_t launch_reset(const BatchDev& bd, const LaunchCfg& lc, const uint8_t*
     k_reset<JW, ST, CL><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, mask, out, obs_bytes);
     return cudaGetLastError();
 }
-template <int JW, bool ST, int CL>
-cudaError_t launch_step(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* actions, jsl_step_out out, int obs_bytes) {
-    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_step<JW, ST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
+template <int JW, bool ST, int CL, bool AUTO>
+cudaError_t launch_step_impl(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* actions, jsl_step_out out, int obs_bytes) {
+    if (lc.smem > 48 * 1024) cudaFuncSetAttribute(k_step<JW, ST, CL, AUTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, lc.smem);
 #ifdef JSL_STEP_PERSISTENT
     {
         static int sms = 0;
@@ -498,11 +521,16 @@ cudaError_t launch_step(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* 
     static bool carved = false;  // per instantiation: room for JSL_STEP_MIN_CTAS resident CTAs' slots, the rest stays L1
     if (!carved) {
         int pct = (int)(((long long)lc.smem + 1024) * JSL_STEP_MIN_CTAS * 100 / (228 * 1024)) + 1;
-        cudaFuncSetAttribute(k_step<JW, ST, CL>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+        cudaFuncSetAttribute(k_step<JW, ST, CL, AUTO>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
         carved = true;
     }
-    k_step<JW, ST, CL><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, actions, out, obs_bytes);
+    k_step<JW, ST, CL, AUTO><<<lc.grid, WARPS_PER_CTA * 32, lc.smem, lc.stream>>>(bd, actions, out, obs_bytes);
     return cudaGetLastError();
+}
+template <int JW, bool ST, int CL>
+cudaError_t launch_step(const BatchDev& bd, const LaunchCfg& lc, const uint8_t* actions, jsl_step_out out, int obs_bytes) {
+    return (out.flags & JSL_STEP_AUTO_RESET) ? launch_step_impl<JW, ST, CL, true>(bd, lc, actions, out, obs_bytes)
+                                             : launch_step_impl<JW, ST, CL, false>(bd, lc, actions, out, obs_bytes);
 }
 template <int JW, bool ST, int CL>
 cudaError_t launch_rollout(const BatchDev& bd, const LaunchCfg& lc, int policy, const uint8_t* tape, int64_t tape_stride,

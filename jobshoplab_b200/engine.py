@@ -116,6 +116,7 @@ class StepResult:
     time: "object"         # i32 [B]
     makespan: "object"     # i32 [B] (-1 unless terminated)
     cand: "object"         # i16 [B, 4]: kind, component, job, n_remaining of possible_transitions[0]
+    ended: "object" = None  # u8 [B]: step(auto_reset=True): 0, or the JSL_ST_* the episode that was reset ended with
 
 
 @dataclass
@@ -175,7 +176,7 @@ class Batch:
             reward=rec[:, 0:8].view(torch.float64)[:, 0],
             terminated=rec[:, 24], truncated=rec[:, 25], status=rec[:, 26],
             time=i32[:, 0], makespan=i32[:, 1],
-            cand=rec[:, 16:24].view(torch.int16),
+            cand=rec[:, 16:24].view(torch.int16), ended=rec[:, 27],
         )
         self.rout = RolloutResult(
             makespan=torch.zeros(self.B, dtype=torch.int32, device=dev),
@@ -186,6 +187,8 @@ class Batch:
         )
         self._step_out = abi.StepOut(self.out.obs.data_ptr() if self.shape.obs_bytes else None, None, None, None, None,
                                      None, None, None, rec.data_ptr(), 0, 0)
+        self._step_out_auto = abi.StepOut(self._step_out.obs, None, None, None, None, None, None, None, rec.data_ptr(),
+                                          abi.STEP_AUTO_RESET, 0)
         r = self.rout
         self._roll_out = abi.RolloutOut(r.makespan.data_ptr(), r.n_steps.data_ptr(), r.ret.data_ptr(),
                                         r.status.data_ptr(), r.no_op_count.data_ptr())
@@ -318,9 +321,13 @@ class Batch:
         self._check(self.L.jsl_reset(self.h, ptr, self._step_out, self._stream()))
         return self.out
 
-    def step(self, actions) -> StepResult:
+    def step(self, actions, auto_reset: bool = False) -> StepResult:
+        """One env.step per env.  auto_reset (JSL_STEP_AUTO_RESET): envs whose episode ends in this step are reset in
+        the same launch; `ended` tells which (0, or the status the episode ended with), reward / terminated /
+        truncated / makespan are the finished step's, observation / time / status / cand the fresh episode's."""
         assert actions.dtype == self.torch.uint8 and actions.is_cuda and actions.numel() == self.B
-        self._check(self.L.jsl_step(self.h, actions.data_ptr(), self._step_out, self._stream()))
+        self._check(self.L.jsl_step(self.h, actions.data_ptr(), self._step_out_auto if auto_reset else self._step_out,
+                                    self._stream()))
         return self.out
 
     def rollout(self, policy, tape=None, max_steps: int = 1 << 30, reset_first=False, writeback=True) -> RolloutResult:

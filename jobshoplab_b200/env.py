@@ -152,9 +152,14 @@ class BatchedJobShopLabEnv:
     def step(self, actions):
         """actions: uint8 CUDA tensor [B].  Returns (obs dict of views, reward, terminated, truncated, out).
         With auto_reset, every env that ended -- terminated, truncated, or dead with an escaped exception
-        (status >= JSL_ST_STEP_FAILED, reported in out.status) -- is reset at once."""
-        out = self.batch.step(actions)
-        if self.auto_reset:
+        (status >= JSL_ST_STEP_FAILED) -- is reset at once: reward / terminated / truncated / makespan are the finished
+        step's, observation / time / status / candidate the fresh episode's (out.ended: the status the episode ended
+        with, when the reset happened inside the kernel)."""
+        # auto-reset is fused into the step kernel (JSL_STEP_AUTO_RESET: no host round trip, no second launch) unless
+        # the instances are redrawn at every reset, which needs jsl_batch_randomize between the step and the reset
+        fused = self.auto_reset and not self.randomize
+        out = self.batch.step(actions, auto_reset=fused)
+        if self.auto_reset and not fused:
             done = (out.terminated | out.truncated | (out.status >= abi.ST_STEP_FAILED).to(out.terminated.dtype)).contiguous()
             if bool(done.any()):
                 final = self.batch.record.clone()

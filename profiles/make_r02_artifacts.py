@@ -92,7 +92,7 @@ def full_captures():
 
 def sass_histograms():
     obj = ROOT / "jobshoplab_b200" / "csrc" / "libjsl_b200.so"
-    want = {"k_step_1_0_2": "_ZN3jsl6k_stepILi1ELb0ELi2EEEvNS_8BatchDevEPKh12jsl_step_outi",
+    want = {"k_step_1_0_2": "_ZN3jsl6k_stepILi1ELb0ELi2ELb0EEEvNS_8BatchDevEPKh12jsl_step_outi",
             "k_rollout_1_0_2": "_ZN3jsl9k_rolloutILi1ELb0ELi2EEEvNS_8BatchDevEiPKhlii15jsl_rollout_out",
             "k_rollout_1_0_3": "_ZN3jsl9k_rolloutILi1ELb0ELi3EEEvNS_8BatchDevEiPKhlii15jsl_rollout_out",
             "k_rollout_1_1_4": "_ZN3jsl9k_rolloutILi1ELb1ELi4EEEvNS_8BatchDevEiPKhlii15jsl_rollout_out"}

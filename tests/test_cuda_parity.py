@@ -330,3 +330,50 @@ def test_packed_variant_upload_equals_int32_upload():
     with pytest.raises(InvalidValue):
         eng.Batch.pack_variants(om, od * 1000)
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("group,name", [("classic", "ft06/random0"), ("buffers", "la01-t/fifo1/random0"),
+                                        ("features", "full_feature_3x3_instance/random0"), ("truncation", "ft06/trunc0/random0"),
+                                        ("transport", "ft10-t/random0")])
+def test_fused_auto_reset_equals_step_then_reset(group, name):
+    """JSL_STEP_AUTO_RESET (the reset of a finished env inside the step launch) against the same thing done with two
+    launches and a host decision: step, look at the flags, jsl_reset with a mask, keep reward / flags / makespan of
+    the finished step.  Records, `ended`, observations and final states, over several episodes per env -- including
+    envs that die with an escaped exception (capacity-1 buffers) and truncated ones."""
+    eng = _engine()
+    sc = G.Scenario(group, name)
+    B = 48
+    a, b = eng.Batch(sc.lowered, B, seed=3, **sc.cfg), eng.Batch(sc.lowered, B, seed=3, **sc.cfg)
+    if not sc.lowered.is_deterministic:
+        seeds = torch.from_numpy(np.tile(sc.start_seeds, (B, 1)).astype(np.int32)).cuda()
+        a.set_start_seeds(seeds); b.set_start_seeds(seeds)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(11)
+    n_ended = 0
+    kinds = set()
+    for i in range(400):
+        acts = torch.from_numpy((rng.random(B) < 0.7).astype(np.uint8)).cuda()
+        fused = a.step(acts, auto_reset=True)
+        out = b.step(acts)
+        done = (out.terminated | out.truncated | (out.status >= abi.ST_STEP_FAILED).to(torch.uint8)).contiguous()
+        want_ended = torch.where(done.bool(), out.status, torch.zeros_like(out.status))
+        if bool(done.any()):
+            final = b.record.clone()
+            b.reset(done)
+            rec = b.record
+            rec[:, 0:8] = final[:, 0:8]; rec[:, 12:16] = final[:, 12:16]; rec[:, 24:26] = final[:, 24:26]
+        n_ended += int(done.sum())
+        kinds |= set(want_ended[want_ended > 0].cpu().tolist())
+        assert torch.equal(fused.ended, want_ended), (i, fused.ended.cpu().tolist(), want_ended.cpu().tolist())
+        assert torch.equal(a.record[:, :27], b.record[:, :27]), (i, "record")
+        assert torch.equal(a.out.obs, b.out.obs), (i, "obs")
+    assert n_ended >= B, n_ended  # every env finished at least one episode on average
+    for e in (0, B // 2, B - 1):
+        assert np.array_equal(a.get_state(e), b.get_state(e)), e
+    # without the flag the byte stays 0, and unknown flag bits are refused
+    assert int(b.out.ended.max()) == 0
+    bad = abi.StepOut(a._step_out.obs, None, None, None, None, None, None, None, a.record.data_ptr(), 2, 0)
+    assert a.L.jsl_step(a.h, acts.data_ptr(), bad, a._stream()) != 0
+    a.close(); b.close()
+    print(group, name, "episodes ended:", n_ended, "with statuses", sorted(kinds))

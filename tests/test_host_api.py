@@ -68,6 +68,12 @@ def test_abi_library_exports_every_declared_symbol():
         for sym in declared:
             getattr(lib, sym)
         assert lib.jsl_abi_version() == abi.ABI_VERSION == 2
+    # constants the Python mirror restates
+    defines = dict(re.findall(r"#define\s+(JSL_[A-Z_0-9]+)\s+(\d+)u?\b", header))
+    assert int(defines["JSL_STEP_AUTO_RESET"]) == abi.STEP_AUTO_RESET
+    assert int(defines["JSL_OBS_STATE"]) == abi.OBS_STATE
+    import ctypes as C
+    assert C.sizeof(abi.StepOut) == 9 * 8 + 8 and abi.STEP_RECORD_BYTES == 32
 
 
 def test_no_cpu_fallback():
