@@ -121,3 +121,36 @@ def test_engine_source_wide_instances():
             fuzz_engine.run_one(sub, max_steps=600, simple=(3, None, 4)[i % 3], jrange=((33, 64), (65, 101))[(i // 3) % 2])
         except AssertionError as ex:
             raise AssertionError(f"wide instance {i}: {str(ex)[:2000]}") from ex
+
+
+def test_reset_of_a_used_env_equals_a_fresh_one():
+    """What JSL_STEP_AUTO_RESET relies on: the engine's reset (env_init + the dummy step) does not depend on what the
+    env's slot held before -- after a finished, a dead or an interrupted episode the state, observation and candidate
+    equal those of a freshly created env.  Engine source on the CPU, every specialisation level incl. stochastic."""
+    from hostsim.hostsim_py import HostSimEnv
+
+    cases = [("classic", "ft06/random0"), ("transport", "ft10-t/random0"), ("buffers", "la01-t/fifo1/random0"),
+             ("buffers", "la01-t/lifo2/noearly/random0"), ("features", "full_feature_3x3_instance/random0"),
+             ("truncation", "ft06/trunc0/random0")]
+    rng = np.random.default_rng(9)
+    for group, name in cases:
+        sc = G.Scenario(group, name)
+
+        def make():
+            e = HostSimEnv(sc.lowered, **sc.cfg)
+            if not sc.lowered.is_deterministic:
+                e.set_start_seeds(sc.start_seeds)
+            return e
+
+        fresh = make(); fresh.reset()
+        want = (fresh.digest().tobytes(), fresh.obs())
+        used = make(); used.reset()
+        for stop_after in (7, 10**9, 23):  # interrupted, run to its end (or death), interrupted again
+            n = 0
+            while n < stop_after:
+                st = used.step(int(rng.random() < 0.7))
+                n += 1
+                if st != 0:
+                    break
+            used.reset()
+            assert (used.digest().tobytes(), used.obs()) == want, (group, name, stop_after)
