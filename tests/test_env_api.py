@@ -227,3 +227,36 @@ def test_gym_surface_of_the_single_env():
         env.reset()
         assert env._batch is b0  # same instance: the device batch is reused, reset is one kernel
     env.close()
+
+
+@pytest.mark.gpu
+def test_host_read_back_paths():
+    """Batch.fetch_host (one env: single copy for a one-env batch, two otherwise) and Batch.fetch_host_all (every env,
+    one copy) return the bytes the device tensors hold; host_observation builds the reference's dict from them."""
+    import torch
+
+    from jobshoplab_b200 import engine
+    from jobshoplab_b200.middleware import host_observation
+
+    sc = G.Scenario("transport", "ft10-t/random0")
+    for B in (1, 5):
+        b = engine.Batch(sc.lowered, B, **sc.cfg)
+        b.reset()
+        rng = np.random.default_rng(B)
+        for i in range(12):
+            b.step(torch.from_numpy(rng.integers(0, 2, B).astype(np.uint8)).cuda())
+        rec_dev, obs_dev = b.record.cpu().numpy(), b.out.obs.cpu().numpy()
+        rec_all, obs_all = b.fetch_host_all()
+        assert np.array_equal(rec_all, rec_dev) and np.array_equal(obs_all, obs_dev)
+        for idx in range(B):
+            rec, obs = b.fetch_host(idx)
+            assert np.array_equal(rec, rec_dev[idx]) and np.array_equal(obs, obs_dev[idx]), (B, idx)
+            d = host_observation(b, idx)
+            views = b.unpack_obs(b.out.obs)
+            assert d["job_progression"] == tuple(int(x) for x in views["job_progression"][idx].cpu())
+            assert d["job_executed_on_machine"] == tuple(tuple(bool(x) for x in row) for row in views["job_executed_on_machine"][idx].cpu())
+            assert np.array_equal(d["current_transition"], views["current_transition"][idx].cpu().numpy())
+        batched = b.unpack_obs_host(obs_all)
+        for k, v in b.unpack_obs(b.out.obs).items():
+            assert np.array_equal(np.asarray(batched[k]), v.cpu().numpy()), k
+        b.close()
